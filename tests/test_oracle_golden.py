@@ -25,7 +25,7 @@ def test_forward_loss_and_grads_match_reference(case):
     assert set(G) == set(grads)
     errs = grads_rel_err(grads, G)
     worst = max(errs, key=errs.get)
-    assert errs[worst] < 2e-4, (worst, errs[worst])
+    assert errs[worst] < 5e-4, (worst, errs[worst])
 
 
 def test_preprocess_matches_reference_semantics():
