@@ -45,7 +45,8 @@ def test_init_params_names_match_reference_state_dict():
 
 
 def test_noam_and_adam_reference():
-    assert abs(O.noam_rate(1, 5120, 1.0, 4000, 1e-6) - 5120 ** -0.5 * 4000 ** -1.5) < 1e-12
+    assert O.noam_rate(1, 5120, 1.0, 4000, 1e-6) == 1e-6            # floored at min_lr (optimizer.py:30)
+    assert abs(O.noam_rate(1, 5120, 1.0, 4000, 0.0) - 5120 ** -0.5 * 4000 ** -1.5) < 1e-15
     p = torch.nn.Parameter(torch.randn(7, 5))
     opt = torch.optim.Adam([p], lr=1e-3, betas=(0.9, 0.98), eps=1e-9)
     m = torch.zeros_like(p); v = torch.zeros_like(p); q = p.detach().clone()
