@@ -1,0 +1,570 @@
+// VGG front end on CUDA cores (precision 0), channels-last [B,T,F,C] activations.
+//   conv3x3_c1_*    : first layer (C_in = 1) -- store-bound; one thread = one pixel x 4 output channels,
+//                     a warp writes 512 contiguous bytes.
+//   conv3x3_igemm   : implicit GEMM (pixels x Cout x 9*Cin), 128-pixel tiles, shared by forward and dgrad
+//                     (dgrad = same kernel on dy with flipped/transposed weights).
+//   conv3x3_wgrad   : per-tap [Cin x P] * [P x Cout] with the pixel axis split over CTAs (atomics).
+//   maxpool2x2      : floor-mode pooling and its gradient (first-max routing, optional ReLU mask).
+#include "../../include/b200asr.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200asr {
+
+// ------------------------------------------------------------------------------------------------ conv1
+// x [B,F,T] -> y [B,T,F,Co]; weights w[Co][1][3(f)][3(t)]
+__global__ void __launch_bounds__(256) conv3x3_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, float* __restrict__ y,
+                                                             int B, int F, int T, int Co, int relu) {
+  const int cqs = Co >> 2;                 // channel quads per pixel
+  const int cq = threadIdx.x % cqs;
+  const int slot = threadIdx.x / cqs;
+  const int slots = blockDim.x / cqs;
+  float wr[4][9], br[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    br[c] = bias ? bias[cq * 4 + c] : 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; t++) wr[c][t] = w[(cq * 4 + c) * 9 + t];
+  }
+  const long long P = (long long)B * T * F;
+  for (long long p = (long long)blockIdx.x * slots + slot; p < P; p += (long long)gridDim.x * slots) {
+    const int f = (int)(p % F);
+    const long long bt = p / F;
+    const int t = (int)(bt % T), b = (int)(bt / T);
+    const float* xb = x + (size_t)b * F * T;
+    float in[9];
+#pragma unroll
+    for (int df = 0; df < 3; df++)
+#pragma unroll
+      for (int dt = 0; dt < 3; dt++) {
+        int ff = f + df - 1, tt = t + dt - 1;
+        in[df * 3 + dt] = (ff >= 0 && ff < F && tt >= 0 && tt < T) ? __ldg(xb + (size_t)ff * T + tt) : 0.f;
+      }
+    float o[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      float a = br[c];
+#pragma unroll
+      for (int k = 0; k < 9; k++) a = fmaf(in[k], wr[c][k], a);
+      o[c] = relu ? fmaxf(a, 0.f) : a;
+    }
+    *reinterpret_cast<float4*>(y + (size_t)p * Co + cq * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// dw[Co][9] += sum_p dy[p][co] * x[p + tap]; dbias[co] += sum_p dy[p][co]
+__global__ void __launch_bounds__(256) conv3x3_c1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                               float* __restrict__ dw, float* __restrict__ dbias, int B,
+                                                               int F, int T, int Co) {
+  extern __shared__ float red[];   // [slots][Co*10]
+  const int cqs = Co >> 2;
+  const int cq = threadIdx.x % cqs;
+  const int slot = threadIdx.x / cqs;
+  const int slots = blockDim.x / cqs;
+  float acc[4][10];
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+#pragma unroll
+    for (int k = 0; k < 10; k++) acc[c][k] = 0.f;
+  const long long P = (long long)B * T * F;
+  for (long long p = (long long)blockIdx.x * slots + slot; p < P; p += (long long)gridDim.x * slots) {
+    const int f = (int)(p % F);
+    const long long bt = p / F;
+    const int t = (int)(bt % T), b = (int)(bt / T);
+    const float* xb = x + (size_t)b * F * T;
+    const float4 g = *reinterpret_cast<const float4*>(dy + (size_t)p * Co + cq * 4);
+    const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int df = 0; df < 3; df++)
+#pragma unroll
+      for (int dt = 0; dt < 3; dt++) {
+        int ff = f + df - 1, tt = t + dt - 1;
+        float v = (ff >= 0 && ff < F && tt >= 0 && tt < T) ? __ldg(xb + (size_t)ff * T + tt) : 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[c][df * 3 + dt] = fmaf(gv[c], v, acc[c][df * 3 + dt]);
+      }
+#pragma unroll
+    for (int c = 0; c < 4; c++) acc[c][9] += gv[c];
+  }
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+#pragma unroll
+    for (int k = 0; k < 10; k++) red[(size_t)slot * Co * 10 + (cq * 4 + c) * 10 + k] = acc[c][k];
+  __syncthreads();
+  for (int i = threadIdx.x; i < Co * 10; i += blockDim.x) {
+    float s = 0.f;
+    for (int sl = 0; sl < slots; sl++) s += red[(size_t)sl * Co * 10 + i];
+    int co = i / 10, k = i % 10;
+    if (k < 9) atomicAdd(dw + co * 9 + k, s);
+    else atomicAdd(dbias + co, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ weight repacks
+// fwd:   wr[tap][ci][co] = w[co][ci][tap]
+// dgrad: wr[tap'][co][ci] = w[co][ci][8 - tap']   (tap' = flipped tap; rows = contraction channel)
+__global__ void conv_repack_kernel(const float* __restrict__ w, float* __restrict__ wr, int Ci, int Co, int dgrad) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int total = 9 * Ci * Co;
+  if (i >= total) return;
+  if (!dgrad) {
+    int co = i % Co, ci = (i / Co) % Ci, tap = i / (Co * Ci);
+    wr[i] = w[((size_t)co * Ci + ci) * 9 + tap];
+  } else {
+    int ci = i % Ci, co = (i / Ci) % Co, tap = i / (Co * Ci);
+    wr[i] = w[((size_t)co * Ci + ci) * 9 + (8 - tap)];
+  }
+}
+// dw[co][ci][tap] = dwr[tap][ci][co]
+__global__ void conv_unpack_wgrad_kernel(const float* __restrict__ dwr, float* __restrict__ dw, int Ci, int Co) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int total = 9 * Ci * Co;
+  if (i >= total) return;
+  int tap = i % 9, ci = (i / 9) % Ci, co = i / (9 * Ci);
+  dw[i] = dwr[((size_t)tap * Ci + ci) * Co + co];
+}
+
+// ------------------------------------------------------------------------------------------------ implicit GEMM
+constexpr int CBM = 128, CBK = 16, CLD = 132;
+
+// out[p][n] = act( sum_{tap,c} in[p + off(tap)][c] * wr[tap][c][n] + bias[n] ) (.* mask>0)
+// in: [P, Cin] pixels (b,t,f order), wr: [9][Cin][Cout]
+template <int BN>
+__global__ void __launch_bounds__(256) conv3x3_igemm_kernel(const float* __restrict__ in, const float* __restrict__ wr,
+                                                            const float* __restrict__ bias,
+                                                            const float* __restrict__ mask, float* __restrict__ out,
+                                                            int B, int T, int F, int Cin, int Cout, int relu) {
+  __shared__ __align__(16) float As[2][CBK][CLD];
+  __shared__ __align__(16) float Bs[2][CBK][BN + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const long long P = (long long)B * T * F;
+  const long long p0 = (long long)blockIdx.y * CBM;
+  const int n0 = blockIdx.x * BN;
+  // this thread's two A rows (pixels) for the loads
+  int rf[2], rt[2];
+  bool rok[2];
+  const int lrow[2] = {tid >> 2, (tid + 256) >> 2};
+  const int kq = (tid & 3) * 4;
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    long long p = p0 + lrow[i];
+    rok[i] = p < P;
+    long long pp = rok[i] ? p : 0;
+    rf[i] = (int)(pp % F);
+    rt[i] = (int)((pp / F) % T);
+  }
+  constexpr int NJ = BN / 16;
+  float acc[8][NJ];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int j = 0; j < NJ; j++) acc[i][j] = 0.f;
+
+  const int cchunks = Cin / CBK;
+  const int nk = 9 * cchunks;
+  float4 ra[2], rb[BN / 64];
+  auto gload = [&](int kt) {
+    const int tap = kt / cchunks, c0 = (kt - tap * cchunks) * CBK;
+    const int df = tap / 3 - 1, dt = tap % 3 - 1;     // tap = kf*3 + kt, as in w[Co][Ci][kf(freq)][kt(time)]
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      int tt = rt[i] + dt, ff = rf[i] + df;
+      if (rok[i] && tt >= 0 && tt < T && ff >= 0 && ff < F)
+        z = *reinterpret_cast<const float4*>(in + (size_t)(p0 + lrow[i] + (long long)dt * F + df) * Cin + c0 + kq);
+      ra[i] = z;
+    }
+    const float* wb = wr + ((size_t)tap * Cin + c0) * Cout + n0;
+#pragma unroll
+    for (int i = 0; i < BN / 64; i++) {
+      int idx = tid + i * 256;
+      int kk = idx / (BN / 4), nq = (idx % (BN / 4)) * 4;
+      rb[i] = *reinterpret_cast<const float4*>(wb + (size_t)kk * Cout + nq);
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      As[buf][kq + 0][lrow[i]] = ra[i].x; As[buf][kq + 1][lrow[i]] = ra[i].y;
+      As[buf][kq + 2][lrow[i]] = ra[i].z; As[buf][kq + 3][lrow[i]] = ra[i].w;
+    }
+#pragma unroll
+    for (int i = 0; i < BN / 64; i++) {
+      int idx = tid + i * 256;
+      int kk = idx / (BN / 4), nq = (idx % (BN / 4)) * 4;
+      *reinterpret_cast<float4*>(&Bs[buf][kk][nq]) = rb[i];
+    }
+  };
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; kt++) {
+    const int cur = kt & 1;
+    if (kt + 1 < nk) gload(kt + 1);
+#pragma unroll
+    for (int k = 0; k < CBK; k++) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 4]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[cur][k][64 + ty * 4]);
+      float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float b[NJ];
+      float4 b0 = *reinterpret_cast<const float4*>(&Bs[cur][k][tx * 4]);
+      b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+      if (NJ == 8) {
+        float4 b1 = *reinterpret_cast<const float4*>(&Bs[cur][k][(BN / 2) + tx * 4]);
+        b[NJ - 4] = b1.x; b[NJ - 3] = b1.y; b[NJ - 2] = b1.z; b[NJ - 1] = b1.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < NJ; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) sstore(cur ^ 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    long long p = p0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (p >= P) continue;
+#pragma unroll
+    for (int jg = 0; jg < NJ / 4; jg++) {
+      int col = n0 + (jg ? BN / 2 : 0) + tx * 4;
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        float t = acc[i][jg * 4 + j];
+        if (bias) t += bias[col + j];
+        if (relu) t = fmaxf(t, 0.f);
+        v[j] = t;
+      }
+      size_t off = (size_t)p * Cout + col;
+      if (mask) {
+        float4 m = *reinterpret_cast<const float4*>(mask + off);
+        v[0] = m.x > 0.f ? v[0] : 0.f; v[1] = m.y > 0.f ? v[1] : 0.f;
+        v[2] = m.z > 0.f ? v[2] : 0.f; v[3] = m.w > 0.f ? v[3] : 0.f;
+      }
+      *reinterpret_cast<float4*>(out + off) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+  }
+}
+
+// dwr[tap][ci][co] += sum_{p in chunk} x[p + off(tap)][ci] * dy[p][co]
+template <int BMC, int BNC>
+__global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                            float* __restrict__ dwr, int B, int T, int F, int Ci,
+                                                            int Co, int chunk) {
+  __shared__ __align__(16) float As[2][CBK][BMC + 4];
+  __shared__ __align__(16) float Bs[2][CBK][BNC + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int tap = blockIdx.z;
+  const int df = tap / 3 - 1, dt = tap % 3 - 1;   // tap = kf*3 + kt
+  const int tiles_n = Co / BNC;
+  const int m0 = (blockIdx.x / tiles_n) * BMC, n0 = (blockIdx.x % tiles_n) * BNC;
+  const long long P = (long long)B * T * F;
+  const long long pbeg = (long long)blockIdx.y * chunk;
+  const long long pend = min(P, pbeg + chunk);
+  constexpr int NI = BMC / 16, NJ = BNC / 16;
+  float acc[NI][NJ];
+#pragma unroll
+  for (int i = 0; i < NI; i++)
+#pragma unroll
+    for (int j = 0; j < NJ; j++) acc[i][j] = 0.f;
+  constexpr int AV = BMC / 64, BV = BNC / 64;     // float4 per thread per tile (16 rows x BMC/4 quads / 256)
+  float4 ra[AV], rb[BV];
+  auto gload = [&](long long pk) {
+#pragma unroll
+    for (int i = 0; i < AV; i++) {
+      int idx = tid + i * 256;
+      int kk = idx / (BMC / 4), mq = (idx % (BMC / 4)) * 4;
+      long long p = pk + kk;
+      float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p < pend) {
+        int f = (int)(p % F), t = (int)((p / F) % T);
+        int tt = t + dt, ff = f + df;
+        if (tt >= 0 && tt < T && ff >= 0 && ff < F)
+          z = *reinterpret_cast<const float4*>(x + (size_t)(p + (long long)dt * F + df) * Ci + m0 + mq);
+      }
+      ra[i] = z;
+    }
+#pragma unroll
+    for (int i = 0; i < BV; i++) {
+      int idx = tid + i * 256;
+      int kk = idx / (BNC / 4), nq = (idx % (BNC / 4)) * 4;
+      long long p = pk + kk;
+      rb[i] = (p < pend) ? *reinterpret_cast<const float4*>(dy + (size_t)p * Co + n0 + nq) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < AV; i++) {
+      int idx = tid + i * 256;
+      *reinterpret_cast<float4*>(&As[buf][idx / (BMC / 4)][(idx % (BMC / 4)) * 4]) = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < BV; i++) {
+      int idx = tid + i * 256;
+      *reinterpret_cast<float4*>(&Bs[buf][idx / (BNC / 4)][(idx % (BNC / 4)) * 4]) = rb[i];
+    }
+  };
+  const int nk = (int)((pend - pbeg + CBK - 1) / CBK);
+  if (nk > 0) { gload(pbeg); sstore(0); }
+  __syncthreads();
+  for (int kt = 0; kt < nk; kt++) {
+    const int cur = kt & 1;
+    if (kt + 1 < nk) gload(pbeg + (long long)(kt + 1) * CBK);
+#pragma unroll
+    for (int k = 0; k < CBK; k++) {
+      float a[NI], b[NJ];
+#pragma unroll
+      for (int g = 0; g < NI / 4; g++) {
+        float4 v = *reinterpret_cast<const float4*>(&As[cur][k][g * 64 + ty * 4]);
+        a[g * 4 + 0] = v.x; a[g * 4 + 1] = v.y; a[g * 4 + 2] = v.z; a[g * 4 + 3] = v.w;
+      }
+#pragma unroll
+      for (int g = 0; g < NJ / 4; g++) {
+        float4 v = *reinterpret_cast<const float4*>(&Bs[cur][k][g * 64 + tx * 4]);
+        b[g * 4 + 0] = v.x; b[g * 4 + 1] = v.y; b[g * 4 + 2] = v.z; b[g * 4 + 3] = v.w;
+      }
+#pragma unroll
+      for (int i = 0; i < NI; i++)
+#pragma unroll
+        for (int j = 0; j < NJ; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) sstore(cur ^ 1);
+    __syncthreads();
+  }
+  float* o = dwr + (size_t)tap * Ci * Co;
+#pragma unroll
+  for (int i = 0; i < NI; i++) {
+    int row = m0 + (i / 4) * 64 + ty * 4 + (i % 4);
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      int col = n0 + (j / 4) * 64 + tx * 4 + (j % 4);
+      atomicAdd(o + (size_t)row * Co + col, acc[i][j]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ pooling
+__global__ void maxpool2x2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int T, int F, int C) {
+  const int T2 = T / 2, F2 = F / 2, C4 = C / 4;
+  long long n = (long long)B * T2 * F2 * C4;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = (int)(i % C4) * 4;
+  long long r = i / C4;
+  int f2 = (int)(r % F2); r /= F2;
+  int t2 = (int)(r % T2);
+  int b = (int)(r / T2);
+  const float* p = x + (((size_t)b * T + 2 * t2) * F + 2 * f2) * C + c;
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 bq = *reinterpret_cast<const float4*>(p + C);
+  float4 cq = *reinterpret_cast<const float4*>(p + (size_t)F * C);
+  float4 d = *reinterpret_cast<const float4*>(p + (size_t)F * C + C);
+  float4 o;
+  o.x = fmaxf(fmaxf(a.x, bq.x), fmaxf(cq.x, d.x));
+  o.y = fmaxf(fmaxf(a.y, bq.y), fmaxf(cq.y, d.y));
+  o.z = fmaxf(fmaxf(a.z, bq.z), fmaxf(cq.z, d.z));
+  o.w = fmaxf(fmaxf(a.w, bq.w), fmaxf(cq.w, d.w));
+  *reinterpret_cast<float4*>(y + (((size_t)b * T2 + t2) * F2 + f2) * C + c) = o;
+}
+
+// one thread = one 2x2 window x 4 channels; writes all four dx positions (and zeroes are written for the odd tails
+// by the tail kernel below).  ATen scans the window freq-major (h = freq outer, w = time inner) and keeps the first max.
+__global__ void maxpool2x2_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx,
+                                      int B, int T, int F, int C, int relu_mask) {
+  const int T2 = T / 2, F2 = F / 2, C4 = C / 4;
+  long long n = (long long)B * T2 * F2 * C4;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = (int)(i % C4) * 4;
+  long long r = i / C4;
+  int f2 = (int)(r % F2); r /= F2;
+  int t2 = (int)(r % T2);
+  int b = (int)(r / T2);
+  const size_t base = (((size_t)b * T + 2 * t2) * F + 2 * f2) * C + c;
+  const size_t o_f = C, o_t = (size_t)F * C;     // +1 in freq, +1 in time
+  // scan order: (f0,t0), (f0,t1), (f1,t0), (f1,t1)
+  const size_t offs[4] = {0, o_t, o_f, o_f + o_t};
+  float4 v[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) v[k] = *reinterpret_cast<const float4*>(x + base + offs[k]);
+  const float4 g = *reinterpret_cast<const float4*>(dy + (((size_t)b * T2 + t2) * F2 + f2) * C + c);
+  float4 out[4];
+  auto route = [&](float a0, float a1, float a2, float a3, float gg, float& o0, float& o1, float& o2, float& o3) {
+    int best = 0; float m = a0;
+    if (a1 > m) { m = a1; best = 1; }
+    if (a2 > m) { m = a2; best = 2; }
+    if (a3 > m) { m = a3; best = 3; }
+    float keep = (!relu_mask || m > 0.f) ? gg : 0.f;
+    o0 = best == 0 ? keep : 0.f; o1 = best == 1 ? keep : 0.f; o2 = best == 2 ? keep : 0.f; o3 = best == 3 ? keep : 0.f;
+  };
+  route(v[0].x, v[1].x, v[2].x, v[3].x, g.x, out[0].x, out[1].x, out[2].x, out[3].x);
+  route(v[0].y, v[1].y, v[2].y, v[3].y, g.y, out[0].y, out[1].y, out[2].y, out[3].y);
+  route(v[0].z, v[1].z, v[2].z, v[3].z, g.z, out[0].z, out[1].z, out[2].z, out[3].z);
+  route(v[0].w, v[1].w, v[2].w, v[3].w, g.w, out[0].w, out[1].w, out[2].w, out[3].w);
+#pragma unroll
+  for (int k = 0; k < 4; k++) *reinterpret_cast<float4*>(dx + base + offs[k]) = out[k];
+}
+// zero the rows/cols that floor-mode pooling never reads (odd T or F)
+__global__ void maxpool2x2_bwd_tail_kernel(float* __restrict__ dx, int B, int T, int F, int C) {
+  long long n = (long long)B * T * F * C;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  long long r = i / C;
+  int f = (int)(r % F);
+  int t = (int)((r / F) % T);
+  if (t >= (T / 2) * 2 || f >= (F / 2) * 2) dx[i] = 0.f;
+}
+
+__global__ void relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx, long long n4) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 g = reinterpret_cast<const float4*>(dy)[i];
+  float4 v = reinterpret_cast<const float4*>(y)[i];
+  g.x = v.x > 0.f ? g.x : 0.f; g.y = v.y > 0.f ? g.y : 0.f; g.z = v.z > 0.f ? g.z : 0.f; g.w = v.w > 0.f ? g.w : 0.f;
+  reinterpret_cast<float4*>(dx)[i] = g;
+}
+
+// host-side launchers used by the API and (for precision 0) nothing else
+int conv3x3_simt(const float* in, const float* wr, const float* bias, const float* mask, float* out, int B, int T, int F,
+                 int Cin, int Cout, int relu, cudaStream_t st) {
+  long long P = (long long)B * T * F;
+  if (Cout % 128 == 0) {
+    dim3 grid(Cout / 128, (unsigned)ceil_div_ll(P, CBM));
+    conv3x3_igemm_kernel<128><<<grid, 256, 0, st>>>(in, wr, bias, mask, out, B, T, F, Cin, Cout, relu);
+  } else {
+    dim3 grid(Cout / 64, (unsigned)ceil_div_ll(P, CBM));
+    conv3x3_igemm_kernel<64><<<grid, 256, 0, st>>>(in, wr, bias, mask, out, B, T, F, Cin, Cout, relu);
+  }
+  return check_launch("conv3x3_igemm");
+}
+
+int conv3x3_wgrad_simt(const float* x, const float* dy, float* dwr, int B, int T, int F, int Ci, int Co, cudaStream_t st) {
+  long long P = (long long)B * T * F;
+  int bm = (Ci % 128 == 0) ? 128 : 64, bn = (Co % 128 == 0) ? 128 : 64;
+  int tiles = (Ci / bm) * (Co / bn);
+  int sms = device_sm_count();
+  long long want = ceil_div_ll(4LL * sms, 9LL * tiles);
+  long long chunk = ceil_div_ll(ceil_div_ll(P, want < 1 ? 1 : want), CBK) * CBK;
+  if (chunk < 1024) chunk = 1024;
+  dim3 grid(tiles, (unsigned)ceil_div_ll(P, chunk), 9);
+  if (bm == 128 && bn == 128) conv3x3_wgrad_kernel<128, 128><<<grid, 256, 0, st>>>(x, dy, dwr, B, T, F, Ci, Co, (int)chunk);
+  else if (bm == 64 && bn == 128) conv3x3_wgrad_kernel<64, 128><<<grid, 256, 0, st>>>(x, dy, dwr, B, T, F, Ci, Co, (int)chunk);
+  else if (bm == 128 && bn == 64) conv3x3_wgrad_kernel<128, 64><<<grid, 256, 0, st>>>(x, dy, dwr, B, T, F, Ci, Co, (int)chunk);
+  else conv3x3_wgrad_kernel<64, 64><<<grid, 256, 0, st>>>(x, dy, dwr, B, T, F, Ci, Co, (int)chunk);
+  return check_launch("conv3x3_wgrad");
+}
+
+}  // namespace b200asr
+
+using namespace b200asr;
+
+extern "C" {
+
+size_t b200asr_conv3x3_ws_bytes(int Ci, int Co) { return sizeof(float) * 9 * (size_t)Ci * Co; }
+
+int b200asr_conv3x3_c1_fwd(const float* x, const float* w, const float* bias, float* y, int B, int F, int T, int Co,
+                           int relu, b200asr_stream_t stream) {
+  B200_REQUIRE(x && w && y, B200ASR_BAD_ARG, "conv3x3_c1_fwd: null pointer");
+  B200_REQUIRE(Co % 4 == 0 && Co <= 1024 && 256 % (Co / 4) == 0, B200ASR_BAD_SHAPE, "conv3x3_c1_fwd: Co=%d unsupported", Co);
+  B200_REQUIRE(aligned16(y), B200ASR_BAD_ALIGN, "conv3x3_c1_fwd: y alignment");
+  long long P = (long long)B * T * F;
+  if (P <= 0) return B200ASR_OK;
+  int slots = 256 / (Co / 4);
+  long long blocks = ceil_div_ll(P, slots * 8LL);
+  int cap = device_sm_count() * 16;
+  conv3x3_c1_fwd_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, B, F, T, Co, relu);
+  return check_launch("conv3x3_c1_fwd");
+}
+
+int b200asr_conv3x3_c1_bwd_weight(const float* x, const float* dy, float* dw, float* dbias, int B, int F, int T, int Co,
+                                  b200asr_stream_t stream) {
+  B200_REQUIRE(x && dy && dw && dbias, B200ASR_BAD_ARG, "conv3x3_c1_bwd_weight: null pointer");
+  B200_REQUIRE(Co % 4 == 0 && 256 % (Co / 4) == 0, B200ASR_BAD_SHAPE, "conv3x3_c1_bwd_weight: Co=%d unsupported", Co);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(dw, 0, sizeof(float) * 9 * (size_t)Co, st);
+  cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)Co, st);
+  long long P = (long long)B * T * F;
+  if (P <= 0) return B200ASR_OK;
+  int slots = 256 / (Co / 4);
+  size_t smem = sizeof(float) * (size_t)slots * Co * 10;
+  B200_REQUIRE(smem <= 48 * 1024, B200ASR_BAD_SHAPE, "conv3x3_c1_bwd_weight: Co=%d too large", Co);
+  int blocks = device_sm_count() * 4;
+  conv3x3_c1_wgrad_kernel<<<blocks, 256, smem, st>>>(x, dy, dw, dbias, B, F, T, Co);
+  return check_launch("conv3x3_c1_wgrad");
+}
+
+static int conv_shape_ok(const char* who, int Ci, int Co) {
+  B200_REQUIRE(Ci % 16 == 0 && Co % 64 == 0, B200ASR_BAD_SHAPE, "%s: need Ci %% 16 == 0 and Co %% 64 == 0 (Ci=%d Co=%d)", who, Ci, Co);
+  return B200ASR_OK;
+}
+
+int b200asr_conv3x3_fwd(const float* x, const float* w, const float* bias, float* y, void* ws, int B, int T, int F,
+                        int Ci, int Co, int relu, int precision, b200asr_stream_t stream) {
+  B200_REQUIRE(x && w && y && ws, B200ASR_BAD_ARG, "conv3x3_fwd: null pointer");
+  int rc = conv_shape_ok("conv3x3_fwd", Ci, Co);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  int total = 9 * Ci * Co;
+  conv_repack_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, (float*)ws, Ci, Co, 0);
+  if (precision == B200ASR_PREC_FP32) return conv3x3_simt(x, (const float*)ws, bias, nullptr, y, B, T, F, Ci, Co, relu, st);
+  return conv3x3_tc(x, (const float*)ws, bias, nullptr, y, B, T, F, Ci, Co, relu, precision, st);
+}
+
+int b200asr_conv3x3_bwd_data(const float* dy, const float* w, const float* relu_out, float* dx, void* ws, int B, int T,
+                             int F, int Ci, int Co, int precision, b200asr_stream_t stream) {
+  B200_REQUIRE(dy && w && dx && ws, B200ASR_BAD_ARG, "conv3x3_bwd_data: null pointer");
+  int rc = conv_shape_ok("conv3x3_bwd_data", Co, Ci);   // roles swap: contraction over Co, output channels Ci
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  int total = 9 * Ci * Co;
+  conv_repack_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, (float*)ws, Ci, Co, 1);
+  if (precision == B200ASR_PREC_FP32) return conv3x3_simt(dy, (const float*)ws, nullptr, relu_out, dx, B, T, F, Co, Ci, 0, st);
+  return conv3x3_tc(dy, (const float*)ws, nullptr, relu_out, dx, B, T, F, Co, Ci, 0, precision, st);
+}
+
+int b200asr_conv3x3_bwd_weight(const float* dy, const float* x, float* dw, float* dbias, void* ws, int B, int T, int F,
+                               int Ci, int Co, int precision, b200asr_stream_t stream) {
+  B200_REQUIRE(dy && x && dw && ws, B200ASR_BAD_ARG, "conv3x3_bwd_weight: null pointer");
+  B200_REQUIRE(Ci % 64 == 0 && Co % 64 == 0, B200ASR_BAD_SHAPE, "conv3x3_bwd_weight: Ci=%d Co=%d must be multiples of 64", Ci, Co);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(ws, 0, sizeof(float) * 9 * (size_t)Ci * Co, st);
+  int rc;
+  if (precision == B200ASR_PREC_FP32) rc = conv3x3_wgrad_simt(x, dy, (float*)ws, B, T, F, Ci, Co, st);
+  else rc = conv3x3_wgrad_tc(x, dy, (float*)ws, B, T, F, Ci, Co, precision, st);
+  if (rc) return rc;
+  int total = 9 * Ci * Co;
+  conv_unpack_wgrad_kernel<<<ceil_div(total, 256), 256, 0, st>>>((const float*)ws, dw, Ci, Co);
+  rc = check_launch("conv_unpack_wgrad");
+  if (rc) return rc;
+  if (dbias) {
+    long long P = (long long)B * T * F;
+    B200_REQUIRE(P < (1LL << 31), B200ASR_BAD_SHAPE, "conv3x3_bwd_weight: too many pixels");
+    return launch_colsum(dy, dbias, (int)P, Co, 0, st);
+  }
+  return B200ASR_OK;
+}
+
+int b200asr_maxpool2x2_fwd(const float* x, float* y, int B, int T, int F, int C, b200asr_stream_t stream) {
+  B200_REQUIRE(x && y && C % 4 == 0, B200ASR_BAD_ARG, "maxpool2x2_fwd: bad arguments");
+  long long n = (long long)B * (T / 2) * (F / 2) * (C / 4);
+  if (n <= 0) return B200ASR_OK;
+  maxpool2x2_fwd_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, B, T, F, C);
+  return check_launch("maxpool2x2_fwd");
+}
+
+int b200asr_maxpool2x2_bwd(const float* dy, const float* x, float* dx, int B, int T, int F, int C, int relu_mask,
+                           b200asr_stream_t stream) {
+  B200_REQUIRE(dy && x && dx && C % 4 == 0, B200ASR_BAD_ARG, "maxpool2x2_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long n = (long long)B * (T / 2) * (F / 2) * (C / 4);
+  if (n > 0) maxpool2x2_bwd_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, st>>>(dy, x, dx, B, T, F, C, relu_mask);
+  if ((T & 1) || (F & 1)) {
+    long long tot = (long long)B * T * F * C;
+    maxpool2x2_bwd_tail_kernel<<<(unsigned)ceil_div_ll(tot, 256), 256, 0, st>>>(dx, B, T, F, C);
+  }
+  return check_launch("maxpool2x2_bwd");
+}
+
+}  // extern "C"

@@ -1,0 +1,265 @@
+// emb_cnn front end (models/asr/transformer.py:33-40): generic strided NCHW convolution (direct form),
+// BatchNorm2d with batch statistics fused with the Hardtanh clamp, and the (B,C,F,T)->(B,T,C*F) flatten.
+// This path only serves the emb_cnn configuration (BASELINE cfg3, a parity case); kernels are direct and
+// coalesced along W, not tensor-core tiled.
+#include "../../include/b200asr.h"
+#include "common.cuh"
+
+namespace b200asr {
+
+struct ConvG { int B, Ci, H, W, Co, KH, KW, SH, SW, PH, PW, OH, OW; };
+
+__global__ void conv2d_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                  float* __restrict__ y, ConvG g) {
+  long long n = (long long)g.B * g.Co * g.OH * g.OW;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int ow = (int)(i % g.OW); long long r = i / g.OW;
+  int oh = (int)(r % g.OH); r /= g.OH;
+  int co = (int)(r % g.Co); int b = (int)(r / g.Co);
+  float acc = bias ? bias[co] : 0.f;
+  for (int ci = 0; ci < g.Ci; ci++) {
+    const float* xp = x + ((size_t)b * g.Ci + ci) * g.H * g.W;
+    const float* wp = w + ((size_t)co * g.Ci + ci) * g.KH * g.KW;
+    for (int kh = 0; kh < g.KH; kh++) {
+      int ih = oh * g.SH - g.PH + kh;
+      if (ih < 0 || ih >= g.H) continue;
+      for (int kw = 0; kw < g.KW; kw++) {
+        int iw = ow * g.SW - g.PW + kw;
+        if (iw < 0 || iw >= g.W) continue;
+        acc = fmaf(xp[(size_t)ih * g.W + iw], wp[kh * g.KW + kw], acc);
+      }
+    }
+  }
+  y[i] = acc;
+}
+
+__global__ void conv2d_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, ConvG g) {
+  long long n = (long long)g.B * g.Ci * g.H * g.W;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int iw = (int)(i % g.W); long long r = i / g.W;
+  int ih = (int)(r % g.H); r /= g.H;
+  int ci = (int)(r % g.Ci); int b = (int)(r / g.Ci);
+  float acc = 0.f;
+  for (int kh = 0; kh < g.KH; kh++) {
+    int th = ih + g.PH - kh;
+    if (th < 0 || th % g.SH) continue;
+    int oh = th / g.SH;
+    if (oh >= g.OH) continue;
+    for (int kw = 0; kw < g.KW; kw++) {
+      int tw = iw + g.PW - kw;
+      if (tw < 0 || tw % g.SW) continue;
+      int ow = tw / g.SW;
+      if (ow >= g.OW) continue;
+      for (int co = 0; co < g.Co; co++)
+        acc = fmaf(dy[(((size_t)b * g.Co + co) * g.OH + oh) * g.OW + ow], w[(((size_t)co * g.Ci + ci) * g.KH + kh) * g.KW + kw], acc);
+    }
+  }
+  dx[i] = acc;
+}
+
+// one CTA per weight element (co,ci,kh,kw): reduce over (b,oh,ow)
+__global__ void __launch_bounds__(128) conv2d_bwd_weight_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                float* __restrict__ dw, ConvG g) {
+  __shared__ float red[4];
+  int i = blockIdx.x;
+  int kw = i % g.KW; int r = i / g.KW;
+  int kh = r % g.KH; r /= g.KH;
+  int ci = r % g.Ci; int co = r / g.Ci;
+  long long n = (long long)g.B * g.OH * g.OW;
+  float acc = 0.f;
+  for (long long j = threadIdx.x; j < n; j += blockDim.x) {
+    int ow = (int)(j % g.OW); long long q = j / g.OW;
+    int oh = (int)(q % g.OH); int b = (int)(q / g.OH);
+    int ih = oh * g.SH - g.PH + kh, iw = ow * g.SW - g.PW + kw;
+    if (ih < 0 || ih >= g.H || iw < 0 || iw >= g.W) continue;
+    acc = fmaf(dy[(((size_t)b * g.Co + co) * g.OH + oh) * g.OW + ow], x[(((size_t)b * g.Ci + ci) * g.H + ih) * g.W + iw], acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) dw[i] = red[0] + red[1] + red[2] + red[3];
+}
+
+// one CTA per output channel: dbias[co] = sum dy
+__global__ void __launch_bounds__(256) conv2d_bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ dbias, int B, int Co, int HW) {
+  __shared__ float red[8];
+  int co = blockIdx.x;
+  float s = 0.f;
+  for (long long j = threadIdx.x; j < (long long)B * HW; j += blockDim.x) {
+    int b = (int)(j / HW); int k = (int)(j % HW);
+    s += dy[((size_t)b * Co + co) * HW + k];
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < 8; w++) t += red[w]; dbias[co] = t; }
+}
+
+__device__ __forceinline__ float block_sum256(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; w++) t += red[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(256) bn_clamp_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float* __restrict__ y,
+                                                           float* __restrict__ mean_out, float* __restrict__ invstd_out, int B,
+                                                           int C, int HW, float eps, float lo, float hi) {
+  __shared__ float red[8];
+  const int c = blockIdx.x;
+  const long long n = (long long)B * HW;
+  float s = 0.f;
+  for (long long j = threadIdx.x; j < n; j += 256) s += x[((size_t)(j / HW) * C + c) * HW + (j % HW)];
+  const float mean = block_sum256(s, red) / (float)n;
+  float q = 0.f;
+  for (long long j = threadIdx.x; j < n; j += 256) { float d = x[((size_t)(j / HW) * C + c) * HW + (j % HW)] - mean; q += d * d; }
+  const float var = block_sum256(q, red) / (float)n;
+  const float invstd = rsqrtf(var + eps);
+  if (threadIdx.x == 0) { mean_out[c] = mean; invstd_out[c] = invstd; }
+  const float ga = gamma[c], be = beta[c];
+  for (long long j = threadIdx.x; j < n; j += 256) {
+    size_t o = ((size_t)(j / HW) * C + c) * HW + (j % HW);
+    float v = (x[o] - mean) * invstd * ga + be;
+    y[o] = fminf(fmaxf(v, lo), hi);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_clamp_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                           const float* __restrict__ y, const float* __restrict__ gamma,
+                                                           const float* __restrict__ mean_in, const float* __restrict__ invstd_in,
+                                                           float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                           int B, int C, int HW, float lo, float hi) {
+  __shared__ float red[8];
+  const int c = blockIdx.x;
+  const long long n = (long long)B * HW;
+  const float mean = mean_in[c], invstd = invstd_in[c], ga = gamma[c];
+  float s1 = 0.f, s2 = 0.f;
+  for (long long j = threadIdx.x; j < n; j += 256) {
+    size_t o = ((size_t)(j / HW) * C + c) * HW + (j % HW);
+    float yv = y[o];
+    float g = (yv > lo && yv < hi) ? dy[o] : 0.f;
+    float xh = (x[o] - mean) * invstd;
+    s1 += g; s2 += g * xh;
+  }
+  s1 = block_sum256(s1, red);
+  s2 = block_sum256(s2, red);
+  if (threadIdx.x == 0) { dbeta[c] = s1; dgamma[c] = s2; }
+  const float inv_n = 1.f / (float)n;
+  for (long long j = threadIdx.x; j < n; j += 256) {
+    size_t o = ((size_t)(j / HW) * C + c) * HW + (j % HW);
+    float yv = y[o];
+    float g = (yv > lo && yv < hi) ? dy[o] : 0.f;
+    float xh = (x[o] - mean) * invstd;
+    dx[o] = ga * invstd * (g - s1 * inv_n - xh * s2 * inv_n);
+  }
+}
+
+// y[b][t][c*F+f] = x[b][c][f][t]  (32x32 smem transpose over (cf, t))
+__global__ void flatten_bcft_kernel(const float* __restrict__ src, float* __restrict__ dst, int CF, int T, int to_btk) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int k0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  const float* s = src + (size_t)b * CF * T;
+  float* d = dst + (size_t)b * CF * T;
+  if (to_btk) {          // src [CF][T] -> dst [T][CF]
+    for (int i = threadIdx.y; i < 32; i += 8) {
+      int k = k0 + i, t = t0 + threadIdx.x;
+      tile[i][threadIdx.x] = (k < CF && t < T) ? s[(size_t)k * T + t] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+      int t = t0 + i, k = k0 + threadIdx.x;
+      if (t < T && k < CF) d[(size_t)t * CF + k] = tile[threadIdx.x][i];
+    }
+  } else {               // src [T][CF] -> dst [CF][T]
+    for (int i = threadIdx.y; i < 32; i += 8) {
+      int t = t0 + i, k = k0 + threadIdx.x;
+      tile[i][threadIdx.x] = (t < T && k < CF) ? s[(size_t)t * CF + k] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+      int k = k0 + i, t = t0 + threadIdx.x;
+      if (k < CF && t < T) d[(size_t)k * T + t] = tile[threadIdx.x][i];
+    }
+  }
+}
+
+static int make_geom(ConvG& g, int B, int Ci, int H, int W, int Co, int KH, int KW, int SH, int SW, int PH, int PW) {
+  B200_REQUIRE(B > 0 && Ci > 0 && Co > 0 && KH > 0 && KW > 0 && SH > 0 && SW > 0 && PH >= 0 && PW >= 0, B200ASR_BAD_SHAPE, "conv2d: bad geometry");
+  g = ConvG{B, Ci, H, W, Co, KH, KW, SH, SW, PH, PW, (H + 2 * PH - KH) / SH + 1, (W + 2 * PW - KW) / SW + 1};
+  B200_REQUIRE(g.OH > 0 && g.OW > 0, B200ASR_BAD_SHAPE, "conv2d: empty output (H=%d W=%d)", H, W);
+  return B200ASR_OK;
+}
+
+}  // namespace b200asr
+
+using namespace b200asr;
+
+extern "C" {
+
+int b200asr_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, int B, int Ci, int H, int W, int Co,
+                       int KH, int KW, int SH, int SW, int PH, int PW, b200asr_stream_t stream) {
+  B200_REQUIRE(x && w && y, B200ASR_BAD_ARG, "conv2d_fwd: null pointer");
+  ConvG g; int rc = make_geom(g, B, Ci, H, W, Co, KH, KW, SH, SW, PH, PW); if (rc) return rc;
+  long long n = (long long)B * Co * g.OH * g.OW;
+  conv2d_fwd_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, g);
+  return check_launch("conv2d_fwd");
+}
+
+int b200asr_conv2d_bwd_data(const float* dy, const float* w, float* dx, int B, int Ci, int H, int W, int Co, int KH, int KW,
+                            int SH, int SW, int PH, int PW, b200asr_stream_t stream) {
+  B200_REQUIRE(dy && w && dx, B200ASR_BAD_ARG, "conv2d_bwd_data: null pointer");
+  ConvG g; int rc = make_geom(g, B, Ci, H, W, Co, KH, KW, SH, SW, PH, PW); if (rc) return rc;
+  long long n = (long long)B * Ci * H * W;
+  conv2d_bwd_data_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, (cudaStream_t)stream>>>(dy, w, dx, g);
+  return check_launch("conv2d_bwd_data");
+}
+
+int b200asr_conv2d_bwd_weight(const float* dy, const float* x, float* dw, float* dbias, int B, int Ci, int H, int W, int Co,
+                              int KH, int KW, int SH, int SW, int PH, int PW, b200asr_stream_t stream) {
+  B200_REQUIRE(dy && x && dw, B200ASR_BAD_ARG, "conv2d_bwd_weight: null pointer");
+  ConvG g; int rc = make_geom(g, B, Ci, H, W, Co, KH, KW, SH, SW, PH, PW); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  conv2d_bwd_weight_kernel<<<Co * Ci * KH * KW, 128, 0, st>>>(dy, x, dw, g);
+  rc = check_launch("conv2d_bwd_weight"); if (rc) return rc;
+  if (dbias) { conv2d_bias_grad_kernel<<<Co, 256, 0, st>>>(dy, dbias, B, Co, g.OH * g.OW); return check_launch("conv2d_bias_grad"); }
+  return B200ASR_OK;
+}
+
+int b200asr_bn_clamp_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* invstd, int B,
+                         int C, int HW, float eps, float lo, float hi, b200asr_stream_t stream) {
+  B200_REQUIRE(x && gamma && beta && y && mean && invstd && B > 0 && C > 0 && HW > 0, B200ASR_BAD_ARG, "bn_clamp_fwd: bad arguments");
+  bn_clamp_fwd_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, y, mean, invstd, B, C, HW, eps, lo, hi);
+  return check_launch("bn_clamp_fwd");
+}
+
+int b200asr_bn_clamp_bwd(const float* dy, const float* x, const float* y, const float* gamma, const float* mean,
+                         const float* invstd, float* dx, float* dgamma, float* dbeta, int B, int C, int HW, float lo, float hi,
+                         b200asr_stream_t stream) {
+  B200_REQUIRE(dy && x && y && gamma && mean && invstd && dx && dgamma && dbeta, B200ASR_BAD_ARG, "bn_clamp_bwd: null pointer");
+  bn_clamp_bwd_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(dy, x, y, gamma, mean, invstd, dx, dgamma, dbeta, B, C, HW, lo, hi);
+  return check_launch("bn_clamp_bwd");
+}
+
+int b200asr_flatten_bcft_fwd(const float* x, float* y, int B, int C, int F, int T, b200asr_stream_t stream) {
+  B200_REQUIRE(x && y && B > 0, B200ASR_BAD_ARG, "flatten_bcft_fwd: bad arguments");
+  dim3 grid(ceil_div(T, 32), ceil_div(C * F, 32), B);
+  flatten_bcft_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, y, C * F, T, 1);
+  return check_launch("flatten_bcft_fwd");
+}
+
+int b200asr_flatten_bcft_bwd(const float* dy, float* dx, int B, int C, int F, int T, b200asr_stream_t stream) {
+  B200_REQUIRE(dy && dx && B > 0, B200ASR_BAD_ARG, "flatten_bcft_bwd: bad arguments");
+  dim3 grid(ceil_div(T, 32), ceil_div(C * F, 32), B);
+  flatten_bcft_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(dy, dx, C * F, T, 0);
+  return check_launch("flatten_bcft_bwd");
+}
+
+}  // extern "C"

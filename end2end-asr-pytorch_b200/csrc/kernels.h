@@ -1,0 +1,25 @@
+// Internal launcher declarations shared between translation units of libb200asr.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace b200asr {
+
+// fp32 CUDA-core GEMM: C[m,n] = sum_k A(m,k) B(k,n); *_kmaj: contraction index contiguous.
+int gemm_simt(const float* A, bool a_kmaj, int lda, const float* B, bool b_kmaj, int ldb, float* C, int ldc, int M,
+              int N, int K, const float* bias, int relu, const float* relu_mask, int accumulate, bool allow_split,
+              cudaStream_t st);
+int launch_colsum(const float* X, float* out, int M, int N, int accumulate, cudaStream_t st);
+
+// tcgen05 GEMM (tc_gemm.cu).  nsplit = 1 (TF32) or 3 (3xTF32).  Returns B200ASR_BAD_SHAPE when the
+// shape/alignment cannot be expressed as TMA tiles (callers turn that into an error, never a fallback).
+int gemm_tc(const float* A, bool a_kmaj, int lda, const float* B, bool b_kmaj, int ldb, float* C, int ldc, int M,
+            int N, int K, const float* bias, int relu, const float* relu_mask, int accumulate, int nsplit,
+            cudaStream_t st);
+
+// tcgen05 implicit-GEMM convolution (tc_conv.cu); wr layouts as produced by conv_repack_kernel.
+int conv3x3_tc(const float* in, const float* wr, const float* bias, const float* mask, float* out, int B, int T, int F,
+               int Cin, int Cout, int relu, int precision, cudaStream_t st);
+int conv3x3_wgrad_tc(const float* x, const float* dy, float* dwr, int B, int T, int F, int Ci, int Co, int precision,
+                     cudaStream_t st);
+
+}  // namespace b200asr

@@ -1,0 +1,47 @@
+// Dense-layer entry points (forward, data gradient, weight gradient) -- see include/b200asr.h.
+#include "../../include/b200asr.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace b200asr;
+
+static int gemm_dispatch(const float* A, bool ak, int lda, const float* B, bool bk, int ldb, float* C, int ldc, int M,
+                         int N, int K, const float* bias, int relu, const float* mask, int accumulate, bool allow_split,
+                         int precision, cudaStream_t st) {
+  if (precision == B200ASR_PREC_FP32)
+    return gemm_simt(A, ak, lda, B, bk, ldb, C, ldc, M, N, K, bias, relu, mask, accumulate, allow_split, st);
+  if (precision == B200ASR_PREC_TF32 || precision == B200ASR_PREC_TF32X3)
+    return gemm_tc(A, ak, lda, B, bk, ldb, C, ldc, M, N, K, bias, relu, mask, accumulate, precision, st);
+  set_error("unknown precision %d", precision);
+  return B200ASR_BAD_ARG;
+}
+
+extern "C" {
+
+int b200asr_linear_fwd(const float* x, const float* w, const float* bias, float* y, int M, int N, int K, int relu,
+                       int precision, b200asr_stream_t stream) {
+  B200_REQUIRE(x && w && y && M >= 0 && N > 0 && K > 0, B200ASR_BAD_ARG, "linear_fwd: bad arguments");
+  return gemm_dispatch(x, true, K, w, true, K, y, N, M, N, K, bias, relu, nullptr, 0, false, precision,
+                       (cudaStream_t)stream);
+}
+
+int b200asr_linear_bwd_data(const float* dy, const float* w, const float* relu_out, float* dx, int M, int N, int K,
+                            int accumulate, int precision, b200asr_stream_t stream) {
+  B200_REQUIRE(dy && w && dx && M >= 0 && N > 0 && K > 0, B200ASR_BAD_ARG, "linear_bwd_data: bad arguments");
+  // dx[m,k] = sum_n dy[m,n] w[n,k]: contraction over n; A = dy (n contiguous), B(n,k) = w[n*K + k] (k contiguous)
+  return gemm_dispatch(dy, true, N, w, false, K, dx, K, M, K, N, nullptr, 0, relu_out, accumulate, false, precision,
+                       (cudaStream_t)stream);
+}
+
+int b200asr_linear_bwd_weight(const float* dy, const float* x, float* dw, float* dbias, int M, int N, int K,
+                              int accumulate, int precision, b200asr_stream_t stream) {
+  B200_REQUIRE(dy && x && dw && M >= 0 && N > 0 && K > 0, B200ASR_BAD_ARG, "linear_bwd_weight: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  // dw[n,k] = sum_m dy[m,n] x[m,k]: contraction over m; A(n,m) = dy[m*N + n], B(m,k) = x[m*K + k]
+  int rc = gemm_dispatch(dy, false, N, x, false, K, dw, K, N, K, M, nullptr, 0, nullptr, accumulate, true, precision, st);
+  if (rc) return rc;
+  if (dbias) return launch_colsum(dy, dbias, M, N, accumulate, st);
+  return B200ASR_OK;
+}
+
+}  // extern "C"

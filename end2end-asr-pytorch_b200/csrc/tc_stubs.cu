@@ -1,0 +1,35 @@
+// Placeholders for tcgen05 entry points that are not built yet: they fail loudly (never fall back).
+#include "../../include/b200asr.h"
+#include "attention.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200asr {
+#ifndef B200ASR_HAVE_TC_GEMM
+int gemm_tc(const float*, bool, int, const float*, bool, int, float*, int, int, int, int, const float*, int, const float*,
+            int, int, cudaStream_t) {
+  set_error("tcgen05 GEMM is not available in this build");
+  return B200ASR_BAD_ARG;
+}
+#endif
+#ifndef B200ASR_HAVE_TC_ATTN
+int sdpa_fwd_tc(const AttnP&, cudaStream_t) {
+  set_error("tcgen05 attention is not available in this build");
+  return B200ASR_BAD_ARG;
+}
+int sdpa_bwd_tc(const AttnP&, const float*, float*, float*, float*, float*, cudaStream_t) {
+  set_error("tcgen05 attention backward is not available in this build");
+  return B200ASR_BAD_ARG;
+}
+#endif
+#ifndef B200ASR_HAVE_TC_CONV
+int conv3x3_tc(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t) {
+  set_error("tcgen05 convolution is not available in this build");
+  return B200ASR_BAD_ARG;
+}
+int conv3x3_wgrad_tc(const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t) {
+  set_error("tcgen05 convolution weight gradient is not available in this build");
+  return B200ASR_BAD_ARG;
+}
+#endif
+}  // namespace b200asr

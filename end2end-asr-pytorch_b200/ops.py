@@ -1,0 +1,556 @@
+"""torch.autograd.Function wrappers over the C ABI (one per kernel group of SURVEY.md §2.3).
+
+PyTorch is used here for device memory, streams and the autograd graph only: every FLOP on the path is a
+kernel of libb200asr.so.  All functions require CUDA tensors; there is no CPU implementation.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+# ----------------------------------------------------------------------------------------------- configuration
+_PREC_NAMES = {"fp32": L.PREC_FP32, "tf32": L.PREC_TF32, "tf32x3": L.PREC_TF32X3}
+
+
+class _Config:
+    """Arithmetic mode per kernel family (include/b200asr.h `precision`)."""
+
+    def __init__(self):
+        self.linear = _PREC_NAMES[os.environ.get("B200ASR_LINEAR", "fp32")]
+        self.conv = _PREC_NAMES[os.environ.get("B200ASR_CONV", "fp32")]
+        self.attn = _PREC_NAMES[os.environ.get("B200ASR_ATTN", "fp32")]
+
+    def set(self, linear=None, conv=None, attn=None):
+        if linear is not None:
+            self.linear = _PREC_NAMES[linear] if isinstance(linear, str) else int(linear)
+        if conv is not None:
+            self.conv = _PREC_NAMES[conv] if isinstance(conv, str) else int(conv)
+        if attn is not None:
+            self.attn = _PREC_NAMES[attn] if isinstance(attn, str) else int(attn)
+
+
+config = _Config()
+
+
+class _Rng:
+    """Seed + per-call offset for the counter-based dropout generator of the kernels."""
+
+    def __init__(self):
+        self.seed = 0x5EED
+        self.offset = 0
+
+    def manual_seed(self, seed: int):
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.offset = 0
+
+    def next(self):
+        self.offset += 1
+        return self.seed, self.offset
+
+
+rng = _Rng()
+
+
+def manual_seed(seed: int):
+    rng.manual_seed(seed)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _lib():
+    return L.load()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("b200asr ops run on CUDA tensors only (no CPU path exists); got a CPU tensor")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"b200asr: expected float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------- dense layers
+def linear_fwd(x2, w, b, relu, prec):
+    M, K = x2.shape
+    N = w.shape[0]
+    y = torch.empty((M, N), device=x2.device, dtype=torch.float32)
+    L.check(_lib().b200asr_linear_fwd(L.ptr(x2), L.ptr(w), L.ptr(b), L.ptr(y), M, N, K, int(relu), prec, _stream()),
+            "linear_fwd")
+    return y
+
+
+def linear_bwd_data(dy2, w, relu_out, prec):
+    M, N = dy2.shape
+    K = w.shape[1]
+    dx = torch.empty((M, K), device=dy2.device, dtype=torch.float32)
+    L.check(_lib().b200asr_linear_bwd_data(L.ptr(dy2), L.ptr(w), L.ptr(relu_out), L.ptr(dx), M, N, K, 0, prec,
+                                           _stream()), "linear_bwd_data")
+    return dx
+
+
+def linear_bwd_weight(dy2, x2, want_bias, prec):
+    M, N = dy2.shape
+    K = x2.shape[1]
+    dw = torch.empty((N, K), device=dy2.device, dtype=torch.float32)
+    db = torch.empty((N,), device=dy2.device, dtype=torch.float32) if want_bias else None
+    L.check(_lib().b200asr_linear_bwd_weight(L.ptr(dy2), L.ptr(x2), L.ptr(dw), L.ptr(db), M, N, K, 0, prec,
+                                             _stream()), "linear_bwd_weight")
+    return dw, db
+
+
+class LinearFn(torch.autograd.Function):
+    """y = x W^T + b   (nn.Linear / Conv1d(k=1) call sites, include/b200asr.h)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        _need_cuda(x, w, b)
+        w2 = _f32c(w.reshape(w.shape[0], -1))
+        x2 = _f32c(x).reshape(-1, w2.shape[1])
+        ctx.prec = config.linear
+        y = linear_fwd(x2, w2, b, False, ctx.prec)
+        ctx.save_for_backward(x2, w2)
+        ctx.xshape, ctx.wshape, ctx.has_bias = x.shape, w.shape, b is not None
+        return y.view(*x.shape[:-1], w2.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w2 = ctx.saved_tensors
+        dy2 = _f32c(dy).reshape(-1, w2.shape[0])
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = linear_bwd_data(dy2, w2, None, ctx.prec).view(ctx.xshape)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = linear_bwd_weight(dy2, x2, ctx.has_bias, ctx.prec)
+            dw = dw.view(ctx.wshape)
+        return dx, dw, db
+
+
+class FFNFn(torch.autograd.Function):
+    """y = relu(x W1^T + b1) W2^T + b2   (models/common_layers.py:137-139; dropout/residual/LN follow in AddLNFn)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        _need_cuda(x, w1, w2)
+        w1m = _f32c(w1.reshape(w1.shape[0], -1))
+        w2m = _f32c(w2.reshape(w2.shape[0], -1))
+        x2 = _f32c(x).reshape(-1, w1m.shape[1])
+        ctx.prec = config.linear
+        h = linear_fwd(x2, w1m, b1, True, ctx.prec)
+        y = linear_fwd(h, w2m, b2, False, ctx.prec)
+        ctx.save_for_backward(x2, h, w1m, w2m)
+        ctx.shapes = (x.shape, w1.shape, w2.shape)
+        return y.view(*x.shape[:-1], w2m.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, h, w1m, w2m = ctx.saved_tensors
+        xs, w1s, w2s = ctx.shapes
+        dy2 = _f32c(dy).reshape(-1, w2m.shape[0])
+        dw2, db2 = linear_bwd_weight(dy2, h, True, ctx.prec)
+        dh = linear_bwd_data(dy2, w2m, h, ctx.prec)          # masked by relu'(h)
+        dw1, db1 = linear_bwd_weight(dh, x2, True, ctx.prec)
+        dx = linear_bwd_data(dh, w1m, None, ctx.prec) if ctx.needs_input_grad[0] else None
+        return (dx.view(xs) if dx is not None else None), dw1.view(w1s), db1, dw2.view(w2s), db2
+
+
+# ----------------------------------------------------------------------------------------------- residual + LN
+class AddLNFn(torch.autograd.Function):
+    """y = (LN(dropout(x) + residual) * gamma + beta + post_add[row % period]) * row_scale[row]."""
+
+    @staticmethod
+    def forward(ctx, x, residual, gamma, beta, post_add, row_scale, eps, p_drop):
+        _need_cuda(x, gamma, beta)
+        d = x.shape[-1]
+        x2 = _f32c(x).reshape(-1, d)
+        rows = x2.shape[0]
+        res2 = _f32c(residual).reshape(-1, d) if residual is not None else None
+        rs = _f32c(row_scale).reshape(-1) if row_scale is not None else None
+        if rs is not None and rs.numel() != rows:
+            raise RuntimeError("AddLN: row_scale must have one entry per row")
+        period = post_add.shape[0] if post_add is not None else 0
+        y = torch.empty_like(x2)
+        need_z = res2 is not None or p_drop > 0.0
+        z = torch.empty_like(x2) if need_z else None
+        mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+        seed, off = rng.next() if p_drop > 0.0 else (0, 0)
+        L.check(_lib().b200asr_add_ln_fwd(L.ptr(x2), L.ptr(res2), L.ptr(gamma), L.ptr(beta), L.ptr(post_add), period,
+                                          L.ptr(rs), L.ptr(y), L.ptr(z), L.ptr(mean), L.ptr(rstd), rows, d, float(eps),
+                                          float(p_drop), seed, off, _stream()), "add_ln_fwd")
+        ctx.save_for_backward(z if need_z else x2, gamma, mean, rstd, rs)
+        ctx.meta = (x.shape, residual is not None, float(p_drop), seed, off, rows, d)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        z, gamma, mean, rstd, rs = ctx.saved_tensors
+        xshape, has_res, p_drop, seed, off, rows, d = ctx.meta
+        dy2 = _f32c(dy).reshape(-1, d)
+        lib = _lib()
+        dz = torch.empty_like(dy2)
+        dx = torch.empty_like(dy2) if p_drop > 0.0 else dz
+        dgamma = torch.empty(d, device=dy.device, dtype=torch.float32)
+        dbeta = torch.empty(d, device=dy.device, dtype=torch.float32)
+        ws = torch.empty(lib.b200asr_add_ln_bwd_ws_bytes(rows, d) // 4, device=dy.device, dtype=torch.float32)
+        L.check(lib.b200asr_add_ln_bwd(L.ptr(dy2), L.ptr(z), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), L.ptr(rs), L.ptr(dz),
+                                       L.ptr(dx), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), rows, d, p_drop, seed, off,
+                                       _stream()), "add_ln_bwd")
+        return dx.view(xshape), (dz.view(xshape) if has_res else None), dgamma, dbeta, None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------- attention
+def _bhtd_strides(t):
+    """(batch, head, row) element strides of a 4-D (B,H,T,d) view whose last dim is contiguous."""
+    if t.dim() != 4 or t.stride(3) != 1:
+        raise RuntimeError("sdpa: expected a (B,H,T,d) view with unit stride on d")
+    return t.stride(0), t.stride(1), t.stride(2)
+
+
+class SdpaFn(torch.autograd.Function):
+    """Fused softmax(q k^T * scale, masks) v over (B,H,T,d) *views* (any batch/head/row strides).
+
+    Output is allocated token-major [B,Tq,H,dv] and returned as the (B,H,Tq,dv) view, so the head merge of
+    models/common_layers.py:194-195 is free."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, key_pad, dense_mask, causal, scale, p_drop, head_major_out=False):
+        _need_cuda(q, k, v)
+        B, H, Tq, dk = q.shape
+        Tk, dv = k.shape[2], v.shape[3]
+        if head_major_out:      # (H,B,Tq,dv) memory: the reference's (H*B) x Tq x dv layout (common_layers.py:185)
+            out = torch.empty((H, B, Tq, dv), device=q.device, dtype=torch.float32).permute(1, 0, 2, 3)
+        else:                   # token-major memory [B,Tq,H,dv]: the head merge of common_layers.py:194-195 is a view
+            out = torch.empty((B, Tq, H, dv), device=q.device, dtype=torch.float32).permute(0, 2, 1, 3)
+        lse = torch.empty((B, H, Tq), device=q.device, dtype=torch.float32)
+        seed, off = rng.next() if p_drop > 0.0 else (0, 0)
+        prec = config.attn
+        qs, ks, vs, os_ = _bhtd_strides(q), _bhtd_strides(k), _bhtd_strides(v), _bhtd_strides(out)
+        L.check(_lib().b200asr_sdpa_fwd(L.ptr(q), L.ptr(k), L.ptr(v), *qs, *ks, *vs, L.ptr(key_pad), L.ptr(dense_mask),
+                                        int(causal), L.ptr(out), *os_, L.ptr(lse), B, H, Tq, Tk, dk, dv, float(scale),
+                                        float(p_drop), seed, off, prec, _stream()), "sdpa_fwd")
+        ctx.save_for_backward(q, k, v, out, lse, key_pad, dense_mask)
+        ctx.meta = (int(causal), float(scale), float(p_drop), seed, off, prec)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, out, lse, key_pad, dense_mask = ctx.saved_tensors
+        causal, scale, p_drop, seed, off, prec = ctx.meta
+        B, H, Tq, dk = q.shape
+        Tk, dv = k.shape[2], v.shape[3]
+        if dout.stride() != out.stride():
+            dout = torch.empty_strided(out.shape, out.stride(), device=out.device, dtype=out.dtype).copy_(dout)
+        dq = torch.empty_strided(q.shape, q.stride(), device=q.device, dtype=torch.float32) if _dense_like(q) else None
+        dkk = torch.empty_strided(k.shape, k.stride(), device=q.device, dtype=torch.float32) if _dense_like(k) else None
+        dvv = torch.empty_strided(v.shape, v.stride(), device=q.device, dtype=torch.float32) if _dense_like(v) else None
+        if dq is None or dkk is None or dvv is None:
+            raise RuntimeError("sdpa backward: q/k/v views must be dense permutations of a contiguous tensor")
+        delta = torch.empty((B, H, Tq), device=q.device, dtype=torch.float32)
+        qs, ks, vs, os_ = _bhtd_strides(q), _bhtd_strides(k), _bhtd_strides(v), _bhtd_strides(out)
+        L.check(_lib().b200asr_sdpa_bwd(L.ptr(dout), L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(out), L.ptr(lse), *qs, *ks, *vs, *os_,
+                                        L.ptr(key_pad), L.ptr(dense_mask), causal, L.ptr(dq), L.ptr(dkk), L.ptr(dvv),
+                                        L.ptr(delta), B, H, Tq, Tk, dk, dv, scale, p_drop, seed, off, prec, _stream()),
+                "sdpa_bwd")
+        return dq, dkk, dvv, None, None, None, None, None, None
+
+
+def _dense_like(t):
+    """True if the view covers a dense block (so empty_strided with the same strides is a plain allocation)."""
+    n = 1
+    for s, st in sorted(zip(t.shape, t.stride()), key=lambda x: x[1]):
+        if s == 1:
+            continue
+        if st != n:
+            return False
+        n *= s
+    return True
+
+
+# ----------------------------------------------------------------------------------------------- VGG front end
+class VggFrontendFn(torch.autograd.Function):
+    """models/asr/transformer.py:42-53 on channels-last [B,T,F,C] activations.
+    Input (B,1,F,T); output [B, T//4, (F//2//2), 128] whose flat view [B, T', F'*128] feeds input_linear."""
+
+    @staticmethod
+    def forward(ctx, x, w0, b0, w2, b2, w5, b5, w7, b7):
+        _need_cuda(x, w0)
+        lib, st, prec = _lib(), _stream(), config.conv
+        x = _f32c(x)
+        B, _, F, T = x.shape
+        dev = x.device
+        C1, C2 = w0.shape[0], w5.shape[0]
+        new = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
+        ws = new(lib.b200asr_conv3x3_ws_bytes(C2, C2) // 4)
+        y1 = new(B, T, F, C1)
+        L.check(lib.b200asr_conv3x3_c1_fwd(L.ptr(x), L.ptr(_f32c(w0)), L.ptr(b0), L.ptr(y1), B, F, T, C1, 1, st), "conv1")
+        y2 = new(B, T, F, C1)
+        L.check(lib.b200asr_conv3x3_fwd(L.ptr(y1), L.ptr(_f32c(w2)), L.ptr(b2), L.ptr(y2), L.ptr(ws), B, T, F, C1, C1, 1,
+                                        prec, st), "conv2")
+        T2, F2 = T // 2, F // 2
+        p1 = new(B, T2, F2, C1)
+        L.check(lib.b200asr_maxpool2x2_fwd(L.ptr(y2), L.ptr(p1), B, T, F, C1, st), "pool1")
+        y3 = new(B, T2, F2, C2)
+        L.check(lib.b200asr_conv3x3_fwd(L.ptr(p1), L.ptr(_f32c(w5)), L.ptr(b5), L.ptr(y3), L.ptr(ws), B, T2, F2, C1, C2, 1,
+                                        prec, st), "conv3")
+        y4 = new(B, T2, F2, C2)
+        L.check(lib.b200asr_conv3x3_fwd(L.ptr(y3), L.ptr(_f32c(w7)), L.ptr(b7), L.ptr(y4), L.ptr(ws), B, T2, F2, C2, C2, 1,
+                                        prec, st), "conv4")
+        T4, F4 = T2 // 2, F2 // 2
+        p2 = new(B, T4, F4, C2)
+        L.check(lib.b200asr_maxpool2x2_fwd(L.ptr(y4), L.ptr(p2), B, T2, F2, C2, st), "pool2")
+        ctx.save_for_backward(x, y1, y2, p1, y3, y4, w0, w2, w5, w7)
+        ctx.prec = prec
+        return p2
+
+    @staticmethod
+    def backward(ctx, dp2):
+        x, y1, y2, p1, y3, y4, w0, w2, w5, w7 = ctx.saved_tensors
+        lib, st, prec = _lib(), _stream(), ctx.prec
+        B, _, F, T = x.shape
+        C1, C2 = w0.shape[0], w5.shape[0]
+        T2, F2 = T // 2, F // 2
+        dev = x.device
+        new = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
+        ws = new(lib.b200asr_conv3x3_ws_bytes(C2, C2) // 4)
+        dp2 = _f32c(dp2)
+        d4 = new(B, T2, F2, C2)
+        L.check(lib.b200asr_maxpool2x2_bwd(L.ptr(dp2), L.ptr(y4), L.ptr(d4), B, T2, F2, C2, 1, st), "pool2_bwd")
+        dw7, db7 = torch.empty_like(w7), new(C2)
+        L.check(lib.b200asr_conv3x3_bwd_weight(L.ptr(d4), L.ptr(y3), L.ptr(dw7), L.ptr(db7), L.ptr(ws), B, T2, F2, C2, C2,
+                                               prec, st), "conv4_wgrad")
+        d3 = new(B, T2, F2, C2)
+        L.check(lib.b200asr_conv3x3_bwd_data(L.ptr(d4), L.ptr(_f32c(w7)), L.ptr(y3), L.ptr(d3), L.ptr(ws), B, T2, F2, C2, C2,
+                                             prec, st), "conv4_dgrad")
+        del d4
+        dw5, db5 = torch.empty_like(w5), new(C2)
+        L.check(lib.b200asr_conv3x3_bwd_weight(L.ptr(d3), L.ptr(p1), L.ptr(dw5), L.ptr(db5), L.ptr(ws), B, T2, F2, C1, C2,
+                                               prec, st), "conv3_wgrad")
+        dp1 = new(B, T2, F2, C1)
+        L.check(lib.b200asr_conv3x3_bwd_data(L.ptr(d3), L.ptr(_f32c(w5)), None, L.ptr(dp1), L.ptr(ws), B, T2, F2, C1, C2,
+                                             prec, st), "conv3_dgrad")
+        del d3
+        d2 = new(B, T, F, C1)
+        L.check(lib.b200asr_maxpool2x2_bwd(L.ptr(dp1), L.ptr(y2), L.ptr(d2), B, T, F, C1, 1, st), "pool1_bwd")
+        dw2, db2 = torch.empty_like(w2), new(C1)
+        L.check(lib.b200asr_conv3x3_bwd_weight(L.ptr(d2), L.ptr(y1), L.ptr(dw2), L.ptr(db2), L.ptr(ws), B, T, F, C1, C1,
+                                               prec, st), "conv2_wgrad")
+        d1 = new(B, T, F, C1)
+        L.check(lib.b200asr_conv3x3_bwd_data(L.ptr(d2), L.ptr(_f32c(w2)), L.ptr(y1), L.ptr(d1), L.ptr(ws), B, T, F, C1, C1,
+                                             prec, st), "conv2_dgrad")
+        del d2
+        dw0, db0 = torch.empty_like(w0), new(C1)
+        L.check(lib.b200asr_conv3x3_c1_bwd_weight(L.ptr(x), L.ptr(d1), L.ptr(dw0), L.ptr(db0), B, F, T, C1, st), "conv1_wgrad")
+        return None, dw0, db0, dw2, db2, dw5, db5, dw7, db7
+
+
+class PermuteColsFn(torch.autograd.Function):
+    """w' [rows, F*C] with w'[:, f*C+c] = w[:, c*F+f]: input_linear's columns re-ordered to the channels-last
+    feature order of VggFrontendFn (replaces the activation transpose of models/asr/transformer.py:74-76)."""
+
+    @staticmethod
+    def forward(ctx, w, C, F):
+        w = _f32c(w)
+        out = torch.empty_like(w)
+        L.check(_lib().b200asr_permute_cols_cf(L.ptr(w), L.ptr(out), w.shape[0], C, F, 0, _stream()), "permute_cols")
+        ctx.cf = (C, F)
+        return out
+
+    @staticmethod
+    def backward(ctx, dw):
+        C, F = ctx.cf
+        dw = _f32c(dw)
+        out = torch.empty_like(dw)
+        L.check(_lib().b200asr_permute_cols_cf(L.ptr(dw), L.ptr(out), dw.shape[0], C, F, 1, _stream()), "permute_cols_inv")
+        return out, None, None
+
+
+# ----------------------------------------------------------------------------------------------- emb_cnn front end
+class EmbFrontendFn(torch.autograd.Function):
+    """models/asr/transformer.py:33-40 (+ flatten :74-76): conv(41x11,s2x2,p0x10)+BN+clamp, conv(21x11,s2x1)+BN+clamp.
+    BatchNorm uses batch statistics (training mode); running statistics are not updated by this path."""
+
+    @staticmethod
+    def forward(ctx, x, w0, b0, g1, be1, w3, b3, g4, be4, eps):
+        _need_cuda(x, w0)
+        lib, st = _lib(), _stream()
+        x = _f32c(x)
+        B, _, H, W = x.shape
+        dev = x.device
+        new = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
+        C = w0.shape[0]
+        H1, W1 = (H - 41) // 2 + 1, (W + 20 - 11) // 2 + 1
+        c1 = new(B, C, H1, W1)
+        L.check(lib.b200asr_conv2d_fwd(L.ptr(x), L.ptr(_f32c(w0)), L.ptr(b0), L.ptr(c1), B, 1, H, W, C, 41, 11, 2, 2, 0, 10, st), "emb_conv1")
+        a1, m1, s1 = new(B, C, H1, W1), new(C), new(C)
+        L.check(lib.b200asr_bn_clamp_fwd(L.ptr(c1), L.ptr(g1), L.ptr(be1), L.ptr(a1), L.ptr(m1), L.ptr(s1), B, C, H1 * W1, eps, 0.0, 20.0, st), "emb_bn1")
+        H2, W2 = (H1 - 21) // 2 + 1, (W1 - 11) // 1 + 1
+        c2 = new(B, C, H2, W2)
+        L.check(lib.b200asr_conv2d_fwd(L.ptr(a1), L.ptr(_f32c(w3)), L.ptr(b3), L.ptr(c2), B, C, H1, W1, C, 21, 11, 2, 1, 0, 0, st), "emb_conv2")
+        a2, m2, s2 = new(B, C, H2, W2), new(C), new(C)
+        L.check(lib.b200asr_bn_clamp_fwd(L.ptr(c2), L.ptr(g4), L.ptr(be4), L.ptr(a2), L.ptr(m2), L.ptr(s2), B, C, H2 * W2, eps, 0.0, 20.0, st), "emb_bn2")
+        out = new(B, W2, C * H2)
+        L.check(lib.b200asr_flatten_bcft_fwd(L.ptr(a2), L.ptr(out), B, C, H2, W2, st), "emb_flatten")
+        ctx.save_for_backward(x, c1, a1, m1, s1, c2, a2, m2, s2, w0, g1, w3, g4)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, c1, a1, m1, s1, c2, a2, m2, s2, w0, g1, w3, g4 = ctx.saved_tensors
+        lib, st = _lib(), _stream()
+        B, _, H, W = x.shape
+        C = w0.shape[0]
+        _, _, H1, W1 = c1.shape
+        _, _, H2, W2 = c2.shape
+        dev = x.device
+        new = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
+        dout = _f32c(dout)
+        da2 = new(B, C, H2, W2)
+        L.check(lib.b200asr_flatten_bcft_bwd(L.ptr(dout), L.ptr(da2), B, C, H2, W2, st), "emb_flatten_bwd")
+        dc2, dg4, dbe4 = new(B, C, H2, W2), new(C), new(C)
+        L.check(lib.b200asr_bn_clamp_bwd(L.ptr(da2), L.ptr(c2), L.ptr(a2), L.ptr(g4), L.ptr(m2), L.ptr(s2), L.ptr(dc2), L.ptr(dg4), L.ptr(dbe4), B, C, H2 * W2, 0.0, 20.0, st), "emb_bn2_bwd")
+        dw3, db3 = torch.empty_like(w3), new(C)
+        L.check(lib.b200asr_conv2d_bwd_weight(L.ptr(dc2), L.ptr(a1), L.ptr(dw3), L.ptr(db3), B, C, H1, W1, C, 21, 11, 2, 1, 0, 0, st), "emb_conv2_wgrad")
+        da1 = new(B, C, H1, W1)
+        L.check(lib.b200asr_conv2d_bwd_data(L.ptr(dc2), L.ptr(_f32c(w3)), L.ptr(da1), B, C, H1, W1, C, 21, 11, 2, 1, 0, 0, st), "emb_conv2_dgrad")
+        dc1, dg1, dbe1 = new(B, C, H1, W1), new(C), new(C)
+        L.check(lib.b200asr_bn_clamp_bwd(L.ptr(da1), L.ptr(c1), L.ptr(a1), L.ptr(g1), L.ptr(m1), L.ptr(s1), L.ptr(dc1), L.ptr(dg1), L.ptr(dbe1), B, C, H1 * W1, 0.0, 20.0, st), "emb_bn1_bwd")
+        dw0, db0 = torch.empty_like(w0), new(C)
+        L.check(lib.b200asr_conv2d_bwd_weight(L.ptr(dc1), L.ptr(x), L.ptr(dw0), L.ptr(db0), B, 1, H, W, C, 41, 11, 2, 2, 0, 10, st), "emb_conv1_wgrad")
+        return None, dw0, db0, dg1, dbe1, dw3, db3, dg4, dbe4, None
+
+
+class FlattenFn(torch.autograd.Function):
+    """(B,C,F,T) -> (B,T,C*F) for feat_extractor='' (C=1) -- models/asr/transformer.py:74-76."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _f32c(x)
+        B, C, F, T = x.shape
+        out = torch.empty((B, T, C * F), device=x.device, dtype=torch.float32)
+        L.check(_lib().b200asr_flatten_bcft_fwd(L.ptr(x), L.ptr(out), B, C, F, T, _stream()), "flatten")
+        ctx.shape = (B, C, F, T)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, C, F, T = ctx.shape
+        dout = _f32c(dout)
+        dx = torch.empty((B, C, F, T), device=dout.device, dtype=torch.float32)
+        L.check(_lib().b200asr_flatten_bcft_bwd(L.ptr(dout), L.ptr(dx), B, C, F, T, _stream()), "flatten_bwd")
+        return dx
+
+
+# ----------------------------------------------------------------------------------------------- decoder input side
+def preprocess_targets(padded_target: torch.Tensor, tgt_max_len: int):
+    """Device-side Decoder.preprocess: returns seq_in, seq_out (int64 [B,Tt]), key_pad (uint8), non_pad (float)."""
+    _need_cuda(padded_target)
+    tgt = padded_target.to(torch.long).contiguous()
+    B, Lt = tgt.shape
+    dev = tgt.device
+    seq_in = torch.empty((B, tgt_max_len), device=dev, dtype=torch.long)
+    seq_out = torch.empty((B, tgt_max_len), device=dev, dtype=torch.long)
+    key_pad = torch.empty((B, tgt_max_len), device=dev, dtype=torch.uint8)
+    non_pad = torch.empty((B, tgt_max_len), device=dev, dtype=torch.float32)
+    status = None
+    if Lt + 1 > tgt_max_len:          # only then can an utterance overflow; otherwise no host sync is needed
+        status = torch.zeros(1, device=dev, dtype=torch.int32)
+    L.check(_lib().b200asr_preprocess_targets(L.ptr(tgt), Lt, L.ptr(seq_in), L.ptr(seq_out), L.ptr(key_pad), L.ptr(non_pad),
+                                              L.ptr(status), B, tgt_max_len, _stream()), "preprocess_targets")
+    if status is not None and int(status.item()) != 0:
+        raise RuntimeError("target longer than tgt_max_len (the reference fails in pad_list, common_layers.py:21)")
+    return seq_in, seq_out, key_pad, non_pad
+
+
+def length_masks(lengths: torch.Tensor, B: int, T: int, device):
+    """key_pad (uint8 [B,T], 1 = frame >= length) and non_pad (float [B,T]) from raw lengths (quirk Q1 preserved)."""
+    lens = lengths.to(device=device, dtype=torch.int32).contiguous()
+    key_pad = torch.empty((B, T), device=device, dtype=torch.uint8)
+    non_pad = torch.empty((B, T), device=device, dtype=torch.float32)
+    L.check(_lib().b200asr_length_masks(L.ptr(lens), L.ptr(key_pad), L.ptr(non_pad), B, T, _stream()), "length_masks")
+    return key_pad, non_pad
+
+
+class EmbedFn(torch.autograd.Function):
+    """dropout(Embedding(tokens) * scale + PE[:T])  (models/asr/transformer.py:292-293)."""
+
+    @staticmethod
+    def forward(ctx, tokens, table, pe, scale, p_drop, pad_idx):
+        _need_cuda(tokens, table, pe)
+        B, T = tokens.shape
+        V, d = table.shape
+        out = torch.empty((B, T, d), device=table.device, dtype=torch.float32)
+        seed, off = rng.next() if p_drop > 0.0 else (0, 0)
+        L.check(_lib().b200asr_embed_fwd(L.ptr(tokens), L.ptr(_f32c(table)), L.ptr(pe), L.ptr(out), B * T, T, d, V, float(scale),
+                                         float(p_drop), seed, off, _stream()), "embed_fwd")
+        ctx.save_for_backward(tokens)
+        ctx.meta = (V, d, float(scale), float(p_drop), seed, off, int(pad_idx))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (tokens,) = ctx.saved_tensors
+        V, d, scale, p_drop, seed, off, pad_idx = ctx.meta
+        dout = _f32c(dout)
+        dtable = torch.zeros((V, d), device=dout.device, dtype=torch.float32)
+        L.check(_lib().b200asr_embed_bwd(L.ptr(tokens), L.ptr(dout), L.ptr(dtable), tokens.numel(), d, V, scale, p_drop, seed,
+                                         off, pad_idx, _stream()), "embed_bwd")
+        return None, dtable, None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------- output side
+def argmax_rows(logits: torch.Tensor) -> torch.Tensor:
+    _need_cuda(logits)
+    V = logits.shape[-1]
+    x = _f32c(logits.detach()).reshape(-1, V)
+    out = torch.empty(x.shape[0], device=x.device, dtype=torch.long)
+    L.check(_lib().b200asr_argmax_rows(L.ptr(x), L.ptr(out), x.shape[0], V, _stream()), "argmax_rows")
+    return out.view(logits.shape[:-1])
+
+
+class CrossEntropyFn(torch.autograd.Function):
+    """Label-smoothed CE / CE of utils/metrics.py:115-132 plus num_correct (:88-94), one pass over the logits.
+
+    Returns (loss, stats): loss is a 0-dim tensor -- the mean over non-PAD tokens (reduction='mean', the
+    reference's value) or the plain sum (reduction='sum', used by the data-parallel step which divides by the
+    all-reduced global token count).  stats = [sum, n_tokens, n_correct, mean, 1/n_tokens] (not differentiable)."""
+
+    @staticmethod
+    def forward(ctx, pred, gold, smoothing, reduction):
+        _need_cuda(pred, gold)
+        V = pred.shape[-1]
+        x = _f32c(pred).reshape(-1, V)
+        g = gold.to(torch.long).contiguous().reshape(-1)
+        rows = x.shape[0]
+        lse = torch.empty(rows, device=x.device, dtype=torch.float32)
+        stats = torch.empty(5, device=x.device, dtype=torch.float32)
+        loss = torch.empty((), device=x.device, dtype=torch.float32)
+        mean = reduction == "mean"
+        lib, st = _lib(), _stream()
+        L.check(lib.b200asr_ce_fwd(L.ptr(x), L.ptr(g), L.ptr(lse), L.ptr(stats), rows, V, float(smoothing), st), "ce_fwd")
+        L.check(lib.b200asr_ce_finalize(L.ptr(stats), L.ptr(loss), int(mean), st), "ce_finalize")
+        ctx.save_for_backward(x, g, lse, stats)
+        ctx.meta = (pred.shape, float(smoothing), mean)
+        ctx.mark_non_differentiable(stats)
+        return loss, stats
+
+    @staticmethod
+    def backward(ctx, dloss, _dstats):
+        x, g, lse, stats = ctx.saved_tensors
+        shape, smoothing, mean = ctx.meta
+        rows, V = x.shape
+        gs = _f32c(dloss)                               # device scalar: no host sync
+        inv_n = stats[4:5] if mean else None            # device scalar 1/num_word
+        dx = torch.empty_like(x)
+        L.check(_lib().b200asr_ce_bwd(L.ptr(x), L.ptr(g), L.ptr(lse), L.ptr(dx), rows, V, smoothing, 1.0, L.ptr(gs),
+                                      L.ptr(inv_n), _stream()), "ce_bwd")
+        return dx.view(shape), None, None, None

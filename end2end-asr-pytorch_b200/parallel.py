@@ -1,0 +1,74 @@
+"""Data-parallel training step: one process per GPU, replicated parameters, ONE all-reduce per step.
+
+Mirrors the reference's `--parallel` nn.DataParallel path (utils/functions.py:154-160) with the
+B200-native strategy of SURVEY.md §5.8: each rank runs forward/backward on its shard of the utterance batch with the
+UN-normalised token-loss sum, the flat gradient buffer (+ [sum-loss, n_tokens]) is all-reduced once over
+NCCL/NVLink, and the optimizer divides by the GLOBAL token count -- exactly the reference's normalisation over the
+gathered global batch (trainer.py:84 + metrics.py:127-130).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import metrics
+from .optim import FlatParams, FusedAdam, NoamOpt
+
+
+def shard_batch(src, lengths, tgt, rank: int, world: int):
+    """Rank r takes utterances [r*B/N, (r+1)*B/N) of the (length-sorted) batch, as DataParallel.scatter would."""
+    B = src.shape[0]
+    if B % world:
+        raise ValueError("the batch has to be divisible by the number of GPUs (reference README.md:73)")
+    n = B // world
+    sl = slice(rank * n, (rank + 1) * n)
+    return src[sl], lengths[sl], tgt[sl]
+
+
+class DataParallelStep:
+    """zero_grad -> forward -> CE(sum) -> backward -> single all-reduce -> Adam(1/global_tokens)."""
+
+    def __init__(self, model, model_size, warmup=4000, k_lr=1.0, min_lr=1e-5, smoothing=0.0, process_group=None,
+                 clip_max_norm=None):
+        self.model = model
+        self.flat = FlatParams(model, extra=2)
+        self.adam = FusedAdam(self.flat, betas=(0.9, 0.98), eps=1e-9)
+        self.opt = NoamOpt(model_size, k_lr, warmup, self.adam, min_lr=min_lr)
+        self.smoothing = smoothing
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.clip = clip_max_norm
+        self._inv_tokens = torch.zeros(1, device=self.flat.flat.device, dtype=torch.float32)
+
+    def forward_backward(self, src, lengths, tgt):
+        """Local shard fwd+bwd with the un-normalised loss; gradients land in the flat buffer."""
+        self.flat.zero_grad()
+        pred, gold, hyp, _ = self.model(src, lengths, tgt)
+        loss_sum, stats = metrics.loss_and_stats(pred, gold, self.smoothing, reduction="sum")
+        loss_sum.backward()
+        self.flat.ensure_grad_views()
+        self.flat.extras.copy_(stats[0:2])            # [sum-loss, n_tokens] ride with the gradients
+        return pred, hyp, stats
+
+    def all_reduce(self):
+        if self.world > 1:
+            dist.all_reduce(self.flat.flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def optimizer_step(self):
+        torch.reciprocal(self.flat.extras[1:2], out=self._inv_tokens)     # 1 / global n_tokens (device scalar)
+        scale = 1.0
+        if self.clip is not None:                                          # trainer.py:108-109 (needs the norm on the host)
+            norm = float(self.adam.grad_sumsq().sqrt().item()) * float(self._inv_tokens.item())
+            scale = min(1.0, self.clip / (norm + 1e-6))
+        self.opt.step(grad_scale=scale, grad_scale_dev=self._inv_tokens)
+
+    def step(self, src, lengths, tgt):
+        pred, hyp, stats = self.forward_backward(src, lengths, tgt)
+        self.all_reduce()
+        self.optimizer_step()
+        return pred, hyp, stats
+
+    def global_loss(self) -> torch.Tensor:
+        """Mean loss over the global batch (device tensor): all-reduced sum / all-reduced token count."""
+        e = self.flat.extras
+        return e[0] / e[1]

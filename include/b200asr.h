@@ -1,0 +1,226 @@
+/* libb200asr -- C ABI of the B200-native speech-Transformer training hot path.
+ *
+ * The reference (gentaiscool/end2end-asr-pytorch) is pure Python on PyTorch and has NO FFI / operator
+ * plugin interface: its seams are nn.Module.forward methods and two free functions.  Each
+ * entry point below therefore cites the reference *call site* whose ATen dispatches it replaces; the
+ * host-side binding a maintainer would add is the ctypes stub shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated; fp32 data,
+ *     int64 token ids (torch.long), uint8 masks (1 = masked / padded).
+ *   - the caller owns all memory (including workspaces); the library never allocates, frees or keeps
+ *     device pointers after the call returns.
+ *   - every function enqueues work on `stream` (a cudaStream_t passed as void*) and returns without
+ *     synchronising.  Return value: 0 on success, <0 on error (B200ASR_* below);
+ *     b200asr_last_error() gives a thread-local message.  No C++ exception crosses the ABI.
+ *   - `precision`: 0 = fp32 FMA on CUDA cores (exact-order fp32 accumulate); 1 = tcgen05 kind::tf32,
+ *     one pass; 3 = tcgen05 3xTF32 split (fp32-grade).  An unsupported (shape, precision) pair is an
+ *     error -- there is no silent fallback of any kind (and no CPU path).
+ *   - dropout: `p_drop` in [0,1); decisions come from a counter-based generator keyed by
+ *     (seed, offset, element index), so *_bwd regenerates the mask of the matching *_fwd call when it is
+ *     given the same (seed, offset).
+ */
+#ifndef B200ASR_H_
+#define B200ASR_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200ASR_OK 0
+#define B200ASR_BAD_SHAPE -1
+#define B200ASR_BAD_ALIGN -2
+#define B200ASR_UNSUPPORTED_ARCH -3
+#define B200ASR_CUDA_ERROR -4
+#define B200ASR_BAD_ARG -5
+
+#define B200ASR_PREC_FP32 0
+#define B200ASR_PREC_TF32 1
+#define B200ASR_PREC_TF32X3 3
+
+typedef void* b200asr_stream_t; /* cudaStream_t */
+
+int b200asr_version(void);
+const char* b200asr_last_error(void);
+/* 0 iff the current device is an sm_100 part (B200).  Called by the loader; everything else assumes it. */
+int b200asr_device_check(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense layers.  Replaces nn.Linear / nn.Conv1d(k=1) dispatches:
+ *   encoder input_linear            models/asr/transformer.py:172
+ *   Q/K/V/output projections        models/common_layers.py:181-183,197
+ *   position-wise FFN conv_1/conv_2 models/common_layers.py:138   (weights (out,in,1) == (out,in))
+ *   decoder output_linear (logits)  models/asr/transformer.py:302
+ * y[M,N] = act(x[M,K] * w[N,K]^T + bias[N]);  bias may be NULL; relu != 0 applies max(0, .)
+ */
+int b200asr_linear_fwd(const float* x, const float* w, const float* bias, float* y, int M, int N, int K,
+                       int relu, int precision, b200asr_stream_t stream);
+/* dx[M,K] (+)= (dy[M,N] * w[N,K]) .* (relu_out[M,K] > 0 if relu_out != NULL) */
+int b200asr_linear_bwd_data(const float* dy, const float* w, const float* relu_out, float* dx, int M, int N,
+                            int K, int accumulate, int precision, b200asr_stream_t stream);
+/* dw[N,K] (+)= dy[M,N]^T * x[M,K];  dbias[N] (+)= column sums of dy (dbias may be NULL) */
+int b200asr_linear_bwd_weight(const float* dy, const float* x, float* dw, float* dbias, int M, int N, int K,
+                              int accumulate, int precision, b200asr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Residual + LayerNorm (+ positional encoding, + non-pad row mask).  Replaces
+ *   dropout -> add residual -> LayerNorm   models/common_layers.py:197-198 (MHA), :140-141 (FFN)
+ *   `out *= non_pad_mask`                   models/asr/transformer.py:198,201,536,540,543
+ *   LayerNorm(Linear(x)) + PE               models/asr/transformer.py:172-173
+ * z = dropout(x) + residual ; y = (LN(z)*gamma + beta + post_add[row % post_period]) * row_scale[row]
+ * residual, post_add, row_scale, z may be NULL (z NULL: LN input is not saved; valid only when it
+ * equals x, i.e. residual == NULL and p_drop == 0).  mean/rstd are [rows].  d % 4 == 0, d <= 1024.
+ */
+int b200asr_add_ln_fwd(const float* x, const float* residual, const float* gamma, const float* beta,
+                       const float* post_add, int post_period, const float* row_scale, float* y, float* z,
+                       float* mean, float* rstd, int rows, int d, float eps, float p_drop, uint64_t seed,
+                       uint64_t offset, b200asr_stream_t stream);
+/* dz = grad wrt LN input (== grad wrt residual); dx = grad wrt x (dz through the dropout mask; pass
+ * dx == dz when p_drop == 0).  dgamma/dbeta are overwritten.  partial_ws: b200asr_add_ln_bwd_ws_bytes. */
+int b200asr_add_ln_bwd(const float* dy, const float* z, const float* gamma, const float* mean,
+                       const float* rstd, const float* row_scale, float* dz, float* dx, float* dgamma,
+                       float* dbeta, void* partial_ws, int rows, int d, float p_drop, uint64_t seed,
+                       uint64_t offset, b200asr_stream_t stream);
+size_t b200asr_add_ln_bwd_ws_bytes(int rows, int d);
+
+/* ------------------------------------------------------------------------------------------------
+ * Scaled dot-product attention, fused (scores never reach HBM).  Replaces
+ *   bmm -> /temperature -> masked_fill(-inf) -> softmax(dim=2) -> dropout -> bmm
+ *   models/common_layers.py:215-223, and the head split/merge copies at :185-187,:194-195 through strides.
+ * Element (b,h,t,c) of q lives at q[b*q_bs + h*q_hs + t*q_rs + c] (likewise k, v, out, and their grads).
+ * key_pad   [B,Tk]     1 = key is padding for every query of that utterance (NULL = none)
+ * dense_mask[B,Tq,Tk]  1 = masked (the reference's generic mask, broadcast over heads; NULL = none)
+ * causal != 0 masks k > q (models/common_layers.py:66-74).  lse is [B,H,Tq] (log-sum-exp of the scaled,
+ * masked scores).  A fully-masked row yields NaN exactly like the reference's softmax.
+ * dk, dv in {16,32,64,128}.
+ */
+int b200asr_sdpa_fwd(const float* q, const float* k, const float* v, long long q_bs, long long q_hs,
+                     long long q_rs, long long k_bs, long long k_hs, long long k_rs, long long v_bs,
+                     long long v_hs, long long v_rs, const uint8_t* key_pad, const uint8_t* dense_mask,
+                     int causal, float* out, long long o_bs, long long o_hs, long long o_rs, float* lse, int B,
+                     int H, int Tq, int Tk, int dk, int dv, float scale, float p_drop, uint64_t seed,
+                     uint64_t offset, int precision, b200asr_stream_t stream);
+/* dq/dk/dv use the strides of q/k/v; they are overwritten.  delta_ws: [B,H,Tq] floats of scratch. */
+int b200asr_sdpa_bwd(const float* dout, const float* q, const float* k, const float* v, const float* out,
+                     const float* lse, long long q_bs, long long q_hs, long long q_rs, long long k_bs,
+                     long long k_hs, long long k_rs, long long v_bs, long long v_hs, long long v_rs,
+                     long long o_bs, long long o_hs, long long o_rs, const uint8_t* key_pad,
+                     const uint8_t* dense_mask, int causal, float* dq, float* dk_out, float* dv_out,
+                     float* delta_ws, int B, int H, int Tq, int Tk, int dk, int dv, float scale, float p_drop,
+                     uint64_t seed, uint64_t offset, int precision, b200asr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * VGG front end (models/asr/transformer.py:42-53).  Activations are kept channels-last with time as the
+ * outer spatial axis, [B,T,F,C], so the flatten/transpose of :74-76 becomes a free view [B*T, F*C]
+ * (feature index f*C+c; the host permutes input_linear's columns once per step instead).
+ * Weights keep the reference layout [Co,Ci,3(freq),3(time)].
+ */
+/* x [B,F,T] (the reference's (B,1,F,T) input as is) -> y [B,T,F,Co], bias + optional ReLU fused */
+int b200asr_conv3x3_c1_fwd(const float* x, const float* w, const float* bias, float* y, int B, int F, int T,
+                           int Co, int relu, b200asr_stream_t stream);
+/* dw[Co,1,3,3], dbias[Co] overwritten; dy is [B,T,F,Co] (already masked by the ReLU derivative) */
+int b200asr_conv3x3_c1_bwd_weight(const float* x, const float* dy, float* dw, float* dbias, int B, int F,
+                                  int T, int Co, b200asr_stream_t stream);
+/* x [B,T,F,Ci] -> y [B,T,F,Co]; ws: b200asr_conv3x3_ws_bytes(Ci,Co) */
+int b200asr_conv3x3_fwd(const float* x, const float* w, const float* bias, float* y, void* ws, int B, int T,
+                        int F, int Ci, int Co, int relu, int precision, b200asr_stream_t stream);
+/* dx[B,T,F,Ci] = conv_transpose(dy) .* (relu_out > 0 if relu_out != NULL) */
+int b200asr_conv3x3_bwd_data(const float* dy, const float* w, const float* relu_out, float* dx, void* ws,
+                             int B, int T, int F, int Ci, int Co, int precision, b200asr_stream_t stream);
+/* dw[Co,Ci,3,3], dbias[Co] overwritten */
+int b200asr_conv3x3_bwd_weight(const float* dy, const float* x, float* dw, float* dbias, void* ws, int B,
+                               int T, int F, int Ci, int Co, int precision, b200asr_stream_t stream);
+size_t b200asr_conv3x3_ws_bytes(int Ci, int Co);
+/* MaxPool2d(2, stride 2), floor mode: [B,T,F,C] -> [B,T/2,F/2,C] */
+int b200asr_maxpool2x2_fwd(const float* x, float* y, int B, int T, int F, int C, b200asr_stream_t stream);
+/* dx[B,T,F,C] = route dy to the first maximum of each window (scan order freq-major, as ATen), then
+ * .* (x > 0) when relu_mask != 0 (x is the post-ReLU pool input). */
+int b200asr_maxpool2x2_bwd(const float* dy, const float* x, float* dx, int B, int T, int F, int C,
+                           int relu_mask, b200asr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * emb_cnn front end (models/asr/transformer.py:33-40): generic strided NCHW convolution, BatchNorm2d
+ * with batch statistics (training mode) fused with Hardtanh(lo,hi), and the (B,C,F,T)->(B,T,C*F)
+ * flatten of :74-76.
+ */
+int b200asr_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, int B, int Ci, int H,
+                       int W, int Co, int KH, int KW, int SH, int SW, int PH, int PW, b200asr_stream_t stream);
+int b200asr_conv2d_bwd_data(const float* dy, const float* w, float* dx, int B, int Ci, int H, int W, int Co,
+                            int KH, int KW, int SH, int SW, int PH, int PW, b200asr_stream_t stream);
+int b200asr_conv2d_bwd_weight(const float* dy, const float* x, float* dw, float* dbias, int B, int Ci, int H,
+                              int W, int Co, int KH, int KW, int SH, int SW, int PH, int PW,
+                              b200asr_stream_t stream);
+/* y = clamp(BN(x), lo, hi); x,y [B,C,HW]; mean/invstd [C] are outputs (biased variance, as ATen) */
+int b200asr_bn_clamp_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean,
+                         float* invstd, int B, int C, int HW, float eps, float lo, float hi,
+                         b200asr_stream_t stream);
+int b200asr_bn_clamp_bwd(const float* dy, const float* x, const float* y, const float* gamma,
+                         const float* mean, const float* invstd, float* dx, float* dgamma, float* dbeta,
+                         int B, int C, int HW, float lo, float hi, b200asr_stream_t stream);
+/* x [B,C,F,T] -> y [B,T,C*F] and its inverse (gradient) */
+int b200asr_flatten_bcft_fwd(const float* x, float* y, int B, int C, int F, int T, b200asr_stream_t stream);
+int b200asr_flatten_bcft_bwd(const float* dy, float* dx, int B, int C, int F, int T, b200asr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Decoder input side.
+ *   Decoder.preprocess + pad_list          models/asr/transformer.py:254-266, common_layers.py:14-22
+ *   non-pad / key-pad masks (== EOS)       models/asr/transformer.py:282-285
+ *   dropout(Embedding(seq_in)*scale + PE)  models/asr/transformer.py:292-293
+ * padded_target [B,L] (0-padded).  Outputs, all [B,Tt]: seq_in (SOS,y..,EOS pad), seq_out (y..,EOS,PAD
+ * pad), key_pad (seq_in == EOS), non_pad (float 1/0).  status[0] (device int) is set to 1 if some
+ * utterance needs more than Tt positions (the reference raises in pad_list).
+ */
+int b200asr_preprocess_targets(const int64_t* padded_target, int L, int64_t* seq_in, int64_t* seq_out,
+                               uint8_t* key_pad, float* non_pad, int* status, int B, int Tt,
+                               b200asr_stream_t stream);
+int b200asr_embed_fwd(const int64_t* tokens, const float* table, const float* pe, float* out, int rows, int T,
+                      int d, int V, float scale, float p_drop, uint64_t seed, uint64_t offset,
+                      b200asr_stream_t stream);
+/* dtable[V,d] += scatter(dout) (caller zeroes dtable); rows with token == pad_idx contribute nothing */
+int b200asr_embed_bwd(const int64_t* tokens, const float* dout, float* dtable, int rows, int d, int V,
+                      float scale, float p_drop, uint64_t seed, uint64_t offset, int pad_idx,
+                      b200asr_stream_t stream);
+/* length masks of models/common_layers.py:28-44,57-64: key_pad[b,t] = (t >= lengths[b]), non_pad = 1-that */
+int b200asr_length_masks(const int32_t* lengths, uint8_t* key_pad, float* non_pad, int B, int T,
+                         b200asr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Output side.
+ *   topk(pred,1)                       models/asr/transformer.py:80-82
+ *   label-smoothed CE / CE / num_correct   utils/metrics.py:115-132, 88-94
+ * stats (device, 5 floats; [3],[4] filled by b200asr_ce_finalize): [0] = sum over non-PAD rows of the row loss, [1] = number of non-PAD rows,
+ * [2] = number of correct argmax among them.  stats[0..2] are overwritten.  row_lse is [rows].
+ */
+int b200asr_argmax_rows(const float* logits, int64_t* out, int rows, int V, b200asr_stream_t stream);
+int b200asr_ce_fwd(const float* logits, const int64_t* gold, float* row_lse, float* stats, int rows, int V,
+                   float smoothing, b200asr_stream_t stream);
+/* stats[3] = stats[0] / stats[1] (the reference's mean loss), stats[4] = 1 / stats[1];
+ * loss_out[0] = mean ? stats[3] : stats[0].  stats therefore holds 5 floats. */
+int b200asr_ce_finalize(float* stats, float* loss_out, int mean, b200asr_stream_t stream);
+/* dlogits = gscale * (*gscale_dev) * (*gscale_dev2) * d(sum of row losses)/dlogits (NULL factors = 1);
+ * PAD rows get 0 */
+int b200asr_ce_bwd(const float* logits, const int64_t* gold, const float* row_lse, float* dlogits, int rows,
+                   int V, float smoothing, float gscale, const float* gscale_dev, const float* gscale_dev2,
+                   b200asr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Step tail ("next" row of SURVEY.md §8f): Adam(betas, eps) with the learning rate supplied by the host
+ * (NoamOpt, utils/optimizer.py:15-32; torch.optim.Adam at utils/functions.py:107) over a flat buffer.
+ * g is read as g * gscale * (*gscale_dev if non-NULL) -- e.g. 1/global num_word and the clip coefficient.
+ */
+int b200asr_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                      float beta2, float eps, int step, float gscale, const float* gscale_dev,
+                      b200asr_stream_t stream);
+/* out[0] += sum(g^2) (caller zeroes out) */
+int b200asr_sumsq(const float* g, long long n, float* out, b200asr_stream_t stream);
+/* dst = src permuted: dst[r, f*C + c] = src[r, c*F + f] (input_linear column order, see VGG note);
+ * inverse != 0 applies the inverse permutation. */
+int b200asr_permute_cols_cf(const float* src, float* dst, int rows, int C, int F, int inverse,
+                            b200asr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ASR_H_ */
