@@ -25,6 +25,7 @@ SIGNATURES = {
     "b200asr_version": (_i, []),
     "b200asr_last_error": (C.c_char_p, []),
     "b200asr_device_check": (_i, []),
+    "b200asr_launch_count": (C.c_ulonglong, []),
     "b200asr_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200asr_linear_bwd_data": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200asr_linear_bwd_weight": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -15,7 +15,8 @@
 namespace b200asr {
 
 void set_error(const char* fmt, ...);
-int check_launch(const char* what);   // cudaGetLastError -> error code (+message)
+int check_launch(const char* what);   // cudaGetLastError -> error code (+message); counts one kernel launch
+void note_launch(int n);              // additional kernel launches not followed by their own check_launch
 int device_sm_count();
 int ensure_sm100();                   // B200ASR_OK iff current device is compute capability 10.x
 

@@ -116,6 +116,21 @@ __global__ void conv_repack_kernel(const float* __restrict__ w, float* __restric
     wr[i] = w[((size_t)co * Ci + ci) * 9 + (8 - tap)];
   }
 }
+// K-major repacks for the tcgen05 path (contraction channel contiguous):
+// fwd:   wk[tap][co][ci] = w[co][ci][tap]
+// dgrad: wk[tap'][ci][co] = w[co][ci][8 - tap']
+__global__ void conv_repack_k_kernel(const float* __restrict__ w, float* __restrict__ wk, int Ci, int Co, int dgrad) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int total = 9 * Ci * Co;
+  if (i >= total) return;
+  if (!dgrad) {
+    int ci = i % Ci, co = (i / Ci) % Co, tap = i / (Co * Ci);
+    wk[i] = w[((size_t)co * Ci + ci) * 9 + tap];
+  } else {
+    int co = i % Co, ci = (i / Co) % Ci, tap = i / (Co * Ci);
+    wk[i] = w[((size_t)co * Ci + ci) * 9 + (8 - tap)];
+  }
+}
 // dw[co][ci][tap] = dwr[tap][ci][co]
 __global__ void conv_unpack_wgrad_kernel(const float* __restrict__ dwr, float* __restrict__ dw, int Ci, int Co) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -507,8 +522,12 @@ int b200asr_conv3x3_fwd(const float* x, const float* w, const float* bias, float
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   int total = 9 * Ci * Co;
-  conv_repack_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, (float*)ws, Ci, Co, 0);
-  if (precision == B200ASR_PREC_FP32) return conv3x3_simt(x, (const float*)ws, bias, nullptr, y, B, T, F, Ci, Co, relu, st);
+  note_launch(1);
+  if (precision == B200ASR_PREC_FP32) {
+    conv_repack_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, (float*)ws, Ci, Co, 0);
+    return conv3x3_simt(x, (const float*)ws, bias, nullptr, y, B, T, F, Ci, Co, relu, st);
+  }
+  conv_repack_k_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, (float*)ws, Ci, Co, 0);
   return conv3x3_tc(x, (const float*)ws, bias, nullptr, y, B, T, F, Ci, Co, relu, precision, st);
 }
 
@@ -519,8 +538,12 @@ int b200asr_conv3x3_bwd_data(const float* dy, const float* w, const float* relu_
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   int total = 9 * Ci * Co;
-  conv_repack_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, (float*)ws, Ci, Co, 1);
-  if (precision == B200ASR_PREC_FP32) return conv3x3_simt(dy, (const float*)ws, nullptr, relu_out, dx, B, T, F, Co, Ci, 0, st);
+  note_launch(1);
+  if (precision == B200ASR_PREC_FP32) {
+    conv_repack_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, (float*)ws, Ci, Co, 1);
+    return conv3x3_simt(dy, (const float*)ws, nullptr, relu_out, dx, B, T, F, Co, Ci, 0, st);
+  }
+  conv_repack_k_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, (float*)ws, Ci, Co, 1);
   return conv3x3_tc(dy, (const float*)ws, nullptr, relu_out, dx, B, T, F, Co, Ci, 0, precision, st);
 }
 
@@ -563,6 +586,7 @@ int b200asr_maxpool2x2_bwd(const float* dy, const float* x, float* dx, int B, in
   if ((T & 1) || (F & 1)) {
     long long tot = (long long)B * T * F * C;
     maxpool2x2_bwd_tail_kernel<<<(unsigned)ceil_div_ll(tot, 256), 256, 0, st>>>(dx, B, T, F, C);
+    note_launch(1);
   }
   return check_launch("maxpool2x2_bwd");
 }

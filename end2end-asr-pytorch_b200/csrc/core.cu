@@ -15,7 +15,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static unsigned long long g_launches = 0;   // kernels launched by this library (process-wide, approximate under threads)
+void note_launch(int n) { g_launches += (unsigned long long)n; }
+
 int check_launch(const char* what) {
+  g_launches += 1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
@@ -60,4 +64,5 @@ extern "C" {
 int b200asr_version(void) { return 100; }
 const char* b200asr_last_error(void) { return b200asr::g_err; }
 int b200asr_device_check(void) { return b200asr::ensure_sm100(); }
+unsigned long long b200asr_launch_count(void) { return b200asr::g_launches; }
 }

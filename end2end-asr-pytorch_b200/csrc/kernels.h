@@ -16,7 +16,8 @@ int gemm_tc(const float* A, bool a_kmaj, int lda, const float* B, bool b_kmaj, i
             int N, int K, const float* bias, int relu, const float* relu_mask, int accumulate, int nsplit,
             cudaStream_t st);
 
-// tcgen05 implicit-GEMM convolution (tc_conv.cu); wr layouts as produced by conv_repack_kernel.
+// tcgen05 implicit-GEMM convolution (tc_conv.cu); takes K-major repacked weights wk[9][Cout][Cin]
+// (conv_repack_k_kernel); the weight-gradient variant takes/produces dwr[9][Ci][Co].
 int conv3x3_tc(const float* in, const float* wr, const float* bias, const float* mask, float* out, int B, int T, int F,
                int Cin, int Cout, int relu, int precision, cudaStream_t st);
 int conv3x3_wgrad_tc(const float* x, const float* dy, float* dwr, int B, int T, int F, int Ci, int Co, int precision,

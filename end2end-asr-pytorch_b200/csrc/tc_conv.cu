@@ -1,0 +1,218 @@
+// tcgen05 implicit-GEMM 3x3 convolution on channels-last [B,T,F,C] activations (forward and data gradient).
+//
+//   out[p][n] = act( sum_{tap} sum_c in[p + off(tap)][c] * wk[tap][n][c] + bias[n] ) (.* mask > 0)
+//
+// One CTA computes an 8 (time) x 16 (freq) patch = 128 output pixels x BN output channels.  The A operand of k-block
+// (tap, 32-channel slice) is ONE 4-D TMA box {32 ch, 16 freq, 8 time, 1 utt} fetched at the tap-shifted coordinate:
+// the zero padding of the convolution is TMA's out-of-bounds fill, so there is no im2col buffer and no halo logic.
+// The box lands in shared memory as 128 rows x 128 B (K-major, 128B swizzle) -- exactly the UMMA canonical tile.
+// The B operand is the repacked weight wk[tap][n][c] (K-major, one 2-D box).  Mainloop, 3xTF32 operand split and
+// TMEM epilogue are the same design as tc_gemm.cu.
+#include "../../include/b200asr.h"
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
+
+namespace b200asr {
+namespace tc {
+
+constexpr int CT_T = 8, CT_F = 16;                    // pixel patch: 8 x 16 = 128 rows of the MMA
+constexpr int A_TILE = 128 * 128;                     // bytes per A k-block
+constexpr int CONV_THREADS = 192;
+
+template <int BN, int NSPLIT> struct ConvCfg {
+  static constexpr int kBTile = BN * 128;
+  static constexpr int kStageBytes = NSPLIT * 0 + (NSPLIT == 1 ? (A_TILE + kBTile) : 2 * (A_TILE + kBTile));
+  static constexpr int kStages = NSPLIT == 1 ? 6 : (BN == 64 ? 4 : 3);
+  static constexpr int kOffAlo = A_TILE;                                   // (x3) A_hi | A_lo | B_hi | B_lo
+  static constexpr int kOffBhi = NSPLIT == 1 ? A_TILE : 2 * A_TILE;
+  static constexpr int kOffBlo = 2 * A_TILE + kBTile;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+struct ConvEpi {
+  float* out;
+  const float* bias;
+  const float* mask;
+  int relu, B, T, F, Cin, Cout;
+};
+
+template <int BN, int NSPLIT>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+tc_conv3x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const ConvEpi e) {
+  using Cfg = ConvCfg<BN, NSPLIT>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + S * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto xfm_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * S + s); };
+  const uint32_t accum_bar = bar_base + 8u * (3 * S);
+  const uint32_t tmem_slot = bar_base + 8u * (3 * S + 1);
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int f0 = blockIdx.x * CT_F, t0 = blockIdx.y * CT_T, b = blockIdx.z;
+  const int cch = e.Cin / 32;
+  const int nkb = 9 * cch;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; s++) { mbar_init(full_bar(s), 1); mbar_init(xfm_bar(s), 128); mbar_init(empty_bar(s), 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; kb++) {
+        const int s = kb % S;
+        const uint32_t ph = (kb / S) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+        const uint32_t sb = sa + Cfg::kOffBhi;
+        const int tap = kb / cch, c0 = (kb - tap * cch) * 32;
+        const int df = tap / 3 - 1, dt = tap % 3 - 1;          // tap = kf*3 + kt of w[Co][Ci][kf(freq)][kt(time)]
+        mbar_expect_tx(full_bar(s), A_TILE + Cfg::kBTile);
+        tma_load_4d(sa, &mapA, full_bar(s), c0, f0 + df, t0 + dt, b);   // halo / image border = TMA zero fill
+        tma_load_2d(sb, &mapB, full_bar(s), c0, tap * BN);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(128, BN, false, false);
+      for (int kb = 0; kb < nkb; kb++) {
+        const int s = kb % S;
+        const uint32_t ph = (kb / S) & 1;
+        mbar_wait(NSPLIT == 1 ? full_bar(s) : xfm_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+        const uint32_t sb = sa + Cfg::kOffBhi;
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++) {
+          const uint64_t a_hi = make_smem_desc(sa + ks * 32, 16, 1024);
+          const uint64_t b_hi = make_smem_desc(sb + ks * 32, 16, 1024);
+          const uint32_t acc0 = (kb | ks) != 0 ? 1u : 0u;
+          if (NSPLIT == 1) {
+            umma_tf32(tmem_base, a_hi, b_hi, idesc, acc0);
+          } else {
+            const uint64_t a_lo = make_smem_desc(sa + Cfg::kOffAlo + ks * 32, 16, 1024);
+            const uint64_t b_lo = make_smem_desc(sa + Cfg::kOffBlo + ks * 32, 16, 1024);
+            umma_tf32(tmem_base, a_lo, b_hi, idesc, acc0);
+            umma_tf32(tmem_base, a_hi, b_lo, idesc, 1u);
+            umma_tf32(tmem_base, a_hi, b_hi, idesc, 1u);
+          }
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(accum_bar);
+    }
+  } else {
+    const int t = threadIdx.x - 64;
+    if (NSPLIT == 3) {
+      for (int kb = 0; kb < nkb; kb++) {
+        const int s = kb % S;
+        const uint32_t ph = (kb / S) & 1;
+        mbar_wait(full_bar(s), ph);
+        float4* stage = reinterpret_cast<float4*>(gen_base + s * Cfg::kStageBytes);
+        split_tf32_inplace(stage, stage + Cfg::kOffAlo / 16, A_TILE / 16, t, 128);
+        split_tf32_inplace(stage + Cfg::kOffBhi / 16, stage + Cfg::kOffBlo / 16, Cfg::kBTile / 16, t, 128);
+        fence_proxy_async_smem();
+        mbar_arrive(xfm_bar(s));
+      }
+    }
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;               // MMA row = pixel (t0 + r/16, f0 + r%16)
+    const int tt = t0 + r / CT_F, ff = f0 + r % CT_F;
+    const bool ok = tt < e.T && ff < e.F;
+    const size_t pix = ((size_t)b * e.T + tt) * e.F + ff;
+    float* orow = e.out + pix * e.Cout;
+    const float* mrow = e.mask ? e.mask + pix * e.Cout : nullptr;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; c++) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), v);
+      if (!ok) continue;
+#pragma unroll
+      for (int j4 = 0; j4 < 8; j4++) {
+        const int col = c * 32 + j4 * 4;
+        float o[4] = {v[j4 * 4 + 0], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]};
+        if (e.bias) {
+          const float4 bb = *reinterpret_cast<const float4*>(e.bias + col);
+          o[0] += bb.x; o[1] += bb.y; o[2] += bb.z; o[3] += bb.w;
+        }
+        if (e.relu) { o[0] = fmaxf(o[0], 0.f); o[1] = fmaxf(o[1], 0.f); o[2] = fmaxf(o[2], 0.f); o[3] = fmaxf(o[3], 0.f); }
+        if (mrow) {
+          const float4 m = *reinterpret_cast<const float4*>(mrow + col);
+          o[0] = m.x > 0.f ? o[0] : 0.f; o[1] = m.y > 0.f ? o[1] : 0.f; o[2] = m.z > 0.f ? o[2] : 0.f; o[3] = m.w > 0.f ? o[3] : 0.f;
+        }
+        *reinterpret_cast<float4*>(orow + col) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+template <int BN, int NSPLIT>
+static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const ConvEpi& e, cudaStream_t st) {
+  using Cfg = ConvCfg<BN, NSPLIT>;
+  auto* kern = tc_conv3x3_kernel<BN, NSPLIT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t r = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (r != cudaSuccess) { set_error("tc_conv: cannot reserve %d bytes of shared memory: %s", Cfg::kSmemBytes, cudaGetErrorString(r)); return B200ASR_CUDA_ERROR; }
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(e.F, CT_F), ceil_div(e.T, CT_T), e.B);
+  kern<<<grid, CONV_THREADS, Cfg::kSmemBytes, st>>>(ma, mb, e);
+  return check_launch("tc_conv3x3");
+}
+
+}  // namespace tc
+
+// wk: [9][Cout][Cin] (K-major weights, produced by conv_repack_k_kernel)
+int conv3x3_tc(const float* in, const float* wk, const float* bias, const float* mask, float* out, int B, int T, int F,
+               int Cin, int Cout, int relu, int precision, cudaStream_t st) {
+  using namespace tc;
+  B200_REQUIRE(precision == 1 || precision == 3, B200ASR_BAD_ARG, "conv3x3_tc: precision must be 1 or 3");
+  B200_REQUIRE(Cin % 32 == 0 && (Cout == 64 || Cout == 128), B200ASR_BAD_SHAPE,
+               "conv3x3_tc: needs Cin %% 32 == 0 and Cout in {64,128} (Cin=%d Cout=%d)", Cin, Cout);
+  B200_REQUIRE(aligned16(in) && aligned16(wk) && aligned16(out) && (!bias || aligned16(bias)) && (!mask || aligned16(mask)),
+               B200ASR_BAD_ALIGN, "conv3x3_tc: pointers must be 16-byte aligned");
+  B200_REQUIRE(B <= 65535 && ceil_div(T, CT_T) <= 65535, B200ASR_BAD_SHAPE, "conv3x3_tc: grid too large");
+  CUtensorMap ma, mb;
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)F, (uint64_t)T, (uint64_t)B};
+    uint64_t strides[3] = {(uint64_t)Cin, (uint64_t)F * Cin, (uint64_t)T * F * Cin};
+    uint32_t box[4] = {32, CT_F, CT_T, 1};
+    int rc = make_tensor_map_f32(&ma, in, 4, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)Cin, (uint64_t)9 * Cout};
+    uint64_t strides[1] = {(uint64_t)Cin};
+    uint32_t box[2] = {32, (uint32_t)Cout};
+    int rc = make_tensor_map_f32(&mb, wk, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  ConvEpi e{out, bias, mask, relu, B, T, F, Cin, Cout};
+  if (Cout == 64) return precision == 1 ? launch_conv<64, 1>(ma, mb, e, st) : launch_conv<64, 3>(ma, mb, e, st);
+  return precision == 1 ? launch_conv<128, 1>(ma, mb, e, st) : launch_conv<128, 3>(ma, mb, e, st);
+}
+
+}  // namespace b200asr

@@ -5,13 +5,6 @@
 #include "kernels.h"
 
 namespace b200asr {
-#ifndef B200ASR_HAVE_TC_GEMM
-int gemm_tc(const float*, bool, int, const float*, bool, int, float*, int, int, int, int, const float*, int, const float*,
-            int, int, cudaStream_t) {
-  set_error("tcgen05 GEMM is not available in this build");
-  return B200ASR_BAD_ARG;
-}
-#endif
 #ifndef B200ASR_HAVE_TC_ATTN
 int sdpa_fwd_tc(const AttnP&, cudaStream_t) {
   set_error("tcgen05 attention is not available in this build");
@@ -23,10 +16,6 @@ int sdpa_bwd_tc(const AttnP&, const float*, float*, float*, float*, float*, cuda
 }
 #endif
 #ifndef B200ASR_HAVE_TC_CONV
-int conv3x3_tc(const float*, const float*, const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t) {
-  set_error("tcgen05 convolution is not available in this build");
-  return B200ASR_BAD_ARG;
-}
 int conv3x3_wgrad_tc(const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t) {
   set_error("tcgen05 convolution weight gradient is not available in this build");
   return B200ASR_BAD_ARG;

@@ -22,9 +22,12 @@ class _Config:
     def __init__(self):
         self.linear = _PREC_NAMES[os.environ.get("B200ASR_LINEAR", "fp32")]
         self.conv = _PREC_NAMES[os.environ.get("B200ASR_CONV", "fp32")]
+        self.conv_wgrad = _PREC_NAMES[os.environ.get("B200ASR_CONV_WGRAD", "fp32")]
         self.attn = _PREC_NAMES[os.environ.get("B200ASR_ATTN", "fp32")]
 
-    def set(self, linear=None, conv=None, attn=None):
+    def set(self, linear=None, conv=None, attn=None, conv_wgrad=None):
+        if conv_wgrad is not None:
+            self.conv_wgrad = _PREC_NAMES[conv_wgrad] if isinstance(conv_wgrad, str) else int(conv_wgrad)
         if linear is not None:
             self.linear = _PREC_NAMES[linear] if isinstance(linear, str) else int(linear)
         if conv is not None:
@@ -63,8 +66,54 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+class _Profiler:
+    """Optional CUDA-event timing of every C-ABI call (bench.py uses it for per-kernel-group durations).
+    Events are recorded on the launching stream around the call; nothing synchronises until report()."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []
+
+    def start(self):
+        self.records, self.enabled = [], True
+
+    def stop(self):
+        self.enabled = False
+
+    def report(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, args, e0, e1 in self.records:
+            out.setdefault(name, []).append((args, e0.elapsed_time(e1)))
+        return out        # name -> [(raw C-ABI args, milliseconds)]
+
+
+profiler = _Profiler()
+
+
+class _ProfiledLib:
+    def __init__(self, lib):
+        self._lib = lib
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if not name.startswith("b200asr_") or name.endswith("_bytes"):
+            return fn
+
+        def call(*args):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*args)
+            e1.record()
+            profiler.records.append((name[len("b200asr_"):], args, e0, e1))
+            return rc
+
+        return call
+
+
 def _lib():
-    return L.load()
+    lib = L.load()
+    return _ProfiledLib(lib) if profiler.enabled else lib
 
 
 def _need_cuda(*ts):
@@ -309,13 +358,13 @@ class VggFrontendFn(torch.autograd.Function):
         p2 = new(B, T4, F4, C2)
         L.check(lib.b200asr_maxpool2x2_fwd(L.ptr(y4), L.ptr(p2), B, T2, F2, C2, st), "pool2")
         ctx.save_for_backward(x, y1, y2, p1, y3, y4, w0, w2, w5, w7)
-        ctx.prec = prec
+        ctx.prec, ctx.prec_w = prec, config.conv_wgrad
         return p2
 
     @staticmethod
     def backward(ctx, dp2):
         x, y1, y2, p1, y3, y4, w0, w2, w5, w7 = ctx.saved_tensors
-        lib, st, prec = _lib(), _stream(), ctx.prec
+        lib, st, prec, prec_w = _lib(), _stream(), ctx.prec, ctx.prec_w
         B, _, F, T = x.shape
         C1, C2 = w0.shape[0], w5.shape[0]
         T2, F2 = T // 2, F // 2
@@ -327,14 +376,14 @@ class VggFrontendFn(torch.autograd.Function):
         L.check(lib.b200asr_maxpool2x2_bwd(L.ptr(dp2), L.ptr(y4), L.ptr(d4), B, T2, F2, C2, 1, st), "pool2_bwd")
         dw7, db7 = torch.empty_like(w7), new(C2)
         L.check(lib.b200asr_conv3x3_bwd_weight(L.ptr(d4), L.ptr(y3), L.ptr(dw7), L.ptr(db7), L.ptr(ws), B, T2, F2, C2, C2,
-                                               prec, st), "conv4_wgrad")
+                                               prec_w, st), "conv4_wgrad")
         d3 = new(B, T2, F2, C2)
         L.check(lib.b200asr_conv3x3_bwd_data(L.ptr(d4), L.ptr(_f32c(w7)), L.ptr(y3), L.ptr(d3), L.ptr(ws), B, T2, F2, C2, C2,
                                              prec, st), "conv4_dgrad")
         del d4
         dw5, db5 = torch.empty_like(w5), new(C2)
         L.check(lib.b200asr_conv3x3_bwd_weight(L.ptr(d3), L.ptr(p1), L.ptr(dw5), L.ptr(db5), L.ptr(ws), B, T2, F2, C1, C2,
-                                               prec, st), "conv3_wgrad")
+                                               prec_w, st), "conv3_wgrad")
         dp1 = new(B, T2, F2, C1)
         L.check(lib.b200asr_conv3x3_bwd_data(L.ptr(d3), L.ptr(_f32c(w5)), None, L.ptr(dp1), L.ptr(ws), B, T2, F2, C1, C2,
                                              prec, st), "conv3_dgrad")
@@ -343,7 +392,7 @@ class VggFrontendFn(torch.autograd.Function):
         L.check(lib.b200asr_maxpool2x2_bwd(L.ptr(dp1), L.ptr(y2), L.ptr(d2), B, T, F, C1, 1, st), "pool1_bwd")
         dw2, db2 = torch.empty_like(w2), new(C1)
         L.check(lib.b200asr_conv3x3_bwd_weight(L.ptr(d2), L.ptr(y1), L.ptr(dw2), L.ptr(db2), L.ptr(ws), B, T, F, C1, C1,
-                                               prec, st), "conv2_wgrad")
+                                               prec_w, st), "conv2_wgrad")
         d1 = new(B, T, F, C1)
         L.check(lib.b200asr_conv3x3_bwd_data(L.ptr(d2), L.ptr(_f32c(w2)), L.ptr(y1), L.ptr(d1), L.ptr(ws), B, T, F, C1, C1,
                                              prec, st), "conv2_dgrad")

@@ -46,6 +46,8 @@ int b200asr_version(void);
 const char* b200asr_last_error(void);
 /* 0 iff the current device is an sm_100 part (B200).  Called by the loader; everything else assumes it. */
 int b200asr_device_check(void);
+/* Number of CUDA kernels this library has launched in the process so far (bench.py reports the per-step delta). */
+unsigned long long b200asr_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Dense layers.  Replaces nn.Linear / nn.Conv1d(k=1) dispatches:
