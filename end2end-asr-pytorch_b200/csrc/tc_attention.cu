@@ -1,0 +1,266 @@
+// Fused attention forward on tcgen05 (precision 1): S = Q K^T and O = P V are tensor-core tiles fed by TMA; scale, masks,
+// softmax and dropout run on the accumulator in TMEM, so scores never touch shared or global memory.
+//
+// One CTA = one (utterance, head, 128-query tile).  The whole score row block 128 x Tk (Tk <= 448) lives in TMEM:
+//   columns [0, Tk32)      S (fp32), later overwritten in place by P (rounded to TF32)
+//   columns [448, 448+DV)  O accumulator
+// warp 0: TMA producer (Q, all K blocks, then a ring of 64-key V blocks)
+// warp 1: MMA issuer   (SS-MMA  S_j = Q K_j^T per 128-key block;  TS-MMA  O += P[tmem] V[smem] per 8 keys)
+// warps 2-5: one thread per query row: pass 1 row max, pass 2 p = exp(s - max) -> TMEM, row sum; epilogue O / sum.
+// Exact (two-pass) softmax: no online rescaling of O is needed because the full row is resident.
+// Layout notes: Q/K tiles are K-major (128B swizzle); V is consumed as an MN-major B operand (dv contiguous), which for
+// fp32/tf32 requires the 128B swizzle with 32-byte atoms.  Strided (B,H,T,d) views are addressed through 4-D tensor maps.
+#include <math.h>
+
+#include "../../include/b200asr.h"
+#include "attention.h"
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace b200asr {
+namespace tc {
+
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_MAX_TK = 448;
+constexpr int ATT_O_COL = 448;
+constexpr int ATT_VSTAGES = 3;
+
+template <int DK, int DV> struct AttCfg {
+  static constexpr int kQBytes = (DK / 32) * 16384;
+  static constexpr int kKBlockBytes = (DK / 32) * 16384;          // 128 keys
+  static constexpr int kKBytes = 4 * kKBlockBytes;
+  static constexpr int kVStageBytes = (DV / 32) * 8192;           // 64 keys
+  static constexpr int kOffK = kQBytes;
+  static constexpr int kOffV = kOffK + kKBytes;
+  static constexpr int kOffPad = kOffV + ATT_VSTAGES * kVStageBytes;   // key_pad bytes (512)
+  static constexpr int kOffBar = kOffPad + 512;
+  static constexpr int kSmemBytes = kOffBar + 256 + 1024;
+};
+
+template <int DK, int DV>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+tc_sdpa_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                   const __grid_constant__ CUtensorMap mapV, const AttnP p) {
+  using Cfg = AttCfg<DK, DV>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t sQ = smem_base, sK = smem_base + Cfg::kOffK, sV = smem_base + Cfg::kOffV;
+  uint8_t* pad_smem = gen_base + Cfg::kOffPad;
+  const uint32_t bar_base = smem_base + Cfg::kOffBar;
+  // barriers: qk_full[4], s_full, p_ready[7], v_full[3], v_empty[3], o_full, tmem slot
+  auto qk_full = [&](int j) { return bar_base + 8u * j; };
+  const uint32_t s_full = bar_base + 8u * 4;
+  auto p_ready = [&](int j) { return bar_base + 8u * (5 + j); };
+  auto v_full = [&](int s) { return bar_base + 8u * (12 + s); };
+  auto v_empty = [&](int s) { return bar_base + 8u * (15 + s); };
+  const uint32_t o_full = bar_base + 8u * 18;
+  const uint32_t tmem_slot = bar_base + 8u * 19;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int Tk = p.Tk;
+  const int tk32 = (Tk + 31) & ~31;                 // score columns computed (keys >= Tk are masked)
+  const int nkblk = (tk32 + 127) / 128;             // 128-key blocks of S
+  const int nvblk = (tk32 + 63) / 64;               // 64-key blocks of P / V
+
+  if (threadIdx.x == 0) {
+    for (int j = 0; j < 4; j++) mbar_init(qk_full(j), 1);
+    mbar_init(s_full, 1);
+    for (int j = 0; j < 7; j++) mbar_init(p_ready(j), 128);
+    for (int s = 0; s < ATT_VSTAGES; s++) { mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&mapQ); tma_prefetch_desc(&mapK); tma_prefetch_desc(&mapV);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      for (int j = 0; j < nkblk; j++) {
+        mbar_expect_tx(qk_full(j), Cfg::kKBlockBytes + (j == 0 ? Cfg::kQBytes : 0));
+        if (j == 0)
+#pragma unroll
+          for (int sub = 0; sub < DK / 32; sub++) tma_load_4d(sQ + sub * 16384, &mapQ, qk_full(0), sub * 32, q0, h, b);
+#pragma unroll
+        for (int sub = 0; sub < DK / 32; sub++)
+          tma_load_4d(sK + j * Cfg::kKBlockBytes + sub * 16384, &mapK, qk_full(j), sub * 32, j * 128, h, b);
+      }
+      for (int vb = 0; vb < nvblk; vb++) {
+        const int s = vb % ATT_VSTAGES;
+        const uint32_t ph = (vb / ATT_VSTAGES) & 1;
+        mbar_wait(v_empty(s), ph ^ 1);
+        mbar_expect_tx(v_full(s), Cfg::kVStageBytes);
+#pragma unroll
+        for (int ch = 0; ch < DV / 32; ch++)
+          tma_load_4d(sV + s * Cfg::kVStageBytes + ch * 8192, &mapV, v_full(s), ch * 32, vb * 64, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- MMA issuer
+      for (int j = 0; j < nkblk; j++) {
+        const int nj = min(128, tk32 - j * 128);
+        const uint32_t idesc = make_idesc_tf32(128, nj, false, false);
+        mbar_wait(qk_full(j), 0);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < DK / 8; ks++) {
+          const uint32_t off = (ks >> 2) * 16384 + (ks & 3) * 32;
+          const uint64_t a = make_smem_desc(sQ + off, 16, 1024);
+          const uint64_t bd = make_smem_desc(sK + j * Cfg::kKBlockBytes + off, 16, 1024);
+          umma_tf32(tmem_base + (uint32_t)(j * 128), a, bd, idesc, ks != 0 ? 1u : 0u);
+        }
+      }
+      umma_commit(s_full);
+      const uint32_t idesc_pv = make_idesc_tf32(128, DV, false, true);
+      for (int vb = 0; vb < nvblk; vb++) {
+        const int s = vb % ATT_VSTAGES;
+        const uint32_t ph = (vb / ATT_VSTAGES) & 1;
+        mbar_wait(p_ready(vb), 0);
+        mbar_wait(v_full(s), ph);
+        tc_fence_after();
+        const int ksteps = min(64, tk32 - vb * 64) / 8;
+        for (int ks = 0; ks < ksteps; ks++) {
+          const uint64_t bd = make_smem_desc(sV + s * Cfg::kVStageBytes + ks * 1024, 8192, 512, kLayoutSW128Base32B);
+          const uint32_t a_tmem = tmem_base + (uint32_t)(vb * 64 + ks * 8);
+          const uint32_t acc = (vb | ks) != 0 ? 1u : 0u;
+          asm volatile(
+              "{\n"
+              ".reg .pred p;\n"
+              "setp.ne.b32 p, %4, 0;\n"
+              "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+              "}\n" ::"r"(tmem_base + (uint32_t)ATT_O_COL),
+              "r"(a_tmem), "l"(bd), "r"(idesc_pv), "r"(acc)
+              : "memory");
+        }
+        umma_commit(v_empty(s));
+      }
+      umma_commit(o_full);
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + epilogue: one thread per query row
+    const int t = threadIdx.x - 64;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int q = q0 + row;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    for (int i = t; i < 512; i += 128) pad_smem[i] = (i < Tk && p.key_pad) ? p.key_pad[(size_t)b * Tk + i] : (i < Tk ? 0 : 1);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const uint8_t* drow = (p.dense && q < p.Tq) ? p.dense + ((size_t)b * p.Tq + q) * Tk : nullptr;
+    const int kcausal = p.causal ? q : 0x7fffffff;   // keys > kcausal are masked
+    const float scale = p.scale;
+    mbar_wait(s_full, 0);
+    tc_fence_after();
+    const int nchunk = tk32 / 32;
+    float m = -INFINITY;
+    for (int c = 0; c < nchunk; c++) {
+      float v[32];
+      tmem_ld32(lane_addr + (uint32_t)(c * 32), v);
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        const int key = c * 32 + j;
+        const bool masked = pad_smem[key] || key > kcausal || (drow && drow[key]);
+        if (!masked) m = fmaxf(m, v[j] * scale);
+      }
+    }
+    float l = 0.f;
+    const size_t drop_row = (((size_t)b * p.H + h) * p.Tq + q) * (size_t)Tk;
+    for (int c = 0; c < nchunk; c++) {
+      float v[32];
+      tmem_ld32(lane_addr + (uint32_t)(c * 32), v);
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        const int key = c * 32 + j;
+        const bool masked = pad_smem[key] || key > kcausal || (drow && drow[key]);
+        float s = masked ? -INFINITY : v[j] * scale;
+        float e = __expf(s - m);                       // fully masked row: -inf - -inf = NaN, as the reference
+        uint32_t u;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(e));
+        e = __uint_as_float(u);
+        l += e;
+        if (p.thresh && key < Tk) e = dropout_keep(p.key, drop_row + key, p.thresh) ? e * p.inv_keep : 0.f;
+        v[j] = e;
+      }
+      tmem_st32(lane_addr + (uint32_t)(c * 32), v);
+      if ((c & 1) || c == nchunk - 1) {
+        tc_fence_before();
+        mbar_arrive(p_ready(c >> 1));
+      }
+    }
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv = 1.f / l;
+    const bool ok = q < p.Tq;
+    float* orow = p.o + b * p.o_bs + h * p.o_hs + (long long)q * p.o_rs;
+#pragma unroll 1
+    for (int c = 0; c < DV / 32; c++) {
+      float v[32];
+      tmem_ld32(lane_addr + (uint32_t)(ATT_O_COL + c * 32), v);
+      if (!ok) continue;
+#pragma unroll
+      for (int j4 = 0; j4 < 8; j4++)
+        *reinterpret_cast<float4*>(orow + c * 32 + j4 * 4) =
+            make_float4(v[j4 * 4] * inv, v[j4 * 4 + 1] * inv, v[j4 * 4 + 2] * inv, v[j4 * 4 + 3] * inv);
+    }
+    if (ok && p.lse) p.lse[((size_t)b * p.H + h) * p.Tq + q] = m + logf(l);
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int make_bhtd_map(CUtensorMap* m, const float* base, int d, int T, int H, int B, long long rs, long long hs, long long bs,
+                         int box_rows, bool atom32b) {
+  uint64_t dims[4] = {(uint64_t)d, (uint64_t)T, (uint64_t)H, (uint64_t)B};
+  uint64_t strides[3] = {(uint64_t)rs, (uint64_t)hs, (uint64_t)bs};
+  uint32_t box[4] = {32, (uint32_t)box_rows, 1, 1};
+  return make_tensor_map_f32(m, base, 4, dims, strides, box, atom32b);
+}
+
+template <int DK, int DV>
+static int launch_att(const AttnP& p, cudaStream_t st) {
+  using Cfg = AttCfg<DK, DV>;
+  CUtensorMap mq, mk, mv;
+  int rc = make_bhtd_map(&mq, p.q, DK, p.Tq, p.H, p.B, p.q_rs, p.q_hs, p.q_bs, 128, false);
+  if (rc) return rc;
+  rc = make_bhtd_map(&mk, p.k, DK, p.Tk, p.H, p.B, p.k_rs, p.k_hs, p.k_bs, 128, false);
+  if (rc) return rc;
+  rc = make_bhtd_map(&mv, p.v, DV, p.Tk, p.H, p.B, p.v_rs, p.v_hs, p.v_bs, 64, true);
+  if (rc) return rc;
+  auto* kern = tc_sdpa_fwd_kernel<DK, DV>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t r = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (r != cudaSuccess) { set_error("tc_sdpa_fwd: cannot reserve %d bytes of shared memory: %s", Cfg::kSmemBytes, cudaGetErrorString(r)); return B200ASR_CUDA_ERROR; }
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(p.Tq, 128), p.H, p.B);
+  kern<<<grid, ATT_THREADS, Cfg::kSmemBytes, st>>>(mq, mk, mv, p);
+  return check_launch("tc_sdpa_fwd");
+}
+
+}  // namespace tc
+
+int sdpa_fwd_tc(const AttnP& p, cudaStream_t st) {
+  using namespace tc;
+  B200_REQUIRE(p.Tk <= ATT_MAX_TK, B200ASR_BAD_SHAPE, "sdpa_fwd (tcgen05): Tk=%d exceeds %d resident score columns; use precision 0", p.Tk, ATT_MAX_TK);
+  B200_REQUIRE(p.H <= 65535 && p.B <= 65535, B200ASR_BAD_SHAPE, "sdpa_fwd (tcgen05): grid too large");
+  if (p.dk == 64 && p.dv == 64) return launch_att<64, 64>(p, st);
+  if (p.dk == 32 && p.dv == 32) return launch_att<32, 32>(p, st);
+  if (p.dk == 64 && p.dv == 32) return launch_att<64, 32>(p, st);
+  if (p.dk == 32 && p.dv == 64) return launch_att<32, 64>(p, st);
+  set_error("sdpa_fwd (tcgen05): (dk=%d, dv=%d) unsupported, needs dk, dv in {32, 64}; use precision 0", p.dk, p.dv);
+  return B200ASR_BAD_SHAPE;
+}
+
+}  // namespace b200asr

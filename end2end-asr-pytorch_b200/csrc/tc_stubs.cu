@@ -6,10 +6,6 @@
 
 namespace b200asr {
 #ifndef B200ASR_HAVE_TC_ATTN
-int sdpa_fwd_tc(const AttnP&, cudaStream_t) {
-  set_error("tcgen05 attention is not available in this build");
-  return B200ASR_BAD_ARG;
-}
 int sdpa_bwd_tc(const AttnP&, const float*, float*, float*, float*, float*, cudaStream_t) {
   set_error("tcgen05 attention backward is not available in this build");
   return B200ASR_BAD_ARG;

@@ -173,6 +173,7 @@ def _front_end(self, padded_input):
 
 def transformer_forward(self, padded_input, input_lengths, padded_target, verbose=False):
     """Transformer.forward -> (pred, gold, hyp_seq, gold_seq) -- models/asr/transformer.py:59-85."""
+    ops._need_cuda(padded_input, padded_target)
     feats, cf = _front_end(self, padded_input)
     enc = _encoder_body(self.encoder, feats, input_lengths, cf)
     pred, gold, *_ = decoder_forward(self.decoder, padded_target, enc, input_lengths)

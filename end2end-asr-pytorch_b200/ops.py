@@ -24,8 +24,11 @@ class _Config:
         self.conv = _PREC_NAMES[os.environ.get("B200ASR_CONV", "fp32")]
         self.conv_wgrad = _PREC_NAMES[os.environ.get("B200ASR_CONV_WGRAD", "fp32")]
         self.attn = _PREC_NAMES[os.environ.get("B200ASR_ATTN", "fp32")]
+        self.attn_bwd = _PREC_NAMES[os.environ.get("B200ASR_ATTN_BWD", "fp32")]
 
-    def set(self, linear=None, conv=None, attn=None, conv_wgrad=None):
+    def set(self, linear=None, conv=None, attn=None, conv_wgrad=None, attn_bwd=None):
+        if attn_bwd is not None:
+            self.attn_bwd = _PREC_NAMES[attn_bwd] if isinstance(attn_bwd, str) else int(attn_bwd)
         if conv_wgrad is not None:
             self.conv_wgrad = _PREC_NAMES[conv_wgrad] if isinstance(conv_wgrad, str) else int(conv_wgrad)
         if linear is not None:
@@ -157,6 +160,12 @@ def linear_bwd_weight(dy2, x2, want_bias, prec):
     return dw, db
 
 
+def _linear_prec(N, K):
+    """Shape rule (documented in DESIGN.md, not a fallback): TMA needs 16-byte row pitches, i.e. N % 4 == 0 and
+    K % 4 == 0; other shapes (e.g. dim_input = 161 with feat_extractor='') run on the fp32 CUDA-core GEMM."""
+    return config.linear if (N % 4 == 0 and K % 4 == 0) else L.PREC_FP32
+
+
 class LinearFn(torch.autograd.Function):
     """y = x W^T + b   (nn.Linear / Conv1d(k=1) call sites, include/b200asr.h)."""
 
@@ -165,7 +174,7 @@ class LinearFn(torch.autograd.Function):
         _need_cuda(x, w, b)
         w2 = _f32c(w.reshape(w.shape[0], -1))
         x2 = _f32c(x).reshape(-1, w2.shape[1])
-        ctx.prec = config.linear
+        ctx.prec = _linear_prec(w2.shape[0], w2.shape[1])
         y = linear_fwd(x2, w2, b, False, ctx.prec)
         ctx.save_for_backward(x2, w2)
         ctx.xshape, ctx.wshape, ctx.has_bias = x.shape, w.shape, b is not None
@@ -193,7 +202,7 @@ class FFNFn(torch.autograd.Function):
         w1m = _f32c(w1.reshape(w1.shape[0], -1))
         w2m = _f32c(w2.reshape(w2.shape[0], -1))
         x2 = _f32c(x).reshape(-1, w1m.shape[1])
-        ctx.prec = config.linear
+        ctx.prec = _linear_prec(w1m.shape[0], w1m.shape[1])
         h = linear_fwd(x2, w1m, b1, True, ctx.prec)
         y = linear_fwd(h, w2m, b2, False, ctx.prec)
         ctx.save_for_backward(x2, h, w1m, w2m)
@@ -282,13 +291,14 @@ class SdpaFn(torch.autograd.Function):
             out = torch.empty((B, Tq, H, dv), device=q.device, dtype=torch.float32).permute(0, 2, 1, 3)
         lse = torch.empty((B, H, Tq), device=q.device, dtype=torch.float32)
         seed, off = rng.next() if p_drop > 0.0 else (0, 0)
-        prec = config.attn
+        # shape rule (not a fallback): the tcgen05 kernel keeps the whole score row in TMEM (Tk <= 448, d in {32,64})
+        prec = config.attn if (Tk <= 448 and dk in (32, 64) and dv in (32, 64)) else L.PREC_FP32
         qs, ks, vs, os_ = _bhtd_strides(q), _bhtd_strides(k), _bhtd_strides(v), _bhtd_strides(out)
         L.check(_lib().b200asr_sdpa_fwd(L.ptr(q), L.ptr(k), L.ptr(v), *qs, *ks, *vs, L.ptr(key_pad), L.ptr(dense_mask),
                                         int(causal), L.ptr(out), *os_, L.ptr(lse), B, H, Tq, Tk, dk, dv, float(scale),
                                         float(p_drop), seed, off, prec, _stream()), "sdpa_fwd")
         ctx.save_for_backward(q, k, v, out, lse, key_pad, dense_mask)
-        ctx.meta = (int(causal), float(scale), float(p_drop), seed, off, prec)
+        ctx.meta = (int(causal), float(scale), float(p_drop), seed, off, config.attn_bwd)
         return out
 
     @staticmethod
@@ -408,6 +418,7 @@ class PermuteColsFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, w, C, F):
+        _need_cuda(w)
         w = _f32c(w)
         out = torch.empty_like(w)
         L.check(_lib().b200asr_permute_cols_cf(L.ptr(w), L.ptr(out), w.shape[0], C, F, 0, _stream()), "permute_cols")
@@ -483,6 +494,7 @@ class FlattenFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x):
+        _need_cuda(x)
         x = _f32c(x)
         B, C, F, T = x.shape
         out = torch.empty((B, T, C * F), device=x.device, dtype=torch.float32)

@@ -29,10 +29,13 @@ class DataParallelStep:
     """zero_grad -> forward -> CE(sum) -> backward -> single all-reduce -> Adam(1/global_tokens)."""
 
     def __init__(self, model, model_size, warmup=4000, k_lr=1.0, min_lr=1e-5, smoothing=0.0, process_group=None,
-                 clip_max_norm=None):
+                 clip_max_norm=None, loss_fn=None, adam_factory=None):
+        """loss_fn(pred, gold, smoothing, reduction='sum') -> (loss_sum, stats[sum, n_tokens, ...]) and
+        adam_factory(flat) default to the CUDA kernels; the gloo/CPU tests of the host protocol inject stand-ins."""
         self.model = model
         self.flat = FlatParams(model, extra=2)
-        self.adam = FusedAdam(self.flat, betas=(0.9, 0.98), eps=1e-9)
+        self.loss_fn = loss_fn or metrics.loss_and_stats
+        self.adam = (adam_factory or (lambda f: FusedAdam(f, betas=(0.9, 0.98), eps=1e-9)))(self.flat)
         self.opt = NoamOpt(model_size, k_lr, warmup, self.adam, min_lr=min_lr)
         self.smoothing = smoothing
         self.pg = process_group
@@ -44,7 +47,7 @@ class DataParallelStep:
         """Local shard fwd+bwd with the un-normalised loss; gradients land in the flat buffer."""
         self.flat.zero_grad()
         pred, gold, hyp, _ = self.model(src, lengths, tgt)
-        loss_sum, stats = metrics.loss_and_stats(pred, gold, self.smoothing, reduction="sum")
+        loss_sum, stats = self.loss_fn(pred, gold, self.smoothing, reduction="sum")
         loss_sum.backward()
         self.flat.ensure_grad_views()
         self.flat.extras.copy_(stats[0:2])            # [sum-loss, n_tokens] ride with the gradients

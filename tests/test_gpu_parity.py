@@ -206,13 +206,32 @@ def test_attention_fully_masked_row_is_nan_like_reference(b200):
     assert torch.isnan(o).all()
 
 
+def _pool_windows_well_separated(h, rel_gap=1e-4):
+    """True if no 2x2 max-pool window of h (B,C,F,T) has its two largest entries within rel_gap of each other
+    (unless the max is <= 0, where the ReLU mask zeroes the gradient anyway).  Max-pool routing is discontinuous:
+    a near-tie lets fp32 rounding noise move the whole gradient to the neighbouring pixel (observed: values
+    0.00735714 vs 0.00735718), so parity inputs must avoid them -- the reference has the same sensitivity."""
+    B, C, Fh, Tw = h.shape
+    w = h[:, :, :Fh // 2 * 2, :Tw // 2 * 2].reshape(B, C, Fh // 2, 2, Tw // 2, 2).permute(0, 1, 2, 4, 3, 5).reshape(B, C, Fh // 2, Tw // 2, 4)
+    top = w.topk(2, dim=-1).values
+    live = top[..., 0] > 0
+    gap = (top[..., 0] - top[..., 1])[live]
+    return bool((gap > rel_gap * h.abs().max()).all())
+
+
 @pytest.mark.parametrize("B,F_,T", [(2, 41, 24), (1, 161, 12), (3, 23, 10)])
 def test_vgg_frontend_fwd_bwd(b200, B, F_, T):
     ops = _ops(b200)
     cfg = O.OracleConfig(num_layers=1, feat_extractor="vgg_cnn", freq=F_)
     P = {k: v.requires_grad_(True) for k, v in O.init_params(cfg, seed=5).items() if k.startswith("conv.")}
-    g = torch.Generator().manual_seed(4)
-    x = torch.randn(B, 1, F_, T, generator=g)
+    for seed in range(4, 40):                                 # first input without max-pool near-ties
+        g = torch.Generator().manual_seed(seed)
+        x = torch.randn(B, 1, F_, T, generator=g)
+        with torch.no_grad():
+            h2 = F.relu(F.conv2d(F.relu(F.conv2d(x, P["conv.0.weight"], P["conv.0.bias"], padding=1)), P["conv.2.weight"], P["conv.2.bias"], padding=1))
+            h4 = F.relu(F.conv2d(F.relu(F.conv2d(F.max_pool2d(h2, 2, 2), P["conv.5.weight"], P["conv.5.bias"], padding=1)), P["conv.7.weight"], P["conv.7.bias"], padding=1))
+        if _pool_windows_well_separated(h2) and _pool_windows_well_separated(h4):
+            break
     y = O.vgg_frontend(x, P)                                  # (B,128,F/4,T/4)
     dy = torch.randn(y.shape, generator=g)
     y.backward(dy)

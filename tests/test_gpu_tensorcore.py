@@ -72,3 +72,68 @@ def test_unaligned_shapes_are_rejected_not_rerouted(L):
     x = torch.randn(8, 161).cuda(); w = torch.randn(16, 161).cuda(); y = torch.empty(8, 16).cuda()
     rc = lib.b200asr_linear_fwd(L.ptr(x), L.ptr(w), None, L.ptr(y), 8, 16, 161, 0, 3, _stream())
     assert rc == -1 and "multiples of 4" in L.last_error()
+
+
+# ------------------------------------------------------------------------------------------------ convolution
+def _conv_case(L, B, T, F_, Ci, Co, seed=0):
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, Ci, F_, T, generator=g)
+    w = torch.randn(Co, Ci, 3, 3, generator=g) * 0.1
+    b = torch.randn(Co, generator=g)
+    y = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    dy = torch.randn(B, Co, F_, T, generator=g)
+    dx = torch.nn.grad.conv2d_input(x.shape, w.double(), dy.double(), padding=1)
+    nhwc = lambda t: t.permute(0, 3, 2, 1).contiguous()
+    return nhwc(x).cuda(), w.cuda(), b.cuda(), nhwc(y), nhwc(dy).cuda(), nhwc(dx)
+
+
+@pytest.mark.parametrize("prec,tol", [(1, 2e-3), (3, 2e-5)])
+@pytest.mark.parametrize("B,T,F_,Ci,Co", [(2, 16, 32, 64, 64), (1, 9, 21, 64, 128), (3, 24, 41, 128, 128), (2, 10, 23, 64, 64),
+                                          (1, 40, 161, 64, 64)])
+def test_conv3x3_forward_and_dgrad_tensor_core(L, B, T, F_, Ci, Co, prec, tol):
+    lib = L.load()
+    x, w, b, y_ref, dy, dx_ref = _conv_case(L, B, T, F_, Ci, Co, seed=B + T)
+    ws = torch.empty(9 * Ci * Co, device="cuda")
+    y = torch.full((B, T, F_, Co), float("nan"), device="cuda")
+    L.check(lib.b200asr_conv3x3_fwd(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), L.ptr(ws), B, T, F_, Ci, Co, 0, prec, _stream()), "conv fwd")
+    assert rel_err(y, y_ref) < tol
+    y2 = torch.empty_like(y)
+    L.check(lib.b200asr_conv3x3_fwd(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y2), L.ptr(ws), B, T, F_, Ci, Co, 1, prec, _stream()), "conv fwd relu")
+    assert rel_err(y2, y_ref.relu()) < tol
+    dx = torch.full((B, T, F_, Ci), float("nan"), device="cuda")
+    mask = torch.randn(B, T, F_, Ci, device="cuda")
+    L.check(lib.b200asr_conv3x3_bwd_data(L.ptr(dy), L.ptr(w), L.ptr(mask), L.ptr(dx), L.ptr(ws), B, T, F_, Ci, Co, prec, _stream()), "conv dgrad")
+    assert rel_err(dx, dx_ref.cuda() * (mask > 0)) < tol
+
+
+# ------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("B,H,Tq,Tk,dk,dv,mode", [
+    (2, 2, 50, 50, 64, 64, "keypad"), (3, 4, 13, 13, 32, 32, "causal+keypad"), (2, 8, 100, 200, 64, 64, "keypad"),
+    (2, 3, 70, 70, 64, 32, "dense"), (1, 2, 129, 65, 32, 64, "none"), (2, 2, 100, 100, 64, 64, "causal"),
+    (1, 1, 200, 200, 64, 64, "keypad"), (1, 2, 300, 448, 64, 64, "keypad"), (2, 2, 257, 400, 64, 64, "none"),
+])
+def test_attention_forward_tensor_core(L, B, H, Tq, Tk, dk, dv, mode):
+    import importlib
+    import b200asr
+    from tests.test_gpu_parity import _attention_case
+    ops = importlib.import_module(b200asr.__name__ + ".ops")
+    old = (ops.config.attn, ops.config.attn_bwd)
+    ops.config.set(attn="tf32", attn_bwd="fp32")
+    try:
+        pairs = _attention_case(ops, B, H, Tq, Tk, dk, dv, mode)
+    finally:
+        ops.config.attn, ops.config.attn_bwd = old
+    (got, ref) = pairs[0]
+    assert rel_err(got, ref) < 2e-3
+    for got, ref in pairs[1:]:          # backward (fp32 kernel) consumes the tcgen05 forward's O and LSE
+        assert rel_err(got, ref) < 3e-3
+
+
+def test_attention_tensor_core_rejects_long_keys(L):
+    lib = L.load()
+    q = torch.randn(1, 1, 64, 64, device="cuda"); k = torch.randn(1, 1, 500, 64, device="cuda"); v = torch.randn(1, 1, 500, 64, device="cuda")
+    o = torch.empty(1, 1, 64, 64, device="cuda"); lse = torch.empty(1, 1, 64, device="cuda")
+    rc = lib.b200asr_sdpa_fwd(L.ptr(q), L.ptr(k), L.ptr(v), 4096, 4096, 64, 32000, 32000, 64, 32000, 32000, 64, None, None, 0,
+                              L.ptr(o), 4096, 4096, 64, L.ptr(lse), 1, 1, 64, 500, 64, 64, 0.125, 0.0, 0, 0, 1, _stream())
+    assert rc == -1 and "precision 0" in L.last_error()

@@ -1,0 +1,112 @@
+"""CPU tests of the host-side mirror: configuration arithmetic, state_dict compatibility with the reference, schedules,
+sharding, flat buffers, the install() patcher and the "CUDA only" contract."""
+import importlib
+import os
+import sys
+import types
+
+import pytest
+import torch
+
+import b200asr
+from oracle import asr_oracle as O
+from tests.helpers import GOLDEN_CASES, load_golden
+
+
+def test_config_dims_follow_reference_formulae():
+    assert b200asr.ASRConfig(feat_extractor="vgg_cnn").dim_input == 5120          # utils/functions.py:128-130
+    assert b200asr.ASRConfig(feat_extractor="emb_cnn").dim_input == 672           # utils/functions.py:121-126
+    assert b200asr.ASRConfig(feat_extractor="").dim_input == 161
+    assert b200asr.ASRConfig().t_enc(800) == 200 and b200asr.ASRConfig(feat_extractor="emb_cnn").t_enc(400) == 195
+    c2 = b200asr.BASELINE_CONFIGS["cfg2"]
+    assert (c2["batch"], c2["t_src"], c2["cfg"].tgt_max_len, c2["cfg"].vocab) == (32, 800, 100, 4364)
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_mirror_state_dict_is_reference_compatible(case):
+    """Parameter names/shapes equal the reference's (fixtures hold its state_dict), so checkpoints round-trip."""
+    from tests.gpu_util import asr_cfg
+    cfg, P, _, _, _ = load_golden(case)
+    m = b200asr.build_model(asr_cfg(cfg))
+    sd = {k: v for k, v in m.state_dict().items() if not (k.endswith("positional_encoding.pe") or "running_" in k or "num_batches" in k)}
+    assert set(sd) == set(P)
+    for k in P:
+        assert tuple(sd[k].shape) == tuple(P[k].shape), k
+    assert sum(p.numel() for p in b200asr.build_model(b200asr.ASRConfig()).parameters()) == 36776384
+
+
+def test_noam_schedule_and_shard_batch():
+    opt = b200asr.NoamOpt(5120, 1.0, 4000, types.SimpleNamespace(param_groups=[{"lr": 0}], step=lambda **kw: None, zero_grad=lambda: None), min_lr=1e-6)
+    for s in range(1, 6):
+        opt.step()
+        assert opt._rate == pytest.approx(O.noam_rate(s, 5120, 1.0, 4000, 1e-6))
+    src, lens, tgt = torch.arange(8).view(8, 1), torch.arange(8), torch.arange(8)
+    a = b200asr.shard_batch(src, lens, tgt, 1, 4)
+    assert a[0].view(-1).tolist() == [2, 3] and a[1].tolist() == [2, 3]
+    with pytest.raises(ValueError):
+        b200asr.shard_batch(src, lens, tgt, 0, 3)
+
+
+def test_flat_params_views_alias_one_buffer():
+    lin = torch.nn.Sequential(torch.nn.Linear(5, 3), torch.nn.Linear(3, 2))
+    before = [p.detach().clone() for p in lin.parameters()]
+    flat = b200asr.FlatParams(lin, extra=2)
+    assert flat.flat_grad.numel() == flat.numel + 2 and all(o % 4 == 0 for o in flat.offsets)
+    for p, b in zip(lin.parameters(), before):
+        assert torch.equal(p.detach(), b)
+        assert p.data_ptr() >= flat.flat.data_ptr() and p.grad.data_ptr() >= flat.flat_grad.data_ptr()
+    lin(torch.randn(4, 5)).sum().backward()
+    assert flat.flat_grad[:flat.numel].abs().sum() > 0            # autograd accumulated straight into the flat buffer
+    lin.zero_grad(set_to_none=True)
+    lin(torch.randn(4, 5)).sum().backward()
+    flat.ensure_grad_views()
+    assert all(p.grad.data_ptr() >= flat.flat_grad.data_ptr() for p in lin.parameters())
+
+
+def test_cpu_tensors_are_rejected_not_computed():
+    m = b200asr.build_model(b200asr.ASRConfig(num_layers=1, vocab=40, feat_extractor="", tgt_max_len=6))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.randn(2, 1, 161, 16), torch.tensor([16, 12]), torch.randint(3, 40, (2, 5)))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        b200asr.calculate_metrics(torch.randn(2, 3, 8), torch.ones(2, 3, dtype=torch.long))
+
+
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout only exists in the build container")
+def test_install_rebinds_reference_classes_and_keeps_module_tree():
+    """Runs in a subprocess because the reference parses flags at import (utils/constant.py:99)."""
+    import subprocess
+    code = r'''
+import sys, types
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+sys.modules["Levenshtein"] = types.ModuleType("Levenshtein")
+sys.argv = ["x", "--num-layers", "1", "--num-heads", "2", "--dim-model", "64", "--dim-emb", "64", "--dim-key", "32", "--dim-value", "32",
+            "--dim-inner", "64", "--feat_extractor", "vgg_cnn", "--tgt-max-len", "8", "--sample-rate", "4000"]
+import torch
+from utils import constant
+from utils.functions import init_transformer_model
+import models.common_layers as cl, models.asr.transformer as tr, utils.metrics as um
+import b200asr
+orig = tr.Transformer.forward
+labels = {i: str(i) for i in range(20)}
+model = init_transformer_model(constant.args, {v: k for k, v in labels.items()}, labels)
+keys = list(model.state_dict().keys())
+b200asr.install()
+assert tr.Transformer.forward is not orig and cl.MultiHeadAttention.forward.__module__.endswith("modules")
+assert um.calculate_metrics.__module__.endswith("metrics")
+assert list(model.state_dict().keys()) == keys                      # module tree / names untouched
+try:
+    model(torch.randn(2, 1, 41, 16), torch.tensor([16, 12], dtype=torch.int32), torch.randint(3, 20, (2, 5)))
+    raise SystemExit("expected the CUDA-only error")
+except RuntimeError as e:
+    assert "CUDA" in str(e)
+b200asr.uninstall()
+assert tr.Transformer.forward is orig
+pred, gold, hyp, _ = model(torch.randn(2, 1, 41, 16), torch.tensor([16, 12], dtype=torch.int32), torch.randint(3, 20, (2, 5)))
+assert pred.shape == (2, 8, 20)
+print("OK")
+''' % (REF, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-2000:]

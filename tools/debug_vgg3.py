@@ -23,7 +23,8 @@ q2.backward(dy)
 new = lambda *s: torch.full(s, float('nan'), device='cuda')
 C1, C2 = 64, 128
 T2, F2 = T // 2, F_ // 2
-cu = lambda n: P[n].detach().cuda()
+_keep = {n: P[n].detach().cuda() for n in P}
+cu = lambda n: _keep[n]
 xc = x.cuda()
 ws = torch.empty(9 * C2 * C2, device='cuda')
 y1 = new(B, T, F_, C1); L.check(lib.b200asr_conv3x3_c1_fwd(L.ptr(xc), L.ptr(cu("conv.0.weight")), L.ptr(cu("conv.0.bias")), L.ptr(y1), B, F_, T, C1, 1, st))
@@ -39,9 +40,28 @@ print("d4 %.1e" % rel_err(d4, ref_d4), "nan", int(torch.isnan(d4).sum()))
 dw7 = new(C2, C2, 3, 3); db7 = new(C2)
 L.check(lib.b200asr_conv3x3_bwd_weight(L.ptr(d4), L.ptr(y3), L.ptr(dw7), L.ptr(db7), L.ptr(ws), B, T2, F2, C2, C2, 0, st))
 print("dw7 %.1e db7 %.1e" % (rel_err(dw7, P["conv.7.weight"].grad), rel_err(db7, P["conv.7.bias"].grad)))
+d3 = new(B, T2, F2, C2); L.check(lib.b200asr_conv3x3_bwd_data(L.ptr(d4), L.ptr(cu("conv.7.weight")), L.ptr(y3), L.ptr(d3), L.ptr(ws), B, T2, F2, C2, C2, 0, st))
+print("d3 %.1e" % rel_err(d3, nhwc((h3.grad * (h3 > 0)).detach())))
+dp1 = new(B, T2, F2, C1); L.check(lib.b200asr_conv3x3_bwd_data(L.ptr(d3), L.ptr(cu("conv.5.weight")), None, L.ptr(dp1), L.ptr(ws), B, T2, F2, C1, C2, 0, st))
+print("dp1 %.1e" % rel_err(dp1, nhwc(q1.grad)))
+d2 = new(B, T, F_, C1); L.check(lib.b200asr_maxpool2x2_bwd(L.ptr(dp1), L.ptr(y2), L.ptr(d2), B, T, F_, C1, 1, st))
+print("d2 %.1e" % rel_err(d2, nhwc((h2.grad * (h2 > 0)).detach())))
 # same with the reference tensors as inputs
 rd4 = ref_d4.cuda(); ry3 = nhwc(h3.detach()).cuda()
 L.check(lib.b200asr_conv3x3_bwd_weight(L.ptr(rd4), L.ptr(ry3), L.ptr(dw7), L.ptr(db7), L.ptr(ws), B, T2, F2, C2, C2, 0, st))
 print("dw7(ref inputs) %.1e" % rel_err(dw7, P["conv.7.weight"].grad))
 tw = torch.nn.grad.conv2d_weight(h3.detach(), P["conv.7.weight"].shape, (h4.grad * (h4 > 0)).detach(), padding=1)
 print("torch conv2d_weight vs autograd %.1e" % rel_err(tw, P["conv.7.weight"].grad))
+diff = (d4.cpu() - ref_d4).abs()
+idx = (diff > 1e-4).nonzero()
+print("mismatch count", idx.shape[0], "of", diff.numel())
+y4c = y4.cpu(); h4n = nhwc(h4.detach())
+for k in range(min(6, idx.shape[0])):
+    b_, t_, f_, c_ = idx[k].tolist()
+    t2, f2 = t_ // 2, f_ // 2
+    print((b_, t_, f_, c_), "ours d4", d4[b_, t_, f_, c_].item(), "ref", ref_d4[b_, t_, f_, c_].item())
+    if t2 * 2 + 1 < T2 and f2 * 2 + 1 < F2:
+        print("   window ours", [y4c[b_, 2 * t2 + a, 2 * f2 + bb, c_].item() for a in (0, 1) for bb in (0, 1)])
+        print("   window ref ", [h4n[b_, 2 * t2 + a, 2 * f2 + bb, c_].item() for a in (0, 1) for bb in (0, 1)])
+        print("   dp2", dp2[b_, t2, f2, c_].item())
+print("per-batch err", [rel_err(d4[i], ref_d4[i]) for i in range(B)])
