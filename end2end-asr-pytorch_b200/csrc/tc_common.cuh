@@ -187,9 +187,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode_tiled();
 // fp32 tensor, `rank` dims (innermost first), strides in ELEMENTS for dims 1..rank-1 (dim 0 is contiguous), 128B swizzle,
-// out-of-bounds elements read as zero.  Returns 0 on success.
+// out-of-bounds elements read as zero.  tf32_dtype selects CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 (the copy engine converts
+// fp32 -> tf32 in flight) instead of FLOAT32.  Returns 0 on success.
 int make_tensor_map_f32(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
-                        const uint32_t* box, bool atom32b = false);
+                        const uint32_t* box, bool atom32b = false, bool tf32_dtype = false);
 
 }  // namespace tc
 }  // namespace b200asr

@@ -200,14 +200,14 @@ int conv3x3_tc(const float* in, const float* wk, const float* bias, const float*
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)F, (uint64_t)T, (uint64_t)B};
     uint64_t strides[3] = {(uint64_t)Cin, (uint64_t)F * Cin, (uint64_t)T * F * Cin};
     uint32_t box[4] = {32, CT_F, CT_T, 1};
-    int rc = make_tensor_map_f32(&ma, in, 4, dims, strides, box);
+    int rc = make_tensor_map_f32(&ma, in, 4, dims, strides, box, false, precision == 1);
     if (rc) return rc;
   }
   {
     uint64_t dims[2] = {(uint64_t)Cin, (uint64_t)9 * Cout};
     uint64_t strides[1] = {(uint64_t)Cin};
     uint32_t box[2] = {32, (uint32_t)Cout};
-    int rc = make_tensor_map_f32(&mb, wk, 2, dims, strides, box);
+    int rc = make_tensor_map_f32(&mb, wk, 2, dims, strides, box, false, precision == 1);
     if (rc) return rc;
   }
   ConvEpi e{out, bias, mask, relu, B, T, F, Cin, Cout};

@@ -10,7 +10,7 @@ import torch
 import torch.nn.functional as F
 
 from oracle import asr_oracle as O
-from tests.helpers import GOLDEN_CASES, grads_rel_err, load_golden, rel_err
+from tests.helpers import GOLDEN_CASES, grads_rel_err, load_golden, rel_err, vgg_pools_well_separated
 
 pytestmark = pytest.mark.gpu
 
@@ -46,21 +46,24 @@ def test_golden_forward_loss_backward(b200, case):
     assert errs[worst] < TOL, (worst, errs[worst])
 
 
-@pytest.mark.parametrize("feat,L,H,d,dk,dv,di,B,T,Tt,V", [
-    ("vgg_cnn", 2, 4, 128, 32, 32, 256, 3, 44, 9, 77),
-    ("", 2, 2, 64, 16, 32, 128, 4, 70, 13, 33),
-    ("emb_cnn", 1, 2, 64, 32, 32, 64, 2, 36, 6, 20),
-    ("vgg_cnn", 1, 8, 512, 64, 64, 2048, 2, 40, 12, 4364),           # cfg2 architecture, 1 layer, short
+@pytest.mark.parametrize("feat,L,H,d,dk,dv,di,B,T,Tt,V,freq", [
+    ("vgg_cnn", 2, 4, 128, 32, 32, 256, 2, 20, 9, 77, 41),
+    ("", 2, 2, 64, 16, 32, 128, 4, 70, 13, 33, 161),
+    ("emb_cnn", 1, 2, 64, 32, 32, 64, 2, 36, 6, 20, 161),
+    ("vgg_cnn", 1, 8, 512, 64, 64, 2048, 2, 16, 12, 4364, 41),        # cfg2 architecture, 1 layer, small spectrogram
 ])
-def test_oracle_forward_loss_backward(b200, feat, L, H, d, dk, dv, di, B, T, Tt, V):
+def test_oracle_forward_loss_backward(b200, feat, L, H, d, dk, dv, di, B, T, Tt, V, freq):
     from tests.gpu_util import TOL, cuda_model, cuda_step
     cfg = O.OracleConfig(num_layers=L, num_heads=H, dim_model=d, dim_key=dk, dim_value=dv, dim_inner=di, vocab=V,
-                         feat_extractor=feat, tgt_max_len=Tt, freq=161 if feat else 161)
+                         feat_extractor=feat, tgt_max_len=Tt, freq=freq)
     P = O.init_params(cfg, seed=3)
     for k in P:                     # move norm scales / biases off (1, 0)
         if P[k].dim() == 1:
             P[k] = P[k] + 0.1 * torch.randn(P[k].shape, generator=torch.Generator().manual_seed(hash(k) % 1000))
-    src, lens, tgt = O.synthetic_batch(cfg, B, T, seed=1, ragged=True)
+    for seed in range(1, 200):      # max-pool routing is discontinuous: use an input without near-tied pooling windows
+        src, lens, tgt = O.synthetic_batch(cfg, B, T, seed=seed, ragged=True)
+        if feat != "vgg_cnn" or vgg_pools_well_separated(P, src):
+            break
     pred_o, gold_o, hyp_o, loss_o, n_word, grads_o = O.forward_backward(P, cfg, src, lens, tgt, 0.1)
     model = cuda_model(cfg, P)
     pred, gold, hyp, loss, stats, grads = cuda_step(model, src, lens, tgt, 0.1)
@@ -206,31 +209,15 @@ def test_attention_fully_masked_row_is_nan_like_reference(b200):
     assert torch.isnan(o).all()
 
 
-def _pool_windows_well_separated(h, rel_gap=1e-4):
-    """True if no 2x2 max-pool window of h (B,C,F,T) has its two largest entries within rel_gap of each other
-    (unless the max is <= 0, where the ReLU mask zeroes the gradient anyway).  Max-pool routing is discontinuous:
-    a near-tie lets fp32 rounding noise move the whole gradient to the neighbouring pixel (observed: values
-    0.00735714 vs 0.00735718), so parity inputs must avoid them -- the reference has the same sensitivity."""
-    B, C, Fh, Tw = h.shape
-    w = h[:, :, :Fh // 2 * 2, :Tw // 2 * 2].reshape(B, C, Fh // 2, 2, Tw // 2, 2).permute(0, 1, 2, 4, 3, 5).reshape(B, C, Fh // 2, Tw // 2, 4)
-    top = w.topk(2, dim=-1).values
-    live = top[..., 0] > 0
-    gap = (top[..., 0] - top[..., 1])[live]
-    return bool((gap > rel_gap * h.abs().max()).all())
-
-
 @pytest.mark.parametrize("B,F_,T", [(2, 41, 24), (1, 161, 12), (3, 23, 10)])
 def test_vgg_frontend_fwd_bwd(b200, B, F_, T):
     ops = _ops(b200)
     cfg = O.OracleConfig(num_layers=1, feat_extractor="vgg_cnn", freq=F_)
     P = {k: v.requires_grad_(True) for k, v in O.init_params(cfg, seed=5).items() if k.startswith("conv.")}
-    for seed in range(4, 40):                                 # first input without max-pool near-ties
+    for seed in range(4, 200):                                # first input without max-pool near-ties
         g = torch.Generator().manual_seed(seed)
         x = torch.randn(B, 1, F_, T, generator=g)
-        with torch.no_grad():
-            h2 = F.relu(F.conv2d(F.relu(F.conv2d(x, P["conv.0.weight"], P["conv.0.bias"], padding=1)), P["conv.2.weight"], P["conv.2.bias"], padding=1))
-            h4 = F.relu(F.conv2d(F.relu(F.conv2d(F.max_pool2d(h2, 2, 2), P["conv.5.weight"], P["conv.5.bias"], padding=1)), P["conv.7.weight"], P["conv.7.bias"], padding=1))
-        if _pool_windows_well_separated(h2) and _pool_windows_well_separated(h4):
+        if vgg_pools_well_separated(P, x):
             break
     y = O.vgg_frontend(x, P)                                  # (B,128,F/4,T/4)
     dy = torch.randn(y.shape, generator=g)

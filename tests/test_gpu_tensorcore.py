@@ -41,8 +41,8 @@ def test_linear_forward_tensor_core(L, M, N, K, prec, tol):
     assert rel_err(y, ref) < tol
 
 
-@pytest.mark.parametrize("prec,tol", [(1, 2e-3), (3, 2e-5)])
-@pytest.mark.parametrize("M,N,K", SHAPES)
+@pytest.mark.parametrize("prec,tol", [(1, 2e-3), (3, 1e-4)])   # 3xTF32: operands exact to ~2^-22; the residual is the
+@pytest.mark.parametrize("M,N,K", SHAPES)                      # tensor core's own fp32 accumulation over long K
 def test_linear_backward_tensor_core(L, M, N, K, prec, tol):
     """bwd_data exercises an MN-major B operand, bwd_weight MN-major A and B (plus split-K atomics)."""
     lib = L.load()
