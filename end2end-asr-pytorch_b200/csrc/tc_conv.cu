@@ -216,3 +216,218 @@ int conv3x3_tc(const float* in, const float* wk, const float* bias, const float*
 }
 
 }  // namespace b200asr
+
+// =====================================================================================================================
+// Weight gradient:  dwr[tap][ci][co] += sum_p x[p + off(tap)][ci] * dy[p][co]
+//
+// GEMM with the PIXEL axis as the contraction: both operands are MN-major (channels contiguous, pixels strided), i.e.
+// exactly the channels-last activations as they lie in HBM -- no transpose.  One k-block = a 2 (time) x 16 (freq) patch
+// of 32 pixels; the A tile is four 32-channel chunks {32 ch, 16, 2, 1} fetched at the tap-shifted coordinate (zero fill
+// = padding), the B tile Co/32 chunks of dy at the unshifted coordinate.  M = 128 rows: one tap when Cin = 128, a PAIR of
+// taps when Cin = 64 (rows 0-63 tap a, 64-127 tap b; they share the dy tile).  Each CTA reduces a contiguous range of
+// pixel blocks and adds its 128 x Co partial into dwr with fp32 atomics (dwr is zeroed by the caller).
+namespace b200asr {
+namespace tc {
+
+constexpr int WG_PF = 16, WG_PT = 2;                 // pixel patch of one k-block (32 pixels)
+
+template <int BN, int NSPLIT> struct WgCfg {
+  static constexpr int kATile = 4 * 4096;
+  static constexpr int kBTile = (BN / 32) * 4096;
+  static constexpr int kStageBytes = (NSPLIT == 1 ? 1 : 2) * (kATile + kBTile);
+  static constexpr int kStages = NSPLIT == 1 ? 6 : (BN == 64 ? 4 : 3);
+  static constexpr int kOffAlo = kATile;
+  static constexpr int kOffBhi = NSPLIT == 1 ? kATile : 2 * kATile;
+  static constexpr int kOffBlo = 2 * kATile + kBTile;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+struct WgP {
+  float* dwr;
+  int B, T, F, Ci, Co, nft, ntt, blocks_per_cta, total_blocks;
+};
+
+template <int CI, int BN, int NSPLIT>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+tc_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapDy, const WgP e) {
+  using Cfg = WgCfg<BN, NSPLIT>;
+  constexpr int S = Cfg::kStages;
+  constexpr int TAPS_PER_CTA = 128 / CI;             // 2 (Cin = 64) or 1 (Cin = 128)
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + S * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto xfm_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * S + s); };
+  const uint32_t accum_bar = bar_base + 8u * (3 * S);
+  const uint32_t tmem_slot = bar_base + 8u * (3 * S + 1);
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tap_a = blockIdx.x * TAPS_PER_CTA;
+  const int tap_b = (TAPS_PER_CTA == 2 && tap_a + 1 < 9) ? tap_a + 1 : tap_a;    // odd tap count: slot b repeats tap a, unused
+  const int blk0 = blockIdx.y * e.blocks_per_cta;
+  const int nkb = max(0, min(e.blocks_per_cta, e.total_blocks - blk0));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; s++) { mbar_init(full_bar(s), 1); mbar_init(xfm_bar(s), 128); mbar_init(empty_bar(s), 1); }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&mapX);
+    tma_prefetch_desc(&mapDy);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; kb++) {
+        const int s = kb % S;
+        const uint32_t ph = (kb / S) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+        const uint32_t sb = sa + Cfg::kOffBhi;
+        const int blk = blk0 + kb;
+        const int ft = blk % e.nft, tt = (blk / e.nft) % e.ntt, b = blk / (e.nft * e.ntt);
+        const int f0 = ft * WG_PF, t0 = tt * WG_PT;
+        mbar_expect_tx(full_bar(s), Cfg::kATile + Cfg::kBTile);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          const int tap = (c * 32) / CI == 0 ? tap_a : tap_b;
+          const int df = tap / 3 - 1, dt = tap % 3 - 1;
+          tma_load_4d(sa + c * 4096, &mapX, full_bar(s), (c * 32) % CI, f0 + df, t0 + dt, b);
+        }
+#pragma unroll
+        for (int c = 0; c < BN / 32; c++) tma_load_4d(sb + c * 4096, &mapDy, full_bar(s), c * 32, f0, t0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(128, BN, true, true);
+      for (int kb = 0; kb < nkb; kb++) {
+        const int s = kb % S;
+        const uint32_t ph = (kb / S) & 1;
+        mbar_wait(NSPLIT == 1 ? full_bar(s) : xfm_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+        const uint32_t sb = sa + Cfg::kOffBhi;
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++) {
+          const uint64_t a_hi = make_smem_desc(sa + ks * 1024, 4096, 512, kLayoutSW128Base32B);
+          const uint64_t b_hi = make_smem_desc(sb + ks * 1024, 4096, 512, kLayoutSW128Base32B);
+          const uint32_t acc0 = (kb | ks) != 0 ? 1u : 0u;
+          if (NSPLIT == 1) {
+            umma_tf32(tmem_base, a_hi, b_hi, idesc, acc0);
+          } else {
+            const uint64_t a_lo = make_smem_desc(sa + Cfg::kOffAlo + ks * 1024, 4096, 512, kLayoutSW128Base32B);
+            const uint64_t b_lo = make_smem_desc(sa + Cfg::kOffBlo + ks * 1024, 4096, 512, kLayoutSW128Base32B);
+            umma_tf32(tmem_base, a_lo, b_hi, idesc, acc0);
+            umma_tf32(tmem_base, a_hi, b_lo, idesc, 1u);
+            umma_tf32(tmem_base, a_hi, b_hi, idesc, 1u);
+          }
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(accum_bar);
+    }
+  } else {
+    const int t = threadIdx.x - 64;
+    if (NSPLIT == 3) {
+      for (int kb = 0; kb < nkb; kb++) {
+        const int s = kb % S;
+        const uint32_t ph = (kb / S) & 1;
+        mbar_wait(full_bar(s), ph);
+        float4* stage = reinterpret_cast<float4*>(gen_base + s * Cfg::kStageBytes);
+        split_tf32_inplace(stage, stage + Cfg::kOffAlo / 16, Cfg::kATile / 16, t, 128);
+        split_tf32_inplace(stage + Cfg::kOffBhi / 16, stage + Cfg::kOffBlo / 16, Cfg::kBTile / 16, t, 128);
+        fence_proxy_async_smem();
+        mbar_arrive(xfm_bar(s));
+      }
+    }
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;                 // MMA row = (tap slot, input channel)
+    const int slot = r / CI, ci = r % CI;
+    const int tap = slot == 0 ? tap_a : tap_b;
+    const bool ok = nkb > 0 && (slot == 0 || tap_b != tap_a);
+    float* orow = e.dwr + ((size_t)tap * e.Ci + ci) * e.Co;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; c++) {
+      float v[32];
+      if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), v);
+      if (!ok) continue;
+#pragma unroll
+      for (int j = 0; j < 32; j++) atomicAdd(orow + c * 32 + j, v[j]);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+template <int CI, int BN, int NSPLIT>
+static int launch_wgrad(const CUtensorMap& mx, const CUtensorMap& mdy, WgP e, cudaStream_t st) {
+  using Cfg = WgCfg<BN, NSPLIT>;
+  auto* kern = tc_conv3x3_wgrad_kernel<CI, BN, NSPLIT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t r = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (r != cudaSuccess) { set_error("tc_conv_wgrad: cannot reserve %d bytes of shared memory: %s", Cfg::kSmemBytes, cudaGetErrorString(r)); return B200ASR_CUDA_ERROR; }
+    attr_set = true;
+  }
+  const int groups = CI == 64 ? 5 : 9;
+  const int sms = device_sm_count();
+  int splits = max(1, (4 * sms) / groups);
+  e.blocks_per_cta = max(64, ceil_div(e.total_blocks, splits));
+  splits = ceil_div(e.total_blocks, e.blocks_per_cta);
+  dim3 grid(groups, splits);
+  kern<<<grid, CONV_THREADS, Cfg::kSmemBytes, st>>>(mx, mdy, e);
+  return check_launch("tc_conv3x3_wgrad");
+}
+
+}  // namespace tc
+
+int conv3x3_wgrad_tc(const float* x, const float* dy, float* dwr, int B, int T, int F, int Ci, int Co, int precision,
+                     cudaStream_t st) {
+  using namespace tc;
+  B200_REQUIRE(precision == 1 || precision == 3, B200ASR_BAD_ARG, "conv3x3_wgrad_tc: precision must be 1 or 3");
+  B200_REQUIRE((Ci == 64 || Ci == 128) && (Co == 64 || Co == 128), B200ASR_BAD_SHAPE,
+               "conv3x3_wgrad_tc: needs Ci, Co in {64,128} (Ci=%d Co=%d)", Ci, Co);
+  B200_REQUIRE(aligned16(x) && aligned16(dy) && aligned16(dwr), B200ASR_BAD_ALIGN, "conv3x3_wgrad_tc: alignment");
+  CUtensorMap mx, mdy;
+  const bool tf32 = precision == 1;
+  {
+    uint64_t dims[4] = {(uint64_t)Ci, (uint64_t)F, (uint64_t)T, (uint64_t)B};
+    uint64_t strides[3] = {(uint64_t)Ci, (uint64_t)F * Ci, (uint64_t)T * F * Ci};
+    uint32_t box[4] = {32, WG_PF, WG_PT, 1};
+    int rc = make_tensor_map_f32(&mx, x, 4, dims, strides, box, true, tf32);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)Co, (uint64_t)F, (uint64_t)T, (uint64_t)B};
+    uint64_t strides[3] = {(uint64_t)Co, (uint64_t)F * Co, (uint64_t)T * F * Co};
+    uint32_t box[4] = {32, WG_PF, WG_PT, 1};
+    int rc = make_tensor_map_f32(&mdy, dy, 4, dims, strides, box, true, tf32);
+    if (rc) return rc;
+  }
+  WgP e{dwr, B, T, F, Ci, Co, ceil_div(F, WG_PF), ceil_div(T, WG_PT), 0, 0};
+  const long long total = (long long)B * e.nft * e.ntt;
+  B200_REQUIRE(total < (1LL << 31), B200ASR_BAD_SHAPE, "conv3x3_wgrad_tc: too many pixel blocks");
+  e.total_blocks = (int)total;
+#define WG(CIv, BNv) return precision == 1 ? launch_wgrad<CIv, BNv, 1>(mx, mdy, e, st) : launch_wgrad<CIv, BNv, 3>(mx, mdy, e, st)
+  if (Ci == 64 && Co == 64) WG(64, 64);
+  if (Ci == 64 && Co == 128) WG(64, 128);
+  if (Ci == 128 && Co == 64) WG(128, 64);
+  WG(128, 128);
+#undef WG
+}
+
+}  // namespace b200asr

@@ -11,10 +11,5 @@ int sdpa_bwd_tc(const AttnP&, const float*, float*, float*, float*, float*, cuda
   return B200ASR_BAD_ARG;
 }
 #endif
-#ifndef B200ASR_HAVE_TC_CONV
-int conv3x3_wgrad_tc(const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t) {
-  set_error("tcgen05 convolution weight gradient is not available in this build");
-  return B200ASR_BAD_ARG;
-}
-#endif
+
 }  // namespace b200asr

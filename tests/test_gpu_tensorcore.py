@@ -137,3 +137,22 @@ def test_attention_tensor_core_rejects_long_keys(L):
     rc = lib.b200asr_sdpa_fwd(L.ptr(q), L.ptr(k), L.ptr(v), 4096, 4096, 64, 32000, 32000, 64, 32000, 32000, 64, None, None, 0,
                               L.ptr(o), 4096, 4096, 64, L.ptr(lse), 1, 1, 64, 500, 64, 64, 0.125, 0.0, 0, 0, 1, _stream())
     assert rc == -1 and "precision 0" in L.last_error()
+
+
+@pytest.mark.parametrize("prec,tol", [(1, 2e-3), (3, 1e-4)])
+@pytest.mark.parametrize("B,T,F_,Ci,Co", [(2, 16, 32, 64, 64), (1, 9, 21, 64, 128), (3, 24, 41, 128, 128), (2, 10, 23, 128, 64),
+                                          (1, 40, 161, 64, 64)])
+def test_conv3x3_weight_gradient_tensor_core(L, B, T, F_, Ci, Co, prec, tol):
+    lib = L.load()
+    g = torch.Generator().manual_seed(B * 7 + T)
+    x = torch.randn(B, Ci, F_, T, generator=g)
+    dy = torch.randn(B, Co, F_, T, generator=g)
+    dw_ref = torch.nn.grad.conv2d_weight(x.double(), (Co, Ci, 3, 3), dy.double(), padding=1)
+    nhwc = lambda t: t.permute(0, 3, 2, 1).contiguous().cuda()
+    xc, dyc = nhwc(x), nhwc(dy)
+    ws = torch.empty(9 * Ci * Co, device="cuda")
+    dw = torch.full((Co, Ci, 3, 3), float("nan"), device="cuda")
+    db = torch.full((Co,), float("nan"), device="cuda")
+    L.check(lib.b200asr_conv3x3_bwd_weight(L.ptr(dyc), L.ptr(xc), L.ptr(dw), L.ptr(db), L.ptr(ws), B, T, F_, Ci, Co, prec, _stream()), "conv wgrad")
+    assert rel_err(dw, dw_ref) < tol
+    assert rel_err(db, dy.double().sum((0, 2, 3))) < 1e-5
