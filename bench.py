@@ -168,8 +168,8 @@ def run_b200(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=dev)
     lib = b200asr._lib.load(check_device=True)
     if args.precision:
-        lin, conv, attn = args.precision.split(",")
-        b200asr.precision.set(linear=lin, conv=conv, attn=attn)
+        names = ["linear", "conv", "attn", "conv_wgrad", "attn_bwd"]
+        b200asr.precision.set(**dict(zip(names, args.precision.split(","))))
     spec = b200asr.BASELINE_CONFIGS[WORKLOAD]
     cfg, B, T = spec["cfg"], args.batch or spec["batch"], spec["t_src"]
     torch.manual_seed(123456)
@@ -252,7 +252,9 @@ def run_b200(args, rank, local_rank, world):
            "dtype": "f32" if not args.precision else "f32(" + args.precision + ")", "data": "synthetic",
            "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": world * B, "t_src": T, "t_tgt": cfg.tgt_max_len,
                       "dropout": cfg.dropout, "label_smoothing": cfg.label_smoothing,
-                      "precision": {"linear": ops.config.linear, "conv": ops.config.conv, "attn": ops.config.attn},
+                      "precision": {"linear": ops.config.linear, "conv": ops.config.conv, "conv_wgrad": ops.config.conv_wgrad,
+                                    "attn": ops.config.attn, "attn_bwd": ops.config.attn_bwd,
+                                    "legend": "0 = fp32 CUDA cores, 1 = tcgen05 TF32 (RN), 3 = tcgen05 3xTF32 (fp32-grade)"},
                       "step": "zero_grad+fwd+CE+bwd+allreduce+adam", "parallelism": f"dp{world}",
                       "l2": "per-step working set (GBs of activations) >> 126 MB L2; no explicit flush"},
            "e2e": {"value": world * B / (ms_e2e / 1e3), "unit": "utt/s", "h2d_bytes_per_step": src_h.numel() * 4 + tgt_h.numel() * 8,
@@ -270,11 +272,11 @@ def run_b200(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (debug only; the metric uses 32)")
-    ap.add_argument("--precision", default="", help="linear,conv,attn in {fp32,tf32,tf32x3} (default: package default)")
+    ap.add_argument("--precision", default="", help="linear,conv,attn[,conv_wgrad[,attn_bwd]] in {fp32,tf32,tf32x3} (default: package default)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
