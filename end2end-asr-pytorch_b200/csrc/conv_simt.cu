@@ -119,16 +119,28 @@ __global__ void conv_repack_kernel(const float* __restrict__ w, float* __restric
 // K-major repacks for the tcgen05 path (contraction channel contiguous):
 // fwd:   wk[tap][co][ci] = w[co][ci][tap]
 // dgrad: wk[tap'][ci][co] = w[co][ci][8 - tap']
-__global__ void conv_repack_k_kernel(const float* __restrict__ w, float* __restrict__ wk, int Ci, int Co, int dgrad) {
+// split != 0 additionally writes the 3xTF32 halves: wk[i] = rna_tf32(w), wk[total + i] = rna_tf32(w - hi)
+__global__ void conv_repack_k_kernel(const float* __restrict__ w, float* __restrict__ wk, int Ci, int Co, int dgrad, int split) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int total = 9 * Ci * Co;
   if (i >= total) return;
+  float v;
   if (!dgrad) {
     int ci = i % Ci, co = (i / Ci) % Co, tap = i / (Co * Ci);
-    wk[i] = w[((size_t)co * Ci + ci) * 9 + tap];
+    v = w[((size_t)co * Ci + ci) * 9 + tap];
   } else {
     int co = i % Co, ci = (i / Co) % Ci, tap = i / (Co * Ci);
-    wk[i] = w[((size_t)co * Ci + ci) * 9 + (8 - tap)];
+    v = w[((size_t)co * Ci + ci) * 9 + (8 - tap)];
+  }
+  if (split) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    float hi = __uint_as_float(u);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v - hi));
+    wk[i] = hi;
+    wk[total + i] = __uint_as_float(u);
+  } else {
+    wk[i] = v;
   }
 }
 // dw[co][ci][tap] = dwr[tap][ci][co]
@@ -421,15 +433,25 @@ __global__ void maxpool2x2_bwd_kernel(const float* __restrict__ dy, const float*
 #pragma unroll
   for (int k = 0; k < 4; k++) *reinterpret_cast<float4*>(dx + base + offs[k]) = out[k];
 }
-// zero the rows/cols that floor-mode pooling never reads (odd T or F)
+// zero the rows/cols that floor-mode pooling never reads (odd T or F): only those positions are visited
 __global__ void maxpool2x2_bwd_tail_kernel(float* __restrict__ dx, int B, int T, int F, int C) {
-  long long n = (long long)B * T * F * C;
+  const int C4 = C / 4;
+  const int odd_f = F & 1, odd_t = T & 1;
+  const int Te = (T / 2) * 2;                                    // rows with t < Te only need the odd freq column
+  const long long n_col = odd_f ? (long long)B * Te * C4 : 0;    // (b, t < Te, f = F-1)
+  const long long n_row = odd_t ? (long long)B * F * C4 : 0;     // (b, t = T-1, all f)
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  long long r = i / C;
-  int f = (int)(r % F);
-  int t = (int)((r / F) % T);
-  if (t >= (T / 2) * 2 || f >= (F / 2) * 2) dx[i] = 0.f;
+  if (i >= n_col + n_row) return;
+  int b, t, f, c;
+  if (i < n_col) {
+    c = (int)(i % C4) * 4; long long r = i / C4;
+    t = (int)(r % Te); b = (int)(r / Te); f = F - 1;
+  } else {
+    i -= n_col;
+    c = (int)(i % C4) * 4; long long r = i / C4;
+    f = (int)(r % F); b = (int)(r / F); t = T - 1;
+  }
+  *reinterpret_cast<float4*>(dx + (((size_t)b * T + t) * F + f) * C + c) = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 __global__ void relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx, long long n4) {
@@ -477,7 +499,7 @@ using namespace b200asr;
 
 extern "C" {
 
-size_t b200asr_conv3x3_ws_bytes(int Ci, int Co) { return sizeof(float) * 9 * (size_t)Ci * Co; }
+size_t b200asr_conv3x3_ws_bytes(int Ci, int Co) { return sizeof(float) * 2 * 9 * (size_t)Ci * Co; }   // [hi | lo] weight halves
 
 int b200asr_conv3x3_c1_fwd(const float* x, const float* w, const float* bias, float* y, int B, int F, int T, int Co,
                            int relu, b200asr_stream_t stream) {
@@ -527,7 +549,7 @@ int b200asr_conv3x3_fwd(const float* x, const float* w, const float* bias, float
     conv_repack_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, (float*)ws, Ci, Co, 0);
     return conv3x3_simt(x, (const float*)ws, bias, nullptr, y, B, T, F, Ci, Co, relu, st);
   }
-  conv_repack_k_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, (float*)ws, Ci, Co, 0);
+  conv_repack_k_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, (float*)ws, Ci, Co, 0, precision == B200ASR_PREC_TF32X3);
   return conv3x3_tc(x, (const float*)ws, bias, nullptr, y, B, T, F, Ci, Co, relu, precision, st);
 }
 
@@ -543,7 +565,7 @@ int b200asr_conv3x3_bwd_data(const float* dy, const float* w, const float* relu_
     conv_repack_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, (float*)ws, Ci, Co, 1);
     return conv3x3_simt(dy, (const float*)ws, nullptr, relu_out, dx, B, T, F, Co, Ci, 0, st);
   }
-  conv_repack_k_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, (float*)ws, Ci, Co, 1);
+  conv_repack_k_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, (float*)ws, Ci, Co, 1, precision == B200ASR_PREC_TF32X3);
   return conv3x3_tc(dy, (const float*)ws, nullptr, relu_out, dx, B, T, F, Co, Ci, 0, precision, st);
 }
 
@@ -584,7 +606,7 @@ int b200asr_maxpool2x2_bwd(const float* dy, const float* x, float* dx, int B, in
   long long n = (long long)B * (T / 2) * (F / 2) * (C / 4);
   if (n > 0) maxpool2x2_bwd_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, st>>>(dy, x, dx, B, T, F, C, relu_mask);
   if ((T & 1) || (F & 1)) {
-    long long tot = (long long)B * T * F * C;
+    long long tot = ((F & 1) ? (long long)B * (T / 2) * 2 * (C / 4) : 0) + ((T & 1) ? (long long)B * F * (C / 4) : 0);
     maxpool2x2_bwd_tail_kernel<<<(unsigned)ceil_div_ll(tot, 256), 256, 0, st>>>(dx, B, T, F, C);
     note_launch(1);
   }

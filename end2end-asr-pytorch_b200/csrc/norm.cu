@@ -158,17 +158,27 @@ add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, con
   }
 }
 
-__global__ void ln_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int d, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= d) return;
+// dgamma/dbeta = column sums of the per-CTA partials: 32 columns per CTA, 8 row lanes, smem tree
+__global__ void __launch_bounds__(256) ln_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int d,
+                                                              float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float ra[8][33], rb[8][33];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   float a = 0.f, b = 0.f;
-  for (int i = 0; i < nblk; i++) {
-    a += partial[(size_t)i * 2 * d + c];
-    b += partial[(size_t)i * 2 * d + d + c];
+  if (c < d)
+    for (int i = rl; i < nblk; i += 8) {
+      a += partial[(size_t)i * 2 * d + c];
+      b += partial[(size_t)i * 2 * d + d + c];
+    }
+  ra[rl][cl] = a; rb[rl][cl] = b;
+  __syncthreads();
+  if (rl == 0 && c < d) {
+    float sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { sa += ra[i][cl]; sb += rb[i][cl]; }
+    dgamma[c] = sa;
+    dbeta[c] = sb;
   }
-  dgamma[c] = a;
-  dbeta[c] = b;
 }
 
 }  // namespace b200asr
@@ -216,7 +226,7 @@ int b200asr_add_ln_bwd(const float* dy, const float* z, const float* gamma, cons
                                                     rows, d, th, dropout_inv_keep(p_drop), dropout_key(seed, offset));
   int rc = check_launch("add_ln_bwd");
   if (rc) return rc;
-  ln_bwd_finalize_kernel<<<ceil_div(d, 128), 128, 0, st>>>((const float*)partial_ws, nblk, d, dgamma, dbeta);
+  ln_bwd_finalize_kernel<<<ceil_div(d, 32), 256, 0, st>>>((const float*)partial_ws, nblk, d, dgamma, dbeta);
   return check_launch("ln_bwd_finalize");
 }
 

@@ -18,7 +18,8 @@ namespace tc {
 
 constexpr int CT_T = 8, CT_F = 16;                    // pixel patch: 8 x 16 = 128 rows of the MMA
 constexpr int A_TILE = 128 * 128;                     // bytes per A k-block
-constexpr int CONV_THREADS = 192;
+constexpr int CONV_THREADS = 320;                     // warp 0 TMA, warp 1 MMA, warps 2-9 split + epilogue
+constexpr int CONV_WORKERS = 256;
 
 template <int BN, int NSPLIT> struct ConvCfg {
   static constexpr int kBTile = BN * 128;
@@ -58,7 +59,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
   const int nkb = 9 * cch;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; s++) { mbar_init(full_bar(s), 1); mbar_init(xfm_bar(s), 128); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < S; s++) { mbar_init(full_bar(s), 1); mbar_init(xfm_bar(s), CONV_WORKERS); mbar_init(empty_bar(s), 1); }
     mbar_init(accum_bar, 1);
     fence_barrier_init();
     tma_prefetch_desc(&mapA);
@@ -80,9 +81,10 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const uint32_t sb = sa + Cfg::kOffBhi;
         const int tap = kb / cch, c0 = (kb - tap * cch) * 32;
         const int df = tap / 3 - 1, dt = tap % 3 - 1;          // tap = kf*3 + kt of w[Co][Ci][kf(freq)][kt(time)]
-        mbar_expect_tx(full_bar(s), A_TILE + Cfg::kBTile);
+        mbar_expect_tx(full_bar(s), A_TILE + (NSPLIT == 1 ? 1 : 2) * Cfg::kBTile);
         tma_load_4d(sa, &mapA, full_bar(s), c0, f0 + df, t0 + dt, b);   // halo / image border = TMA zero fill
         tma_load_2d(sb, &mapB, full_bar(s), c0, tap * BN);
+        if (NSPLIT == 3) tma_load_2d(sa + Cfg::kOffBlo, &mapB, full_bar(s), c0, (9 + tap) * BN);   // pre-split lo half
       }
     }
   } else if (warp == 1) {
@@ -122,8 +124,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
         const uint32_t ph = (kb / S) & 1;
         mbar_wait(full_bar(s), ph);
         float4* stage = reinterpret_cast<float4*>(gen_base + s * Cfg::kStageBytes);
-        split_tf32_inplace(stage, stage + Cfg::kOffAlo / 16, A_TILE / 16, t, 128);
-        split_tf32_inplace(stage + Cfg::kOffBhi / 16, stage + Cfg::kOffBlo / 16, Cfg::kBTile / 16, t, 128);
+        split_tf32_inplace(stage, stage + Cfg::kOffAlo / 16, A_TILE / 16, t, CONV_WORKERS);   // weights arrive pre-split
         fence_proxy_async_smem();
         mbar_arrive(xfm_bar(s));
       }
@@ -131,6 +132,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;               // MMA row = pixel (t0 + r/16, f0 + r%16)
     const int tt = t0 + r / CT_F, ff = f0 + r % CT_F;
     const bool ok = tt < e.T && ff < e.F;
@@ -138,7 +140,7 @@ tc_conv3x3_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constan
     float* orow = e.out + pix * e.Cout;
     const float* mrow = e.mask ? e.mask + pix * e.Cout : nullptr;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; c++) {
+    for (int c = half; c < BN / 32; c += 2) {
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), v);
       if (!ok) continue;
@@ -185,7 +187,8 @@ static int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const ConvE
 
 }  // namespace tc
 
-// wk: [9][Cout][Cin] (K-major weights, produced by conv_repack_k_kernel)
+// wk: [9][Cout][Cin] K-major weights (conv_repack_k_kernel); for precision 3 the buffer holds [2][9][Cout][Cin]:
+// hi = rna_tf32(w) followed by lo = rna_tf32(w - hi), so the kernel only has to split the activation tiles.
 int conv3x3_tc(const float* in, const float* wk, const float* bias, const float* mask, float* out, int B, int T, int F,
                int Cin, int Cout, int relu, int precision, cudaStream_t st) {
   using namespace tc;
@@ -204,7 +207,7 @@ int conv3x3_tc(const float* in, const float* wk, const float* bias, const float*
     if (rc) return rc;
   }
   {
-    uint64_t dims[2] = {(uint64_t)Cin, (uint64_t)9 * Cout};
+    uint64_t dims[2] = {(uint64_t)Cin, (uint64_t)(precision == 3 ? 18 : 9) * Cout};     // [hi | lo] halves for 3xTF32
     uint64_t strides[1] = {(uint64_t)Cin};
     uint32_t box[2] = {32, (uint32_t)Cout};
     int rc = make_tensor_map_f32(&mb, wk, 2, dims, strides, box, false, precision == 1);
@@ -270,7 +273,7 @@ tc_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_c
   const int nkb = max(0, min(e.blocks_per_cta, e.total_blocks - blk0));
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; s++) { mbar_init(full_bar(s), 1); mbar_init(xfm_bar(s), 128); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < S; s++) { mbar_init(full_bar(s), 1); mbar_init(xfm_bar(s), CONV_WORKERS); mbar_init(empty_bar(s), 1); }
     mbar_init(accum_bar, 1);
     fence_barrier_init();
     tma_prefetch_desc(&mapX);
@@ -341,8 +344,8 @@ tc_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_c
         const uint32_t ph = (kb / S) & 1;
         mbar_wait(full_bar(s), ph);
         float4* stage = reinterpret_cast<float4*>(gen_base + s * Cfg::kStageBytes);
-        split_tf32_inplace(stage, stage + Cfg::kOffAlo / 16, Cfg::kATile / 16, t, 128);
-        split_tf32_inplace(stage + Cfg::kOffBhi / 16, stage + Cfg::kOffBlo / 16, Cfg::kBTile / 16, t, 128);
+        split_tf32_inplace(stage, stage + Cfg::kOffAlo / 16, Cfg::kATile / 16, t, CONV_WORKERS);
+        split_tf32_inplace(stage + Cfg::kOffBhi / 16, stage + Cfg::kOffBlo / 16, Cfg::kBTile / 16, t, CONV_WORKERS);
         fence_proxy_async_smem();
         mbar_arrive(xfm_bar(s));
       }
@@ -350,13 +353,14 @@ tc_conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_c
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;                 // MMA row = (tap slot, input channel)
     const int slot = r / CI, ci = r % CI;
     const int tap = slot == 0 ? tap_a : tap_b;
     const bool ok = nkb > 0 && (slot == 0 || tap_b != tap_a);
     float* orow = e.dwr + ((size_t)tap * e.Ci + ci) * e.Co;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; c++) {
+    for (int c = half; c < BN / 32; c += 2) {
       float v[32];
       if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), v);
       if (!ok) continue;

@@ -4,7 +4,7 @@
 //     operand may be K-major (contraction contiguous) or MN-major (rows contiguous) -- forward, data-gradient and
 //     weight-gradient GEMMs all run without a transpose pass;
 //   * one CTA = one 128x128 output tile, 32-deep k-blocks, multi-stage mbarrier ring;
-//     warp 0 = TMA producer, warp 1 = MMA issuer (single thread) + TMEM owner, warps 2-5 = operand split + epilogue;
+//     warp 0 = TMA producer, warp 1 = MMA issuer (single thread) + TMEM owner, warps 2-9 = operand split + epilogue;
 //   * NSPLIT = 1: kind::tf32 once; the tensor maps use the TFLOAT32 data type, so the copy engine rounds fp32 -> tf32
 //     to nearest in flight (measured: 4-5x lower error than letting the tensor core truncate the fp32 operands);
 //     NSPLIT = 3: "3xTF32" -- the transform warps split every staged tile in place into hi = rna_tf32(x) and
@@ -50,7 +50,8 @@ int make_tensor_map_f32(CUtensorMap* map, const void* base, int rank, const uint
 
 constexpr int GBM = 128, GBN = 128, GBK = 32;            // tile; k-block in fp32 elements (= 128 bytes)
 constexpr int TILE_BYTES = GBM * GBK * 4;                // 16 KB per operand per stage
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;                       // warp 0 TMA, warp 1 MMA, warps 2-9 split + epilogue
+constexpr int GEMM_WORKERS = 256;
 
 template <int NSPLIT> struct GemmCfg {
   static constexpr int kStages = NSPLIT == 1 ? 6 : 3;
@@ -91,7 +92,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int nkb = (kend - kbeg + GBK - 1) / GBK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; s++) { mbar_init(full_bar(s), 1); mbar_init(xfm_bar(s), 128); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < S; s++) { mbar_init(full_bar(s), 1); mbar_init(xfm_bar(s), GEMM_WORKERS); mbar_init(empty_bar(s), 1); }
     mbar_init(accum_bar, 1);
     fence_barrier_init();
     tma_prefetch_desc(&mapA);
@@ -159,7 +160,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       umma_commit(accum_bar);                      // accumulators complete
     }
   } else {
-    const int t = threadIdx.x - 64;                // 0..127
+    const int t = threadIdx.x - 64;                // 0..255
     if (NSPLIT == 3) {
       // ---------------------------------------------------------------- operand split: x -> (rna_tf32(x), x - hi)
       for (int kb = 0; kb < nkb; kb++) {
@@ -171,7 +172,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int op = 0; op < 2; op++) {
           float4* hi = stage + (op == 0 ? 0 : Cfg::kOffBhi / 16);
           float4* lo = stage + (op == 0 ? Cfg::kOffAlo / 16 : Cfg::kOffBlo / 16);
-          split_tf32_inplace(hi, lo, TILE_BYTES / 16, t, 128);
+          split_tf32_inplace(hi, lo, TILE_BYTES / 16, t, GEMM_WORKERS);
         }
         fence_proxy_async_smem();                  // generic-proxy writes -> visible to tcgen05.mma (async proxy)
         mbar_arrive(xfm_bar(s));
@@ -181,12 +182,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     const int quarter = warp & 3;                  // TMEM lanes [32*quarter, +32) belong to this warp
+    const int half = (warp - 2) >> 2;              // two warps share a lane quarter and take alternate 32-column chunks
     const int row = m0 + quarter * 32 + lane;
     const bool atomic = e.splits > 1;
     const bool first = blockIdx.z == 0;
     const bool vec_ok = ((e.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0);
 #pragma unroll 1
-    for (int c = 0; c < GBN / 32; c++) {
+    for (int c = half; c < GBN / 32; c += 2) {
       float v[32];
       if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), v);
       else

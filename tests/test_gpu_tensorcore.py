@@ -94,7 +94,7 @@ def _conv_case(L, B, T, F_, Ci, Co, seed=0):
 def test_conv3x3_forward_and_dgrad_tensor_core(L, B, T, F_, Ci, Co, prec, tol):
     lib = L.load()
     x, w, b, y_ref, dy, dx_ref = _conv_case(L, B, T, F_, Ci, Co, seed=B + T)
-    ws = torch.empty(9 * Ci * Co, device="cuda")
+    ws = torch.empty(lib.b200asr_conv3x3_ws_bytes(Ci, Co) // 4, device="cuda")
     y = torch.full((B, T, F_, Co), float("nan"), device="cuda")
     L.check(lib.b200asr_conv3x3_fwd(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), L.ptr(ws), B, T, F_, Ci, Co, 0, prec, _stream()), "conv fwd")
     assert rel_err(y, y_ref) < tol
@@ -150,7 +150,7 @@ def test_conv3x3_weight_gradient_tensor_core(L, B, T, F_, Ci, Co, prec, tol):
     dw_ref = torch.nn.grad.conv2d_weight(x.double(), (Co, Ci, 3, 3), dy.double(), padding=1)
     nhwc = lambda t: t.permute(0, 3, 2, 1).contiguous().cuda()
     xc, dyc = nhwc(x), nhwc(dy)
-    ws = torch.empty(9 * Ci * Co, device="cuda")
+    ws = torch.empty(lib.b200asr_conv3x3_ws_bytes(Ci, Co) // 4, device="cuda")
     dw = torch.full((Co, Ci, 3, 3), float("nan"), device="cuda")
     db = torch.full((Co,), float("nan"), device="cuda")
     L.check(lib.b200asr_conv3x3_bwd_weight(L.ptr(dyc), L.ptr(xc), L.ptr(dw), L.ptr(db), L.ptr(ws), B, T, F_, Ci, Co, prec, _stream()), "conv wgrad")
