@@ -164,8 +164,9 @@ __device__ __forceinline__ void split_tf32_inplace(float4* __restrict__ hi, floa
 //   (512 B).  Chunks of 32 MN-elements are LBO apart, groups of 4 k-lines SBO = 512 B apart.
 constexpr uint32_t kLayoutSW128 = 2, kLayoutSW128Base32B = 1;
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                                   uint32_t layout_type = 2) {
+                                                   uint32_t layout_type = 2, uint32_t base_offset = 0) {
   uint64_t d = 0;
+  d |= (uint64_t)(base_offset & 7u) << 49;   // swizzle phase of the first row when the start is not 1024-byte aligned
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;

@@ -1,0 +1,197 @@
+// Persistent tcgen05 tile engine shared by the GEMM and the implicit-GEMM convolutions.
+//
+// One CTA per SM loops over output tiles (static round-robin).  Warp roles:
+//   warp 0      TMA producer            -- runs ahead across tiles through a ring of smem stages
+//   warp 1      MMA issuer + TMEM owner -- accumulates tile i into TMEM buffer (i & 1)
+//   warps 2-5   epilogue                -- drain buffer (i & 1) with tcgen05.ld while tile i+1 is being multiplied
+//   warps 6-13  3xTF32 operand split    -- hi = rna(x) in place, lo = rna(x - hi) (only when NSPLIT == 3)
+// so per-tile prologue/epilogue latency is hidden behind the next tile's mainloop instead of being paid 200+ times per SM.
+//
+// A Policy supplies the problem-specific parts:
+//   static constexpr int  BN, kABytes, kBBytes;  static constexpr bool kSplitA, kSplitB (operand needs the in-kernel split);
+//   static constexpr bool kAMN, kBMN (operand majors);  struct Params;
+//   static __device__ int  num_tiles(const Params&);          static __device__ int num_kb(const Params&, int tile);
+//   static __device__ void load(p, mapA, mapB, tile, kb, sa, sa_lo, sb, sb_lo, bar);   // TMA for one stage (fixed tx bytes)
+//   static __device__ uint64_t a_desc(uint32_t saddr, int ks); static __device__ uint64_t b_desc(uint32_t saddr, int ks);
+//   static __device__ void store(p, tile, row, col0, const float (&v)[32]);            // 32 accumulator columns of one row
+#pragma once
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace b200asr {
+namespace tc {
+
+constexpr int ENG_THREADS_X1 = 192;     // TMA, MMA, 4 epilogue warps
+constexpr int ENG_THREADS_X3 = 448;     // + 8 split warps
+constexpr int ENG_SPLIT_THREADS = 256;
+
+template <class Policy, int NSPLIT> struct EngineCfg {
+  static constexpr int kStageBytes = (NSPLIT == 1 ? 1 : 2) * (Policy::kABytes + Policy::kBBytes);
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kOffAlo = Policy::kABytes;
+  static constexpr int kOffBhi = (NSPLIT == 1 ? 1 : 2) * Policy::kABytes;
+  static constexpr int kOffBlo = kOffBhi + Policy::kBBytes;
+  static constexpr int kBarOff = kStages * kStageBytes;
+  static constexpr int kSmemBytes = kBarOff + 512 + 1024;
+  static constexpr int kTmemCols = 2 * Policy::BN <= 32 ? 32 : (2 * Policy::BN <= 64 ? 64 : (2 * Policy::BN <= 128 ? 128 : 256));
+  static constexpr int kTxBytes = Policy::kABytes + Policy::kBBytes +
+                                  (NSPLIT == 3 && !Policy::kSplitA ? Policy::kABytes : 0) +
+                                  (NSPLIT == 3 && !Policy::kSplitB ? Policy::kBBytes : 0);   // pre-split operands arrive as hi+lo
+  static_assert(kStages >= 2, "stage too large");
+};
+
+template <class Policy, int NSPLIT>
+__global__ void __launch_bounds__(NSPLIT == 1 ? ENG_THREADS_X1 : ENG_THREADS_X3, 1)
+tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                 const typename Policy::Params p) {
+  using Cfg = EngineCfg<Policy, NSPLIT>;
+  constexpr int S = Cfg::kStages;
+  constexpr int BN = Policy::BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + Cfg::kBarOff;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto xfm_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * S + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (3 * S + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (3 * S + 2 + b); };
+  const uint32_t tmem_slot = bar_base + 8u * (3 * S + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = Policy::num_tiles(p);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; s++) { mbar_init(full_bar(s), 1); mbar_init(xfm_bar(s), ENG_SPLIT_THREADS); mbar_init(empty_bar(s), 1); }
+    for (int b = 0; b < 2; b++) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 128); }
+    fence_barrier_init();
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      uint32_t kbg = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int nkb = Policy::num_kb(p, tile);
+        for (int kb = 0; kb < nkb; kb++, kbg++) {
+          const int s = kbg % S;
+          mbar_wait(empty_bar(s), ((kbg / S) & 1) ^ 1);
+          const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+          mbar_expect_tx(full_bar(s), Cfg::kTxBytes);
+          Policy::load(p, &mapA, &mapB, tile, kb, sa, sa + Cfg::kOffAlo, sa + Cfg::kOffBhi, sa + Cfg::kOffBlo, full_bar(s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- MMA issuer
+      constexpr uint32_t idesc = make_idesc_tf32(128, BN, Policy::kAMN, Policy::kBMN);
+      constexpr bool kNeedXfm = NSPLIT == 3 && (Policy::kSplitA || Policy::kSplitB);
+      uint32_t kbg = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
+        const int nkb = Policy::num_kb(p, tile);
+        const uint32_t buf = tcount & 1;
+        mbar_wait(tempty_bar(buf), ((tcount >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        for (int kb = 0; kb < nkb; kb++, kbg++) {
+          const int s = kbg % S;
+          mbar_wait(kNeedXfm ? xfm_bar(s) : full_bar(s), (kbg / S) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++) {
+            const uint64_t a_hi = Policy::a_desc(sa, ks), b_hi = Policy::b_desc(sa + Cfg::kOffBhi, ks);
+            const uint32_t acc0 = (kb | ks) != 0 ? 1u : 0u;
+            if (NSPLIT == 1) {
+              umma_tf32(d_tmem, a_hi, b_hi, idesc, acc0);
+            } else {
+              const uint64_t a_lo = Policy::a_desc(sa + Cfg::kOffAlo, ks), b_lo = Policy::b_desc(sa + Cfg::kOffBlo, ks);
+              umma_tf32(d_tmem, a_lo, b_hi, idesc, acc0);
+              umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+            }
+          }
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar(buf));
+      }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------------ epilogue (warps 2-5: TMEM lane quarters 2,3,0,1)
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
+      const uint32_t buf = tcount & 1;
+      const int nkb = Policy::num_kb(p, tile);
+      mbar_wait(tfull_bar(buf), (tcount >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; c++) {
+        float v[32];
+        if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + (uint32_t)(c * 32), v);
+        else
+#pragma unroll
+          for (int j = 0; j < 32; j++) v[j] = 0.f;
+        if (c == BN / 32 - 1) {            // all TMEM reads of this buffer are done: hand it back before the global stores
+          tc_fence_before();
+          mbar_arrive(tempty_bar(buf));
+        }
+        Policy::store(p, tile, row, c * 32, v);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ operand split warps (3xTF32 only)
+    if (NSPLIT == 3 && (Policy::kSplitA || Policy::kSplitB)) {
+      const int t = threadIdx.x - 192;
+      uint32_t kbg = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int nkb = Policy::num_kb(p, tile);
+        for (int kb = 0; kb < nkb; kb++, kbg++) {
+          const int s = kbg % S;
+          mbar_wait(full_bar(s), (kbg / S) & 1);
+          float4* stage = reinterpret_cast<float4*>(gen_base + s * Cfg::kStageBytes);
+          if (Policy::kSplitA) split_tf32_inplace(stage, stage + Cfg::kOffAlo / 16, Policy::kABytes / 16, t, ENG_SPLIT_THREADS);
+          if (Policy::kSplitB) split_tf32_inplace(stage + Cfg::kOffBhi / 16, stage + Cfg::kOffBlo / 16, Policy::kBBytes / 16, t, ENG_SPLIT_THREADS);
+          fence_proxy_async_smem();
+          mbar_arrive(xfm_bar(s));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+template <class Policy, int NSPLIT>
+int launch_engine(const CUtensorMap& ma, const CUtensorMap& mb, const typename Policy::Params& p, int ntiles, cudaStream_t st,
+                  const char* what) {
+  using Cfg = EngineCfg<Policy, NSPLIT>;
+  auto* kern = tc_engine_kernel<Policy, NSPLIT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t r = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (r != cudaSuccess) { set_error("%s: cannot reserve %d bytes of shared memory: %s", what, Cfg::kSmemBytes, cudaGetErrorString(r)); return B200ASR_CUDA_ERROR; }
+    attr_set = true;
+  }
+  if (ntiles <= 0) return B200ASR_OK;
+  const int grid = min(ntiles, device_sm_count());
+  kern<<<grid, NSPLIT == 1 ? ENG_THREADS_X1 : ENG_THREADS_X3, Cfg::kSmemBytes, st>>>(ma, mb, p);
+  return check_launch(what);
+}
+
+}  // namespace tc
+}  // namespace b200asr

