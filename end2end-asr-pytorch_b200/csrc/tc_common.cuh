@@ -134,22 +134,20 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-// 3xTF32 operand split, in place: hi <- rna_tf32(x), lo <- rna_tf32(x - hi).  Both halves are exactly representable in
-// TF32, so the tensor core's operand truncation is a no-op and the residual error (~2^-22 relative) is unbiased.
-// Elementwise, hence independent of the (swizzled) tile layout.  `nthreads` threads cover n_f4 float4 slots.
+// 3xTF32 operand split, in place: hi <- x rounded to TF32 (nearest, ties away -- the same value cvt.rna.tf32.f32 gives,
+// but computed with two integer ops on the ALU pipe: the cvt instruction issues at a fraction of the rate and made the
+// split warps the bottleneck of the mainloop, see profiles/), lo <- x - hi (exact in fp32, |lo| <= 2^-12 |x|; the tensor
+// core truncates it to TF32, an error of <= 2^-22 |x|).  Elementwise, hence independent of the (swizzled) tile layout.
+__device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ void split_tf32_inplace(float4* __restrict__ hi, float4* __restrict__ lo, int n_f4, int t, int nthreads) {
 #pragma unroll 4
   for (int idx = t; idx < n_f4; idx += nthreads) {
-    float4 x = hi[idx], h, l;
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.x)); h.x = __uint_as_float(u);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.x - h.x)); l.x = __uint_as_float(u);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.y)); h.y = __uint_as_float(u);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.y - h.y)); l.y = __uint_as_float(u);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.z)); h.z = __uint_as_float(u);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.z - h.z)); l.z = __uint_as_float(u);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.w)); h.w = __uint_as_float(u);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x.w - h.w)); l.w = __uint_as_float(u);
+    const float4 x = hi[idx];
+    float4 h, l;
+    h.x = tf32_rn(x.x); l.x = x.x - h.x;
+    h.y = tf32_rn(x.y); l.y = x.y - h.y;
+    h.z = tf32_rn(x.z); l.z = x.z - h.z;
+    h.w = tf32_rn(x.w); l.w = x.w - h.w;
     hi[idx] = h;
     lo[idx] = l;
   }
