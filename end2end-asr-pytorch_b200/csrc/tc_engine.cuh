@@ -4,7 +4,7 @@
 //   warp 0      TMA producer            -- runs ahead across tiles through a ring of smem stages
 //   warp 1      MMA issuer + TMEM owner -- accumulates tile i into TMEM buffer (i & 1)
 //   warps 2-5   epilogue                -- drain buffer (i & 1) with tcgen05.ld while tile i+1 is being multiplied
-//   warps 6-13  3xTF32 operand split    -- hi = rna(x) in place, lo = rna(x - hi) (only when NSPLIT == 3)
+//   warps 6-13  3xTF32 operand split    -- A: smem -> (hi, lo) in TMEM; B: hi in place / lo in smem (only when NSPLIT == 3)
 // so per-tile prologue/epilogue latency is hidden behind the next tile's mainloop instead of being paid 200+ times per SM.
 //
 // A Policy supplies the problem-specific parts:
@@ -25,18 +25,24 @@ constexpr int ENG_THREADS_X1 = 192;     // TMA, MMA, 4 epilogue warps
 constexpr int ENG_THREADS_X3 = 448;     // + 8 split warps
 constexpr int ENG_SPLIT_THREADS = 256;
 
+// 3xTF32 keeps the A operand in TENSOR MEMORY: the split warps read the raw fp32 tile from smem once and write
+// hi / lo straight into TMEM (tcgen05.st), and the MMAs run in the TS form (A from TMEM, B from smem).  Shared memory then
+// holds only [A_raw | B_hi | B_lo] per stage (48 KB instead of 64 KB for a 128x128 tile -> one more stage in flight) and the
+// tensor core no longer competes with the split for smem bandwidth on the A side (an SS 128x128x8 MMA reads 8 KB of smem
+// per 64 cycles = the full 128 B/clk of the SM).
 template <class Policy, int NSPLIT> struct EngineCfg {
-  static constexpr int kStageBytes = (NSPLIT == 1 ? 1 : 2) * (Policy::kABytes + Policy::kBBytes);
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
-  static constexpr int kOffAlo = Policy::kABytes;
-  static constexpr int kOffBhi = (NSPLIT == 1 ? 1 : 2) * Policy::kABytes;
+  static constexpr int kStageBytes = NSPLIT == 1 ? (Policy::kABytes + Policy::kBBytes) : (Policy::kABytes + 2 * Policy::kBBytes);
+  static constexpr int kMaxByTmem = NSPLIT == 1 ? 8 : (512 - 2 * Policy::BN) / 64;          // 64 TMEM columns of A per stage
+  static constexpr int kBySmem = (200 * 1024) / kStageBytes;
+  static constexpr int kStages = kBySmem < kMaxByTmem ? (kBySmem > 8 ? 8 : kBySmem) : (kMaxByTmem > 8 ? 8 : kMaxByTmem);
+  static constexpr int kOffBhi = Policy::kABytes;
   static constexpr int kOffBlo = kOffBhi + Policy::kBBytes;
   static constexpr int kBarOff = kStages * kStageBytes;
   static constexpr int kSmemBytes = kBarOff + 512 + 1024;
-  static constexpr int kTmemCols = 2 * Policy::BN <= 32 ? 32 : (2 * Policy::BN <= 64 ? 64 : (2 * Policy::BN <= 128 ? 128 : 256));
+  static constexpr int kAccCols = 2 * Policy::BN;
+  static constexpr int kTmemCols = NSPLIT == 3 ? 512 : (kAccCols <= 32 ? 32 : (kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : 256)));
   static constexpr int kTxBytes = Policy::kABytes + Policy::kBBytes +
-                                  (NSPLIT == 3 && !Policy::kSplitA ? Policy::kABytes : 0) +
-                                  (NSPLIT == 3 && !Policy::kSplitB ? Policy::kBBytes : 0);   // pre-split operands arrive as hi+lo
+                                  (NSPLIT == 3 && !Policy::kSplitB ? Policy::kBBytes : 0);   // pre-split B arrives as hi+lo
   static_assert(kStages >= 2, "stage too large");
 };
 
@@ -85,7 +91,7 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           mbar_wait(empty_bar(s), ((kbg / S) & 1) ^ 1);
           const uint32_t sa = smem_base + s * Cfg::kStageBytes;
           mbar_expect_tx(full_bar(s), Cfg::kTxBytes);
-          Policy::load(p, &mapA, &mapB, tile, kb, sa, sa + Cfg::kOffAlo, sa + Cfg::kOffBhi, sa + Cfg::kOffBlo, full_bar(s));
+          Policy::load(p, &mapA, &mapB, tile, kb, sa, 0u, sa + Cfg::kOffBhi, sa + Cfg::kOffBlo, full_bar(s));
         }
       }
     }
@@ -93,7 +99,7 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (lane == 0) {
       // ---------------------------------------------------------------- MMA issuer
       constexpr uint32_t idesc = make_idesc_tf32(128, BN, Policy::kAMN, Policy::kBMN);
-      constexpr bool kNeedXfm = NSPLIT == 3 && (Policy::kSplitA || Policy::kSplitB);
+      constexpr bool kNeedXfm = NSPLIT == 3;
       uint32_t kbg = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
         const int nkb = Policy::num_kb(p, tile);
@@ -108,15 +114,17 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           const uint32_t sa = smem_base + s * Cfg::kStageBytes;
 #pragma unroll
           for (int ks = 0; ks < 4; ks++) {
-            const uint64_t a_hi = Policy::a_desc(sa, ks), b_hi = Policy::b_desc(sa + Cfg::kOffBhi, ks);
+            const uint64_t b_hi = Policy::b_desc(sa + Cfg::kOffBhi, ks);
             const uint32_t acc0 = (kb | ks) != 0 ? 1u : 0u;
             if (NSPLIT == 1) {
-              umma_tf32(d_tmem, a_hi, b_hi, idesc, acc0);
+              umma_tf32(d_tmem, Policy::a_desc(sa, ks), b_hi, idesc, acc0);
             } else {
-              const uint64_t a_lo = Policy::a_desc(sa + Cfg::kOffAlo, ks), b_lo = Policy::b_desc(sa + Cfg::kOffBlo, ks);
-              umma_tf32(d_tmem, a_lo, b_hi, idesc, acc0);
-              umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
-              umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+              constexpr uint32_t idesc_ts = make_idesc_tf32(128, BN, false, Policy::kBMN);
+              const uint64_t b_lo = Policy::b_desc(sa + Cfg::kOffBlo, ks);
+              const uint32_t a_hi = tmem_base + Cfg::kAccCols + s * 64 + ks * 8, a_lo = a_hi + 32;
+              umma_tf32_ts(d_tmem, a_lo, b_hi, idesc_ts, acc0);
+              umma_tf32_ts(d_tmem, a_hi, b_lo, idesc_ts, 1u);
+              umma_tf32_ts(d_tmem, a_hi, b_hi, idesc_ts, 1u);
             }
           }
           umma_commit(empty_bar(s));
@@ -150,18 +158,51 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
   } else {
     // ------------------------------------------------------------------ operand split warps (3xTF32 only)
-    if (NSPLIT == 3 && (Policy::kSplitA || Policy::kSplitB)) {
+    if (NSPLIT == 3) {
       const int t = threadIdx.x - 192;
+      const int quarter = warp & 3;                 // TMEM lanes this warp may touch
+      const int khalf = (warp - 6) >> 2;            // k columns [16*khalf, +16) of the 32-deep block
+      const int row = quarter * 32 + lane;          // A-tile row owned by this thread
       uint32_t kbg = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int nkb = Policy::num_kb(p, tile);
         for (int kb = 0; kb < nkb; kb++, kbg++) {
           const int s = kbg % S;
           mbar_wait(full_bar(s), (kbg / S) & 1);
-          float4* stage = reinterpret_cast<float4*>(gen_base + s * Cfg::kStageBytes);
-          if (Policy::kSplitA) split_tf32_inplace(stage, stage + Cfg::kOffAlo / 16, Policy::kABytes / 16, t, ENG_SPLIT_THREADS);
-          if (Policy::kSplitB) split_tf32_inplace(stage + Cfg::kOffBhi / 16, stage + Cfg::kOffBlo / 16, Policy::kBBytes / 16, t, ENG_SPLIT_THREADS);
-          fence_proxy_async_smem();
+          const uint8_t* araw = gen_base + s * Cfg::kStageBytes;
+          float hi[16], lo[16];
+          if (!Policy::kAMN) {
+            // K-major tile: row = 128 B, 16-byte chunk j stored at chunk (j ^ (row & 7)) (128B swizzle)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const int chunk = (khalf * 4 + j) ^ (row & 7);
+              const float4 x = *reinterpret_cast<const float4*>(araw + row * 128 + chunk * 16);
+              hi[j * 4 + 0] = tf32_rn(x.x); lo[j * 4 + 0] = x.x - hi[j * 4 + 0];
+              hi[j * 4 + 1] = tf32_rn(x.y); lo[j * 4 + 1] = x.y - hi[j * 4 + 1];
+              hi[j * 4 + 2] = tf32_rn(x.z); lo[j * 4 + 2] = x.z - hi[j * 4 + 2];
+              hi[j * 4 + 3] = tf32_rn(x.w); lo[j * 4 + 3] = x.w - hi[j * 4 + 3];
+            }
+          } else {
+            // MN-major tile: chunk (row/32) of 32 k-lines x 128 B; 32-byte atom a = (row%32)/8 stored at atom (a ^ (k & 3))
+            const uint8_t* cbase = araw + (row >> 5) * 4096 + (row & 7) * 4;
+            const int atom = (row & 31) >> 3;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+              const int k = khalf * 16 + j;
+              const float x = *reinterpret_cast<const float*>(cbase + k * 128 + ((atom ^ (k & 3)) << 5));
+              hi[j] = tf32_rn(x); lo[j] = x - hi[j];
+            }
+          }
+          const uint32_t acol = tmem_base + ((uint32_t)(quarter * 32) << 16) + Cfg::kAccCols + s * 64 + khalf * 16;
+          tmem_st16(acol, hi);
+          tmem_st16(acol + 32, lo);
+          if (Policy::kSplitB) {
+            float4* stage = reinterpret_cast<float4*>(gen_base + s * Cfg::kStageBytes);
+            split_tf32_inplace(stage + Cfg::kOffBhi / 16, stage + Cfg::kOffBlo / 16, Policy::kBBytes / 16, t, ENG_SPLIT_THREADS);
+            fence_proxy_async_smem();
+          }
+          tmem_wait_st();
+          tc_fence_before();
           mbar_arrive(xfm_bar(s));
         }
       }
