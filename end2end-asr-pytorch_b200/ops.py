@@ -305,7 +305,8 @@ class SdpaFn(torch.autograd.Function):
                                         int(causal), L.ptr(out), *os_, L.ptr(lse), B, H, Tq, Tk, dk, dv, float(scale),
                                         float(p_drop), seed, off, prec, _stream()), "sdpa_fwd")
         ctx.save_for_backward(q, k, v, out, lse, key_pad, dense_mask)
-        ctx.meta = (int(causal), float(scale), float(p_drop), seed, off, config.attn_bwd)
+        bwd_prec = config.attn_bwd if (dk in (32, 64) and dv in (32, 64)) else L.PREC_FP32
+        ctx.meta = (int(causal), float(scale), float(p_drop), seed, off, bwd_prec)
         return out
 
     @staticmethod

@@ -113,20 +113,22 @@ def test_conv3x3_forward_and_dgrad_tensor_core(L, B, T, F_, Ci, Co, prec, tol):
     (2, 3, 70, 70, 64, 32, "dense"), (1, 2, 129, 65, 32, 64, "none"), (2, 2, 100, 100, 64, 64, "causal"),
     (1, 1, 200, 200, 64, 64, "keypad"), (1, 2, 300, 448, 64, 64, "keypad"), (2, 2, 257, 400, 64, 64, "none"),
 ])
-def test_attention_forward_tensor_core(L, B, H, Tq, Tk, dk, dv, mode):
+@pytest.mark.parametrize("bwd", ["fp32", "tf32"])
+def test_attention_tensor_core(L, B, H, Tq, Tk, dk, dv, mode, bwd):
+    """tcgen05 forward with either the fp32 CUDA-core backward or the tcgen05 backward (dK/dV kernel + dQ kernel)."""
     import importlib
     import b200asr
     from tests.test_gpu_parity import _attention_case
     ops = importlib.import_module(b200asr.__name__ + ".ops")
     old = (ops.config.attn, ops.config.attn_bwd)
-    ops.config.set(attn="tf32", attn_bwd="fp32")
+    ops.config.set(attn="tf32", attn_bwd=bwd)
     try:
         pairs = _attention_case(ops, B, H, Tq, Tk, dk, dv, mode)
     finally:
         ops.config.attn, ops.config.attn_bwd = old
     (got, ref) = pairs[0]
     assert rel_err(got, ref) < 2e-3
-    for got, ref in pairs[1:]:          # backward (fp32 kernel) consumes the tcgen05 forward's O and LSE
+    for got, ref in pairs[1:]:
         assert rel_err(got, ref) < 3e-3
 
 

@@ -28,19 +28,19 @@ print("oracle fp64+fp32 %.1fs; fp32 oracle vs fp64: pred %.2e loss %.2e grads %.
     max(grads_rel_err(grads32, {k: v.float() for k, v in grads64.items()}).values())))
 real = gold.ne(O.PAD)
 model = cuda_model(cfg, P)
-mixes = [("fp32", "fp32", "fp32", "fp32"), ("tf32x3", "tf32x3", "tf32x3", "fp32"), ("tf32x3", "tf32", "tf32", "fp32"),
-         ("tf32", "tf32", "tf32", "fp32"), ("tf32x3", "tf32x3", "tf32x3", "tf32"), ("fp32", "fp32", "fp32", "tf32"),
-         ("tf32", "tf32x3", "tf32x3", "fp32")]
-for lin, conv, convw, attn in mixes:
-    ops.config.set(linear=lin, conv=conv, conv_wgrad=convw, attn=attn, attn_bwd="fp32")
+mixes = [("fp32", "fp32", "fp32", "fp32", "fp32"), ("tf32x3", "tf32x3", "tf32x3", "fp32", "fp32"),
+         ("tf32x3", "tf32x3", "tf32x3", "tf32", "tf32"), ("tf32x3", "tf32x3", "tf32x3", "tf32", "fp32"),
+         ("fp32", "fp32", "fp32", "tf32", "tf32"), ("tf32x3", "tf32", "tf32", "tf32", "tf32"), ("tf32", "tf32", "tf32", "tf32", "tf32")]
+for lin, conv, convw, attn, attnb in mixes:
+    ops.config.set(linear=lin, conv=conv, conv_wgrad=convw, attn=attn, attn_bwd=attnb)
     try:
         pred, g2, hyp, loss, stats, grads = cuda_step(model, src, lens, tgt, 0.1)
     except RuntimeError as e:
-        print((lin, conv, convw, attn), "ERROR", str(e)[:150])
+        print((lin, conv, convw, attn, attnb), "ERROR", str(e)[:150])
         continue
     errs = grads_rel_err(grads, {k: v.float() for k, v in grads64.items()})
     worst = max(errs, key=errs.get)
     flips = int((hyp[real] != hyp64[real]).sum())
-    print("linear=%-6s conv=%-6s conv_wgrad=%-6s attn=%-4s | pred %.2e loss %.2e grads max %.2e (%s) median %.2e argmax flips %d/%d" % (
-        lin, conv, convw, attn, rel_err(pred, pred64), abs(loss.item() - loss64.item()) / abs(loss64.item()), errs[worst], worst,
+    print("linear=%-6s conv=%-6s conv_wgrad=%-6s attn=%-4s/%-4s | pred %.2e loss %.2e grads max %.2e (%s) median %.2e argmax flips %d/%d" % (
+        lin, conv, convw, attn, attnb, rel_err(pred, pred64), abs(loss.item() - loss64.item()) / abs(loss64.item()), errs[worst], worst,
         sorted(errs.values())[len(errs) // 2], flips, int(real.sum())))
