@@ -12,11 +12,12 @@
 namespace b200asr {
 
 // ------------------------------------------------------------------------------------------------ conv1
-// x [B,F,T] -> y [B,T,F,Co]; weights w[Co][1][3(f)][3(t)]
+// x [B,F,T] -> y [B,T,F,Co]; weights w[Co][1][3(f)][3(t)].  One CTA walks output rows (b,t); a thread owns a channel quad
+// and a freq phase, so a warp stores 2 pixels x 256 B = 512 contiguous bytes and no integer division is needed.
 __global__ void __launch_bounds__(256) conv3x3_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ bias, float* __restrict__ y,
                                                              int B, int F, int T, int Co, int relu) {
-  const int cqs = Co >> 2;                 // channel quads per pixel
+  const int cqs = Co >> 2;
   const int cq = threadIdx.x % cqs;
   const int slot = threadIdx.x / cqs;
   const int slots = blockDim.x / cqs;
@@ -27,29 +28,30 @@ __global__ void __launch_bounds__(256) conv3x3_c1_fwd_kernel(const float* __rest
 #pragma unroll
     for (int t = 0; t < 9; t++) wr[c][t] = w[(cq * 4 + c) * 9 + t];
   }
-  const long long P = (long long)B * T * F;
-  for (long long p = (long long)blockIdx.x * slots + slot; p < P; p += (long long)gridDim.x * slots) {
-    const int f = (int)(p % F);
-    const long long bt = p / F;
-    const int t = (int)(bt % T), b = (int)(bt / T);
+  const int rows = B * T;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int b = r / T, t = r - b * T;
     const float* xb = x + (size_t)b * F * T;
-    float in[9];
+    float* yrow = y + (size_t)r * F * Co;
+    for (int f = slot; f < F; f += slots) {
+      float in[9];
 #pragma unroll
-    for (int df = 0; df < 3; df++)
+      for (int df = 0; df < 3; df++)
 #pragma unroll
-      for (int dt = 0; dt < 3; dt++) {
-        int ff = f + df - 1, tt = t + dt - 1;
-        in[df * 3 + dt] = (ff >= 0 && ff < F && tt >= 0 && tt < T) ? __ldg(xb + (size_t)ff * T + tt) : 0.f;
+        for (int dt = 0; dt < 3; dt++) {
+          const int ff = f + df - 1, tt = t + dt - 1;
+          in[df * 3 + dt] = (ff >= 0 && ff < F && tt >= 0 && tt < T) ? __ldg(xb + (size_t)ff * T + tt) : 0.f;
+        }
+      float o[4];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        float a = br[c];
+#pragma unroll
+        for (int k = 0; k < 9; k++) a = fmaf(in[k], wr[c][k], a);
+        o[c] = relu ? fmaxf(a, 0.f) : a;
       }
-    float o[4];
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-      float a = br[c];
-#pragma unroll
-      for (int k = 0; k < 9; k++) a = fmaf(in[k], wr[c][k], a);
-      o[c] = relu ? fmaxf(a, 0.f) : a;
+      *reinterpret_cast<float4*>(yrow + (size_t)f * Co + cq * 4) = make_float4(o[0], o[1], o[2], o[3]);
     }
-    *reinterpret_cast<float4*>(y + (size_t)p * Co + cq * 4) = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -67,25 +69,26 @@ __global__ void __launch_bounds__(256) conv3x3_c1_wgrad_kernel(const float* __re
   for (int c = 0; c < 4; c++)
 #pragma unroll
     for (int k = 0; k < 10; k++) acc[c][k] = 0.f;
-  const long long P = (long long)B * T * F;
-  for (long long p = (long long)blockIdx.x * slots + slot; p < P; p += (long long)gridDim.x * slots) {
-    const int f = (int)(p % F);
-    const long long bt = p / F;
-    const int t = (int)(bt % T), b = (int)(bt / T);
+  const int rows = B * T;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int b = r / T, t = r - b * T;
     const float* xb = x + (size_t)b * F * T;
-    const float4 g = *reinterpret_cast<const float4*>(dy + (size_t)p * Co + cq * 4);
-    const float gv[4] = {g.x, g.y, g.z, g.w};
+    const float* dyrow = dy + (size_t)r * F * Co;
+    for (int f = slot; f < F; f += slots) {
+      const float4 g = *reinterpret_cast<const float4*>(dyrow + (size_t)f * Co + cq * 4);
+      const float gv[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
-    for (int df = 0; df < 3; df++)
+      for (int df = 0; df < 3; df++)
 #pragma unroll
-      for (int dt = 0; dt < 3; dt++) {
-        int ff = f + df - 1, tt = t + dt - 1;
-        float v = (ff >= 0 && ff < F && tt >= 0 && tt < T) ? __ldg(xb + (size_t)ff * T + tt) : 0.f;
+        for (int dt = 0; dt < 3; dt++) {
+          const int ff = f + df - 1, tt = t + dt - 1;
+          const float v = (ff >= 0 && ff < F && tt >= 0 && tt < T) ? __ldg(xb + (size_t)ff * T + tt) : 0.f;
 #pragma unroll
-        for (int c = 0; c < 4; c++) acc[c][df * 3 + dt] = fmaf(gv[c], v, acc[c][df * 3 + dt]);
-      }
+          for (int c = 0; c < 4; c++) acc[c][df * 3 + dt] = fmaf(gv[c], v, acc[c][df * 3 + dt]);
+        }
 #pragma unroll
-    for (int c = 0; c < 4; c++) acc[c][9] += gv[c];
+      for (int c = 0; c < 4; c++) acc[c][9] += gv[c];
+    }
   }
 #pragma unroll
   for (int c = 0; c < 4; c++)
@@ -508,10 +511,10 @@ int b200asr_conv3x3_c1_fwd(const float* x, const float* w, const float* bias, fl
   B200_REQUIRE(aligned16(y), B200ASR_BAD_ALIGN, "conv3x3_c1_fwd: y alignment");
   long long P = (long long)B * T * F;
   if (P <= 0) return B200ASR_OK;
-  int slots = 256 / (Co / 4);
-  long long blocks = ceil_div_ll(P, slots * 8LL);
-  int cap = device_sm_count() * 16;
-  conv3x3_c1_fwd_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, B, F, T, Co, relu);
+  long long rows = (long long)B * T;
+  B200_REQUIRE(rows < (1LL << 31), B200ASR_BAD_SHAPE, "conv3x3_c1_fwd: too many rows");
+  int cap = device_sm_count() * 32;
+  conv3x3_c1_fwd_kernel<<<(unsigned)(rows < cap ? rows : cap), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, B, F, T, Co, relu);
   return check_launch("conv3x3_c1_fwd");
 }
 

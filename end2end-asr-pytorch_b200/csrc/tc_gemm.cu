@@ -371,18 +371,19 @@ int gemm_tc(const float* A, bool a_kmaj, int lda, const float* B, bool b_kmaj, i
   }
   EpiP e{C, ldc, M, N, K, bias, relu_mask, relu, accumulate, 1, ceil_div(K, GBK) * GBK};
   const int tiles = ceil_div(M, GBM) * ceil_div(N, GBN);
-  if (!relu && !relu_mask && K >= 1024) {
+  static const int engine = [] { const char* v = getenv("B200ASR_ENGINE"); return v ? atoi(v) : 1; }();
+  if (!relu && !relu_mask && K >= 1024 && tiles * 2 <= device_sm_count()) {
+    // Split-K only for skinny outputs (weight gradients: few tiles, long contraction).  A general "split against wave
+    // quantisation" rule was measured and lost: the zero-fill plus the per-element atomic epilogue cost more than the
+    // idle SMs of the last round (linear fwd 3.5 -> 4.9 ms per step at cfg2).
     const int sms = device_sm_count();
-    if (tiles * 2 <= sms) {
-      int splits = min(min(sms / tiles, K / 256), 32);
-      if (splits > 1) {
-        e.klen = ceil_div(ceil_div(K, splits), GBK) * GBK;
-        e.splits = ceil_div(K, e.klen);
-      }
+    int splits = min(min(sms / tiles, K / 256), engine ? 16 : 32);
+    if (splits > 1) {
+      e.klen = ceil_div(ceil_div(K, splits), GBK) * GBK;
+      e.splits = ceil_div(K, e.klen);
     }
   }
   if (e.splits > 1 && !accumulate) cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * ldc, st);
-  static const int engine = [] { const char* v = getenv("B200ASR_ENGINE"); return v ? atoi(v) : 1; }();
 #define GO(AM, BM_, NS) return engine ? launch_persistent<AM, BM_, NS>(ma, mb, e, st) : launch<AM, BM_, NS>(ma, mb, e, st)
   const bool a_mn = !a_kmaj, b_mn = !b_kmaj;
   if (nsplit == 1) {
