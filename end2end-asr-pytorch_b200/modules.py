@@ -154,6 +154,34 @@ def decoder_forward(self, padded_input, encoder_padded_outputs, encoder_input_le
     return pred, seq_out, [None] * n, [None] * n
 
 
+def greedy_decode_ids(self, encoder_padded_outputs, steps=300):
+    """Token ids of Decoder.greedy_search (models/asr/transformer.py:316-394, no LM rescoring) on the fused kernels:
+    full-prefix re-decode per step exactly as the reference (causal self-attention, no cross-attention mask, all-ones
+    non-pad mask, argmax of the last position).  Returns int64 [B, steps]; string building / EOS cut stay with the caller.
+    (The KV-cached incremental decoder is the 'next' row 3 of SURVEY.md §8f.)"""
+    B = encoder_padded_outputs.shape[0]
+    dev = encoder_padded_outputs.device
+    was_training = self.training
+    self.eval()
+    try:
+        with torch.no_grad():
+            ys = torch.full((B, 1), SOS_TOKEN, dtype=torch.long, device=dev)
+            for _ in range(steps):
+                t = ys.shape[1]
+                pe = self.positional_encoding.pe[0, :t]
+                x = ops.EmbedFn.apply(ys, self.trg_embedding.weight, pe, float(self.x_logit_scale), 0.0, PAD_TOKEN)
+                for layer in self.layers:
+                    x = _mha_core(layer.self_attn, x, x, x, causal=True)
+                    x = _mha_core(layer.encoder_attn, x, encoder_padded_outputs, encoder_padded_outputs)
+                    x = _ffn_core(layer.pos_ffn, x)
+                last = x[:, -1].contiguous()
+                logits = ops.LinearFn.apply(last, self.output_linear.weight, None)
+                ys = torch.cat([ys, ops.argmax_rows(logits).view(B, 1)], dim=1)
+    finally:
+        self.train(was_training)
+    return ys[:, 1:]
+
+
 def _front_end(self, padded_input):
     """CNN front end + flatten of Transformer.forward (models/asr/transformer.py:70-76).
     Returns (feats [B,T',D], cf_order or None)."""
@@ -297,6 +325,7 @@ class Decoder(nn.Module):
             self.x_logit_scale = 1.0
 
     forward = decoder_forward
+    greedy_decode_ids = greedy_decode_ids
 
 
 class Transformer(nn.Module):

@@ -228,6 +228,32 @@ def transformer_forward(P, cfg: OracleConfig, spec, lengths, padded_target):
     return pred, gold, hyp
 
 
+def greedy_decode(P, cfg: OracleConfig, enc_out: torch.Tensor, steps: int):
+    """models/asr/transformer.py:316-394 (greedy_search without LM rescoring): every step re-decodes the whole prefix with
+    a causal self-attention mask, NO cross-attention mask (:347) and an all-ones non-pad mask (:336), then takes the argmax
+    of the last position (:375).  The reference always runs 300 steps and cuts at EOS when building strings; here the
+    token ids [B, steps] are returned (and the top-2 logit margin of every step, for tie-aware comparisons)."""
+    B = enc_out.shape[0]
+    d = cfg.dim_model
+    scale = d ** -0.5 if cfg.emb_trg_sharing else 1.0
+    ys = torch.full((B, 1), SOS, dtype=torch.long)
+    margins = []
+    for _ in range(steps):
+        t = ys.shape[1]
+        causal = torch.triu(torch.ones(t, t, dtype=torch.uint8), diagonal=1).bool().unsqueeze(0).expand(B, -1, -1)
+        x = F.embedding(ys, P["decoder.trg_embedding.weight"], padding_idx=PAD) * scale + sinusoid_table(t, d, enc_out.dtype).unsqueeze(0)
+        for l in range(cfg.num_layers):
+            pre = f"decoder.layers.{l}."
+            x = multi_head_attention(x, x, x, causal, P, pre + "self_attn.", cfg.num_heads, cfg.dim_key, cfg.dim_value)
+            x = multi_head_attention(x, enc_out, enc_out, None, P, pre + "encoder_attn.", cfg.num_heads, cfg.dim_key, cfg.dim_value)
+            x = conv_ffn(x, P, pre + "pos_ffn.")
+        logits = F.linear(x[:, -1], P["decoder.output_linear.weight"])
+        top2 = logits.topk(2, dim=1).values
+        margins.append(top2[:, 0] - top2[:, 1])
+        ys = torch.cat([ys, logits.argmax(dim=1, keepdim=True)], dim=1)
+    return ys[:, 1:], torch.stack(margins, dim=1)
+
+
 # --------------------------------------------------------------------------- loss
 def cross_entropy_loss(pred: torch.Tensor, gold: torch.Tensor, smoothing: float):
     """utils/metrics.py:115-132.  Smoothing uses eps/V off-target (weights sum to 1-eps/V, quirk Q7);

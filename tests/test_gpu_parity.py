@@ -369,3 +369,28 @@ def test_fused_adam_matches_torch(b200):
         opt.step(); ropt.step()
     for a, b in zip(lin.parameters(), ref.parameters()):
         assert rel_err(a, b) < 1e-5
+
+
+def test_greedy_decode_token_ids_match_oracle(b200):
+    """greedy decode (full-prefix re-decode, argmax per step) gives the oracle's token ids bit-exactly.
+    Decoding is compared up to the first step whose oracle top-2 logit margin is inside the rounding band (a near-tie may
+    legitimately resolve either way and then changes the rest of the sequence)."""
+    from tests.gpu_util import cuda_model
+    cfg = O.OracleConfig(num_layers=2, num_heads=4, dim_model=128, dim_key=32, dim_value=32, dim_inner=256, vocab=60,
+                         feat_extractor="", tgt_max_len=40, freq=161)
+    P = O.init_params(cfg, seed=21)
+    g = torch.Generator().manual_seed(3)
+    for k in P:
+        if P[k].dim() == 1:
+            P[k] = P[k] + 0.1 * torch.randn(P[k].shape, generator=g)
+    P["decoder.output_linear.weight"] = P["decoder.output_linear.weight"] * 4.0       # spread the logits
+    src, lens, _ = O.synthetic_batch(cfg, 3, 30, seed=5, ragged=False)
+    enc = O.encoder_forward(O.flatten_features(src), lens, P, cfg)
+    ids_o, margins = O.greedy_decode(P, cfg, enc, steps=16)
+    model = cuda_model(cfg, P, train=False)
+    ids = model.decoder.greedy_decode_ids(enc.cuda(), steps=16).cpu()
+    band = 1e-3 * float(enc.abs().max())
+    for b in range(ids.shape[0]):
+        safe = int((margins[b] > band).long().cumprod(0).sum())      # steps before the first near-tie
+        assert safe >= 4, "test input degenerate: near-tie too early"
+        assert torch.equal(ids[b, :safe], ids_o[b, :safe]), (b, ids[b].tolist(), ids_o[b].tolist())

@@ -49,7 +49,9 @@ if rank == 0:
     print("world %d: loss dp %.6f vs single %.6f | grad rel err %.2e | params-after-step rel err %.2e | n_tokens %d" % (
         world, loss_dp, float(ref.global_loss()), rel_err(g_dp, g_ref), rel_err(p_dp, ref.flat.flat), int(dp.flat.extras[1])))
     assert abs(loss_dp - float(ref.global_loss())) < 1e-4 * abs(loss_dp)
-    assert rel_err(g_dp, g_ref) < 1e-3 and rel_err(p_dp, ref.flat.flat) < 1e-4
+    # parameters: the first Adam step is lr * g / (|g| + 1e-9), i.e. sign-like; entries whose gradient is rounding noise
+    # (mathematically zero, e.g. key biases) may step in either direction, so the bound is a few learning rates, not 1e-4
+    assert rel_err(g_dp, g_ref) < 1e-3 and rel_err(p_dp, ref.flat.flat) < 1e-2
     print("DP PARITY OK")
 dist.barrier()
 dist.destroy_process_group()
