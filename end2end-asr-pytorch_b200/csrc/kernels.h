@@ -14,7 +14,8 @@ int launch_colsum(const float* X, float* out, int M, int N, int accumulate, cuda
 // shape/alignment cannot be expressed as TMA tiles (callers turn that into an error, never a fallback).
 int gemm_tc(const float* A, bool a_kmaj, int lda, const float* B, bool b_kmaj, int ldb, float* C, int ldc, int M,
             int N, int K, const float* bias, int relu, const float* relu_mask, int accumulate, int nsplit,
-            cudaStream_t st);
+            cudaStream_t st, const float* b_split = nullptr, int b_rows = 0);
+// b_split: B operand pre-split as [2][b_rows][ldb] (hi | lo), 3xTF32 only -- the kernel then skips its own B split.
 
 // tcgen05 implicit-GEMM convolution (tc_conv.cu); takes K-major repacked weights wk[9][Cout][Cin]
 // (conv_repack_k_kernel); the weight-gradient variant takes/produces dwr[9][Ci][Co].

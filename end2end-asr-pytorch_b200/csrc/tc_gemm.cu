@@ -259,11 +259,11 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const EpiP& e, c
 // ---------------------------------------------------------------------------------------------------------------------
 // GEMM policy for the persistent engine (tc_engine.cuh): tile = (m-tile, n-tile, k-split), n fastest so that the CTAs that
 // run concurrently share the same A rows through L2.
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, bool PRESPLIT = false>
 struct GemmPolicy {
   static constexpr int BN = GBN, kABytes = TILE_BYTES, kBBytes = TILE_BYTES;
-  static constexpr bool kSplitA = true, kSplitB = true, kAMN = A_MN, kBMN = B_MN;
-  struct Params { EpiP e; int tiles_m, tiles_n; };
+  static constexpr bool kSplitA = true, kSplitB = !PRESPLIT, kAMN = A_MN, kBMN = B_MN;
+  struct Params { EpiP e; int tiles_m, tiles_n, b_rows; };
   static __device__ __forceinline__ int num_tiles(const Params& p) { return p.tiles_m * p.tiles_n * p.e.splits; }
   static __device__ __forceinline__ void decode(const Params& p, int tile, int& m0, int& n0, int& z) {
     const int n = tile % p.tiles_n, r = tile / p.tiles_n;
@@ -275,7 +275,7 @@ struct GemmPolicy {
     return (kend - kbeg + GBK - 1) / GBK;
   }
   static __device__ __forceinline__ void load(const Params& p, const CUtensorMap* mapA, const CUtensorMap* mapB, int tile, int kb,
-                                              uint32_t sa, uint32_t, uint32_t sb, uint32_t, uint32_t bar) {
+                                              uint32_t sa, uint32_t, uint32_t sb, uint32_t sb_lo, uint32_t bar) {
     int m0, n0, z;
     decode(p, tile, m0, n0, z);
     const int k0 = z * p.e.klen + kb * GBK;
@@ -283,10 +283,16 @@ struct GemmPolicy {
     else
 #pragma unroll
       for (int c = 0; c < 4; c++) tma_load_2d(sa + c * 4096, mapA, bar, m0 + 32 * c, k0);
-    if (!B_MN) tma_load_2d(sb, mapB, bar, k0, n0);
-    else
+    // pre-split B: the lo half is the second [b_rows x ld] matrix of the same buffer -> same map, row offset b_rows
 #pragma unroll
-      for (int c = 0; c < 4; c++) tma_load_2d(sb + c * 4096, mapB, bar, n0 + 32 * c, k0);
+    for (int half = 0; half < (PRESPLIT ? 2 : 1); half++) {
+      const uint32_t dst = half ? sb_lo : sb;
+      const int roff = half ? p.b_rows : 0;
+      if (!B_MN) tma_load_2d(dst, mapB, bar, k0, n0 + roff);
+      else
+#pragma unroll
+        for (int c = 0; c < 4; c++) tma_load_2d(dst + c * 4096, mapB, bar, n0 + 32 * c, k0 + roff);
+    }
   }
   static __device__ __forceinline__ uint64_t a_desc(uint32_t s, int ks) {
     return A_MN ? make_smem_desc(s + ks * 1024, 4096, 512, kLayoutSW128Base32B) : make_smem_desc(s + ks * 32, 16, 1024);
@@ -335,17 +341,22 @@ struct GemmPolicy {
   }
 };
 
-template <bool A_MN, bool B_MN, int NSPLIT>
-static int launch_persistent(const CUtensorMap& ma, const CUtensorMap& mb, const EpiP& e, cudaStream_t st) {
-  typename GemmPolicy<A_MN, B_MN>::Params p{e, ceil_div(e.M, GBM), ceil_div(e.N, GBN)};
-  return launch_engine<GemmPolicy<A_MN, B_MN>, NSPLIT>(ma, mb, p, p.tiles_m * p.tiles_n * e.splits, st, "tc_gemm");
+template <bool A_MN, bool B_MN, int NSPLIT, bool PRESPLIT = false>
+static int launch_persistent(const CUtensorMap& ma, const CUtensorMap& mb, const EpiP& e, cudaStream_t st, int b_rows = 0) {
+  using Pol = GemmPolicy<A_MN, B_MN, PRESPLIT>;
+  typename Pol::Params p{e, ceil_div(e.M, GBM), ceil_div(e.N, GBN), b_rows};
+  return launch_engine<Pol, NSPLIT>(ma, mb, p, p.tiles_m * p.tiles_n * e.splits, st, "tc_gemm");
 }
 
 }  // namespace tc
 
 int gemm_tc(const float* A, bool a_kmaj, int lda, const float* B, bool b_kmaj, int ldb, float* C, int ldc, int M, int N,
-            int K, const float* bias, int relu, const float* relu_mask, int accumulate, int nsplit, cudaStream_t st) {
+            int K, const float* bias, int relu, const float* relu_mask, int accumulate, int nsplit, cudaStream_t st,
+            const float* b_split, int b_rows) {
   using namespace tc;
+  static const int engine = [] { const char* v = getenv("B200ASR_ENGINE"); return v ? atoi(v) : 1; }();
+  const bool presplit = b_split != nullptr && nsplit == 3 && engine && a_kmaj;   // fwd (B K-major) and dgrad (B MN-major)
+  if (presplit) B = b_split;
   if (M <= 0 || N <= 0) return B200ASR_OK;
   B200_REQUIRE(nsplit == 1 || nsplit == 3, B200ASR_BAD_ARG, "gemm_tc: nsplit must be 1 or 3");
   B200_REQUIRE(aligned16(A) && aligned16(B) && lda % 4 == 0 && ldb % 4 == 0, B200ASR_BAD_SHAPE,
@@ -364,14 +375,14 @@ int gemm_tc(const float* A, bool a_kmaj, int lda, const float* B, bool b_kmaj, i
   {
     uint64_t dims[2], strides[1] = {(uint64_t)ldb};
     uint32_t box[2];
-    if (b_kmaj) { dims[0] = (uint64_t)K; dims[1] = (uint64_t)N; box[0] = GBK; box[1] = GBN; }
-    else        { dims[0] = (uint64_t)N; dims[1] = (uint64_t)K; box[0] = 32;  box[1] = GBK; }
+    // pre-split B = [hi | lo] stacked along the row axis of the weight matrix (b_rows rows each)
+    if (b_kmaj) { dims[0] = (uint64_t)K; dims[1] = (uint64_t)(presplit ? 2 * b_rows : N); box[0] = GBK; box[1] = GBN; }
+    else        { dims[0] = (uint64_t)N; dims[1] = (uint64_t)(presplit ? 2 * b_rows : K); box[0] = 32;  box[1] = GBK; }
     rc = make_tensor_map_f32(&mb, B, 2, dims, strides, box, !b_kmaj, nsplit == 1);
     if (rc) return rc;
   }
   EpiP e{C, ldc, M, N, K, bias, relu_mask, relu, accumulate, 1, ceil_div(K, GBK) * GBK};
   const int tiles = ceil_div(M, GBM) * ceil_div(N, GBN);
-  static const int engine = [] { const char* v = getenv("B200ASR_ENGINE"); return v ? atoi(v) : 1; }();
   if (!relu && !relu_mask && K >= 1024 && tiles * 2 <= device_sm_count()) {
     // Split-K only for skinny outputs (weight gradients: few tiles, long contraction).  A general "split against wave
     // quantisation" rule was measured and lost: the zero-fill plus the per-element atomic epilogue cost more than the
@@ -386,6 +397,10 @@ int gemm_tc(const float* A, bool a_kmaj, int lda, const float* B, bool b_kmaj, i
   if (e.splits > 1 && !accumulate) cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * ldc, st);
 #define GO(AM, BM_, NS) return engine ? launch_persistent<AM, BM_, NS>(ma, mb, e, st) : launch<AM, BM_, NS>(ma, mb, e, st)
   const bool a_mn = !a_kmaj, b_mn = !b_kmaj;
+  if (presplit) {
+    if (!b_mn) return launch_persistent<false, false, 3, true>(ma, mb, e, st, b_rows);
+    return launch_persistent<false, true, 3, true>(ma, mb, e, st, b_rows);
+  }
   if (nsplit == 1) {
     if (!a_mn && !b_mn) GO(false, false, 1);
     if (!a_mn && b_mn) GO(false, true, 1);

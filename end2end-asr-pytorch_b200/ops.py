@@ -139,21 +139,30 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------------------------- dense layers
-def linear_fwd(x2, w, b, relu, prec):
+def split_weight(w2, prec):
+    """[2,N,K] = (rn_tf32(w), w - hi) for the 3xTF32 GEMM (done once per step and weight; the backward reuses it)."""
+    if prec != L.PREC_TF32X3:
+        return None
+    ws = torch.empty((2,) + tuple(w2.shape), device=w2.device, dtype=torch.float32)
+    L.check(_lib().b200asr_split_tf32(L.ptr(w2), L.ptr(ws), w2.numel(), _stream()), "split_tf32")
+    return ws
+
+
+def linear_fwd(x2, w, b, relu, prec, w_split=None):
     M, K = x2.shape
     N = w.shape[0]
     y = torch.empty((M, N), device=x2.device, dtype=torch.float32)
-    L.check(_lib().b200asr_linear_fwd(L.ptr(x2), L.ptr(w), L.ptr(b), L.ptr(y), M, N, K, int(relu), prec, _stream()),
-            "linear_fwd")
+    L.check(_lib().b200asr_linear_fwd(L.ptr(x2), L.ptr(w), L.ptr(b), L.ptr(y), M, N, K, int(relu), prec, L.ptr(w_split),
+                                      _stream()), "linear_fwd")
     return y
 
 
-def linear_bwd_data(dy2, w, relu_out, prec):
+def linear_bwd_data(dy2, w, relu_out, prec, w_split=None):
     M, N = dy2.shape
     K = w.shape[1]
     dx = torch.empty((M, K), device=dy2.device, dtype=torch.float32)
     L.check(_lib().b200asr_linear_bwd_data(L.ptr(dy2), L.ptr(w), L.ptr(relu_out), L.ptr(dx), M, N, K, 0, prec,
-                                           _stream()), "linear_bwd_data")
+                                           L.ptr(w_split), _stream()), "linear_bwd_data")
     return dx
 
 
@@ -182,18 +191,19 @@ class LinearFn(torch.autograd.Function):
         w2 = _f32c(w.reshape(w.shape[0], -1))
         x2 = _f32c(x).reshape(-1, w2.shape[1])
         ctx.prec = _linear_prec(w2.shape[0], w2.shape[1])
-        y = linear_fwd(x2, w2, b, False, ctx.prec)
-        ctx.save_for_backward(x2, w2)
+        ws = split_weight(w2, ctx.prec)
+        y = linear_fwd(x2, w2, b, False, ctx.prec, ws)
+        ctx.save_for_backward(x2, w2, ws)
         ctx.xshape, ctx.wshape, ctx.has_bias = x.shape, w.shape, b is not None
         return y.view(*x.shape[:-1], w2.shape[0])
 
     @staticmethod
     def backward(ctx, dy):
-        x2, w2 = ctx.saved_tensors
+        x2, w2, ws = ctx.saved_tensors
         dy2 = _f32c(dy).reshape(-1, w2.shape[0])
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = linear_bwd_data(dy2, w2, None, ctx.prec).view(ctx.xshape)
+            dx = linear_bwd_data(dy2, w2, None, ctx.prec, ws).view(ctx.xshape)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dw, db = linear_bwd_weight(dy2, x2, ctx.has_bias, ctx.prec)
             dw = dw.view(ctx.wshape)
@@ -210,21 +220,22 @@ class FFNFn(torch.autograd.Function):
         w2m = _f32c(w2.reshape(w2.shape[0], -1))
         x2 = _f32c(x).reshape(-1, w1m.shape[1])
         ctx.prec = _linear_prec(w1m.shape[0], w1m.shape[1])
-        h = linear_fwd(x2, w1m, b1, True, ctx.prec)
-        y = linear_fwd(h, w2m, b2, False, ctx.prec)
-        ctx.save_for_backward(x2, h, w1m, w2m)
+        ws1, ws2 = split_weight(w1m, ctx.prec), split_weight(w2m, ctx.prec)
+        h = linear_fwd(x2, w1m, b1, True, ctx.prec, ws1)
+        y = linear_fwd(h, w2m, b2, False, ctx.prec, ws2)
+        ctx.save_for_backward(x2, h, w1m, w2m, ws1, ws2)
         ctx.shapes = (x.shape, w1.shape, w2.shape)
         return y.view(*x.shape[:-1], w2m.shape[0])
 
     @staticmethod
     def backward(ctx, dy):
-        x2, h, w1m, w2m = ctx.saved_tensors
+        x2, h, w1m, w2m, ws1, ws2 = ctx.saved_tensors
         xs, w1s, w2s = ctx.shapes
         dy2 = _f32c(dy).reshape(-1, w2m.shape[0])
         dw2, db2 = linear_bwd_weight(dy2, h, True, ctx.prec)
-        dh = linear_bwd_data(dy2, w2m, h, ctx.prec)          # masked by relu'(h)
+        dh = linear_bwd_data(dy2, w2m, h, ctx.prec, ws2)     # masked by relu'(h)
         dw1, db1 = linear_bwd_weight(dh, x2, True, ctx.prec)
-        dx = linear_bwd_data(dh, w1m, None, ctx.prec) if ctx.needs_input_grad[0] else None
+        dx = linear_bwd_data(dh, w1m, None, ctx.prec, ws1) if ctx.needs_input_grad[0] else None
         return (dx.view(xs) if dx is not None else None), dw1.view(w1s), db1, dw2.view(w2s), db2
 
 

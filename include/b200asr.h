@@ -58,10 +58,14 @@ unsigned long long b200asr_launch_count(void);
  * y[M,N] = act(x[M,K] * w[N,K]^T + bias[N]);  bias may be NULL; relu != 0 applies max(0, .)
  */
 int b200asr_linear_fwd(const float* x, const float* w, const float* bias, float* y, int M, int N, int K,
-                       int relu, int precision, b200asr_stream_t stream);
+                       int relu, int precision, const float* w_split, b200asr_stream_t stream);
 /* dx[M,K] (+)= (dy[M,N] * w[N,K]) .* (relu_out[M,K] > 0 if relu_out != NULL) */
 int b200asr_linear_bwd_data(const float* dy, const float* w, const float* relu_out, float* dx, int M, int N,
-                            int K, int accumulate, int precision, b200asr_stream_t stream);
+                            int K, int accumulate, int precision, const float* w_split, b200asr_stream_t stream);
+/* w_split (optional, precision 3 only): the weight pre-split for the 3xTF32 path by b200asr_split_tf32 --
+ * [2][N][K] = hi = rn_tf32(w) followed by lo = w - hi.  Passing it removes the per-tile weight split from the GEMM
+ * (the forward's split is reused by the backward); NULL keeps the split inside the kernel. */
+int b200asr_split_tf32(const float* src, float* dst_hi_lo, long long n, b200asr_stream_t stream);
 /* dw[N,K] (+)= dy[M,N]^T * x[M,K];  dbias[N] (+)= column sums of dy (dbias may be NULL) */
 int b200asr_linear_bwd_weight(const float* dy, const float* x, float* dw, float* dbias, int M, int N, int K,
                               int accumulate, int precision, b200asr_stream_t stream);

@@ -66,3 +66,24 @@ def vgg_pools_well_separated(P, x, rel_gap=3e-6):
         h2 = F.relu(F.conv2d(F.relu(F.conv2d(x, P["conv.0.weight"], P["conv.0.bias"], padding=1)), P["conv.2.weight"], P["conv.2.bias"], padding=1))
         h4 = F.relu(F.conv2d(F.relu(F.conv2d(F.max_pool2d(h2, 2, 2), P["conv.5.weight"], P["conv.5.bias"], padding=1)), P["conv.7.weight"], P["conv.7.bias"], padding=1))
     return pool_windows_well_separated(h2, rel_gap) and pool_windows_well_separated(h4, rel_gap)
+
+
+def assert_grads_close(grads: dict, ref: dict, tol: float, exact_kernels: bool):
+    """Gradient parity criterion.
+    exact_kernels=True (fp32 CUDA-core mode): every tensor within `tol` in the max norm (with the floor of grads_rel_err).
+    Tensor-core default mode: arithmetic differs from fp32 by ~1e-5, which is enough to flip individual ReLU / max-pool
+    decisions that sit within rounding of their threshold (a discontinuity of the MODEL -- the reference on a GPU with TF32
+    convolutions shows the same); a flipped unit moves O(1/n_tokens) of a weight-gradient row.  The bound is therefore:
+    median tensor error <= tol, and every tensor <= 10*tol in the relative L2 norm."""
+    errs = grads_rel_err(grads, ref)
+    worst = max(errs, key=errs.get)
+    if exact_kernels:
+        assert errs[worst] < tol, (worst, errs[worst])
+        return
+    med = sorted(errs.values())[len(errs) // 2]
+    assert med < tol, ("median", med)
+    gmax = max(float(v.abs().max()) for v in ref.values())
+    for k, r in ref.items():
+        g = grads[k].detach().double().cpu()
+        denom = max(float(r.double().norm()), 1e-3 * gmax * r.numel() ** 0.5)
+        assert float((g - r.double()).norm()) / denom < 10 * tol, k

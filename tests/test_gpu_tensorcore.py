@@ -36,7 +36,7 @@ def test_linear_forward_tensor_core(L, M, N, K, prec, tol):
     b = torch.randn(N, generator=g).cuda()
     ref = (x.double() @ w.double().t() + b.double()).relu()
     y = torch.full((M, N), float("nan"), device="cuda")
-    L.check(lib.b200asr_linear_fwd(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), M, N, K, 1, prec, _stream()), "linear_fwd")
+    L.check(lib.b200asr_linear_fwd(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), M, N, K, 1, prec, None, _stream()), "linear_fwd")
     torch.cuda.synchronize()
     assert rel_err(y, ref) < tol
 
@@ -52,7 +52,7 @@ def test_linear_backward_tensor_core(L, M, N, K, prec, tol):
     dy = torch.randn(M, N, generator=g).cuda()
     h = torch.randn(M, K, generator=g).cuda()
     dx = torch.full((M, K), float("nan"), device="cuda")
-    L.check(lib.b200asr_linear_bwd_data(L.ptr(dy), L.ptr(w), L.ptr(h), L.ptr(dx), M, N, K, 0, prec, _stream()), "bwd_data")
+    L.check(lib.b200asr_linear_bwd_data(L.ptr(dy), L.ptr(w), L.ptr(h), L.ptr(dx), M, N, K, 0, prec, None, _stream()), "bwd_data")
     ref_dx = (dy.double() @ w.double()) * (h > 0)
     assert rel_err(dx, ref_dx) < tol
     dw = torch.full((N, K), float("nan"), device="cuda")
@@ -70,7 +70,7 @@ def test_linear_backward_tensor_core(L, M, N, K, prec, tol):
 def test_unaligned_shapes_are_rejected_not_rerouted(L):
     lib = L.load()
     x = torch.randn(8, 161).cuda(); w = torch.randn(16, 161).cuda(); y = torch.empty(8, 16).cuda()
-    rc = lib.b200asr_linear_fwd(L.ptr(x), L.ptr(w), None, L.ptr(y), 8, 16, 161, 0, 3, _stream())
+    rc = lib.b200asr_linear_fwd(L.ptr(x), L.ptr(w), None, L.ptr(y), 8, 16, 161, 0, 3, None, _stream())
     assert rc == -1 and "multiples of 4" in L.last_error()
 
 
@@ -158,3 +158,21 @@ def test_conv3x3_weight_gradient_tensor_core(L, B, T, F_, Ci, Co, prec, tol):
     L.check(lib.b200asr_conv3x3_bwd_weight(L.ptr(dyc), L.ptr(xc), L.ptr(dw), L.ptr(db), L.ptr(ws), B, T, F_, Ci, Co, prec, _stream()), "conv wgrad")
     assert rel_err(dw, dw_ref) < tol
     assert rel_err(db, dy.double().sum((0, 2, 3))) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 512, 512), (130, 4364, 128), (77, 52, 164), (800, 512, 1280)])
+def test_linear_with_presplit_weights(L, M, N, K):
+    """3xTF32 GEMM with the weight pre-split once by b200asr_split_tf32 (forward K-major B, data-gradient MN-major B)."""
+    lib = L.load()
+    g = torch.Generator().manual_seed(5 * M + N)
+    x = torch.randn(M, K, generator=g).cuda(); w = torch.randn(N, K, generator=g).cuda(); b = torch.randn(N, generator=g).cuda()
+    dy = torch.randn(M, N, generator=g).cuda()
+    ws = torch.empty(2, N, K, device="cuda")
+    L.check(lib.b200asr_split_tf32(L.ptr(w), L.ptr(ws), N * K, _stream()), "split")
+    assert torch.equal(ws[0] + ws[1], w) and float((ws[1].abs() / w.abs().clamp_min(1e-30)).max()) < 2.0 ** -11
+    y = torch.full((M, N), float("nan"), device="cuda")
+    L.check(lib.b200asr_linear_fwd(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y), M, N, K, 0, 3, L.ptr(ws), _stream()), "fwd")
+    assert rel_err(y, x.double() @ w.double().t() + b.double()) < 2e-5
+    dx = torch.full((M, K), float("nan"), device="cuda")
+    L.check(lib.b200asr_linear_bwd_data(L.ptr(dy), L.ptr(w), None, L.ptr(dx), M, N, K, 0, 3, L.ptr(ws), _stream()), "dgrad")
+    assert rel_err(dx, dy.double() @ w.double()) < 1e-4
