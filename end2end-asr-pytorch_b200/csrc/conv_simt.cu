@@ -12,15 +12,26 @@
 namespace b200asr {
 
 // ------------------------------------------------------------------------------------------------ conv1
-// x [B,F,T] -> y [B,T,F,Co]; weights w[Co][1][3(f)][3(t)].  One CTA walks output rows (b,t); a thread owns a channel quad
-// and a freq phase, so a warp stores 2 pixels x 256 B = 512 contiguous bytes and no integer division is needed.
+// x [B,F,T] -> y [B,T,F,Co]; weights w[Co][1][3(f)][3(t)].  A CTA owns a 32 (time) x 8 (freq) pixel tile: the input patch
+// with halo (10 x 34 floats) is staged in shared memory with loads coalesced along time, and each thread owns one channel
+// quad, so a warp stores 2 pixels x 256 B = 512 contiguous bytes.  Store-bound by design (1.06 GB at cfg2).
+constexpr int C1_TT = 32, C1_TF = 8;
+
 __global__ void __launch_bounds__(256) conv3x3_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                              const float* __restrict__ bias, float* __restrict__ y,
                                                              int B, int F, int T, int Co, int relu) {
+  __shared__ float patch[C1_TF + 2][C1_TT + 2 + 1];
   const int cqs = Co >> 2;
   const int cq = threadIdx.x % cqs;
   const int slot = threadIdx.x / cqs;
   const int slots = blockDim.x / cqs;
+  const int t0 = blockIdx.x * C1_TT, f0 = blockIdx.y * C1_TF, b = blockIdx.z;
+  const float* xb = x + (size_t)b * F * T;
+  for (int i = threadIdx.x; i < (C1_TF + 2) * (C1_TT + 2); i += blockDim.x) {
+    const int pf = i / (C1_TT + 2), pt = i - pf * (C1_TT + 2);
+    const int ff = f0 + pf - 1, tt = t0 + pt - 1;
+    patch[pf][pt] = (ff >= 0 && ff < F && tt >= 0 && tt < T) ? xb[(size_t)ff * T + tt] : 0.f;
+  }
   float wr[4][9], br[4];
 #pragma unroll
   for (int c = 0; c < 4; c++) {
@@ -28,38 +39,31 @@ __global__ void __launch_bounds__(256) conv3x3_c1_fwd_kernel(const float* __rest
 #pragma unroll
     for (int t = 0; t < 9; t++) wr[c][t] = w[(cq * 4 + c) * 9 + t];
   }
-  const int rows = B * T;
-  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
-    const int b = r / T, t = r - b * T;
-    const float* xb = x + (size_t)b * F * T;
-    float* yrow = y + (size_t)r * F * Co;
-    for (int f = slot; f < F; f += slots) {
-      float in[9];
+  __syncthreads();
+  for (int px = slot; px < C1_TT * C1_TF; px += slots) {      // pixel order: freq fastest -> contiguous output
+    const int tl = px / C1_TF, fl = px - tl * C1_TF;
+    const int t = t0 + tl, f = f0 + fl;
+    if (t >= T || f >= F) continue;
+    float o[4] = {br[0], br[1], br[2], br[3]};
 #pragma unroll
-      for (int df = 0; df < 3; df++)
+    for (int df = 0; df < 3; df++)
 #pragma unroll
-        for (int dt = 0; dt < 3; dt++) {
-          const int ff = f + df - 1, tt = t + dt - 1;
-          in[df * 3 + dt] = (ff >= 0 && ff < F && tt >= 0 && tt < T) ? __ldg(xb + (size_t)ff * T + tt) : 0.f;
-        }
-      float o[4];
+      for (int dt = 0; dt < 3; dt++) {
+        const float v = patch[fl + df][tl + dt];
 #pragma unroll
-      for (int c = 0; c < 4; c++) {
-        float a = br[c];
-#pragma unroll
-        for (int k = 0; k < 9; k++) a = fmaf(in[k], wr[c][k], a);
-        o[c] = relu ? fmaxf(a, 0.f) : a;
+        for (int c = 0; c < 4; c++) o[c] = fmaf(v, wr[c][df * 3 + dt], o[c]);
       }
-      *reinterpret_cast<float4*>(yrow + (size_t)f * Co + cq * 4) = make_float4(o[0], o[1], o[2], o[3]);
-    }
+    if (relu) { o[0] = fmaxf(o[0], 0.f); o[1] = fmaxf(o[1], 0.f); o[2] = fmaxf(o[2], 0.f); o[3] = fmaxf(o[3], 0.f); }
+    *reinterpret_cast<float4*>(y + (((size_t)b * T + t) * F + f) * Co + cq * 4) = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
-// dw[Co][9] += sum_p dy[p][co] * x[p + tap]; dbias[co] += sum_p dy[p][co]
+// dw[Co][9] += sum_p dy[p][co] * x[p + tap]; dbias[co] += sum_p dy[p][co]; same tiling, grid-stride over tiles
 __global__ void __launch_bounds__(256) conv3x3_c1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                float* __restrict__ dw, float* __restrict__ dbias, int B,
                                                                int F, int T, int Co) {
-  extern __shared__ float red[];   // [slots][Co*10]
+  extern __shared__ float red[];   // [slots][Co*10] (also reused for nothing else)
+  __shared__ float patch[C1_TF + 2][C1_TT + 2 + 1];
   const int cqs = Co >> 2;
   const int cq = threadIdx.x % cqs;
   const int slot = threadIdx.x / cqs;
@@ -69,20 +73,31 @@ __global__ void __launch_bounds__(256) conv3x3_c1_wgrad_kernel(const float* __re
   for (int c = 0; c < 4; c++)
 #pragma unroll
     for (int k = 0; k < 10; k++) acc[c][k] = 0.f;
-  const int rows = B * T;
-  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
-    const int b = r / T, t = r - b * T;
+  const int ntt = (T + C1_TT - 1) / C1_TT, nft = (F + C1_TF - 1) / C1_TF;
+  const int ntiles = ntt * nft * B;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int ft = tile % nft, r = tile / nft;
+    const int tti = r % ntt, b = r / ntt;
+    const int t0 = tti * C1_TT, f0 = ft * C1_TF;
     const float* xb = x + (size_t)b * F * T;
-    const float* dyrow = dy + (size_t)r * F * Co;
-    for (int f = slot; f < F; f += slots) {
-      const float4 g = *reinterpret_cast<const float4*>(dyrow + (size_t)f * Co + cq * 4);
+    __syncthreads();
+    for (int i = threadIdx.x; i < (C1_TF + 2) * (C1_TT + 2); i += blockDim.x) {
+      const int pf = i / (C1_TT + 2), pt = i - pf * (C1_TT + 2);
+      const int ff = f0 + pf - 1, tt = t0 + pt - 1;
+      patch[pf][pt] = (ff >= 0 && ff < F && tt >= 0 && tt < T) ? xb[(size_t)ff * T + tt] : 0.f;
+    }
+    __syncthreads();
+    for (int px = slot; px < C1_TT * C1_TF; px += slots) {
+      const int tl = px / C1_TF, fl = px - tl * C1_TF;
+      const int t = t0 + tl, f = f0 + fl;
+      if (t >= T || f >= F) continue;
+      const float4 g = *reinterpret_cast<const float4*>(dy + (((size_t)b * T + t) * F + f) * Co + cq * 4);
       const float gv[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
       for (int df = 0; df < 3; df++)
 #pragma unroll
         for (int dt = 0; dt < 3; dt++) {
-          const int ff = f + df - 1, tt = t + dt - 1;
-          const float v = (ff >= 0 && ff < F && tt >= 0 && tt < T) ? __ldg(xb + (size_t)ff * T + tt) : 0.f;
+          const float v = patch[fl + df][tl + dt];
 #pragma unroll
           for (int c = 0; c < 4; c++) acc[c][df * 3 + dt] = fmaf(gv[c], v, acc[c][df * 3 + dt]);
         }
@@ -511,10 +526,9 @@ int b200asr_conv3x3_c1_fwd(const float* x, const float* w, const float* bias, fl
   B200_REQUIRE(aligned16(y), B200ASR_BAD_ALIGN, "conv3x3_c1_fwd: y alignment");
   long long P = (long long)B * T * F;
   if (P <= 0) return B200ASR_OK;
-  long long rows = (long long)B * T;
-  B200_REQUIRE(rows < (1LL << 31), B200ASR_BAD_SHAPE, "conv3x3_c1_fwd: too many rows");
-  int cap = device_sm_count() * 32;
-  conv3x3_c1_fwd_kernel<<<(unsigned)(rows < cap ? rows : cap), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, B, F, T, Co, relu);
+  B200_REQUIRE(B <= 65535 && ceil_div(F, C1_TF) <= 65535, B200ASR_BAD_SHAPE, "conv3x3_c1_fwd: grid too large");
+  dim3 grid(ceil_div(T, C1_TT), ceil_div(F, C1_TF), B);
+  conv3x3_c1_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, B, F, T, Co, relu);
   return check_launch("conv3x3_c1_fwd");
 }
 
@@ -529,7 +543,7 @@ int b200asr_conv3x3_c1_bwd_weight(const float* x, const float* dy, float* dw, fl
   if (P <= 0) return B200ASR_OK;
   int slots = 256 / (Co / 4);
   size_t smem = sizeof(float) * (size_t)slots * Co * 10;
-  B200_REQUIRE(smem <= 48 * 1024, B200ASR_BAD_SHAPE, "conv3x3_c1_bwd_weight: Co=%d too large", Co);
+  B200_REQUIRE(smem <= 44 * 1024, B200ASR_BAD_SHAPE, "conv3x3_c1_bwd_weight: Co=%d too large", Co);
   int blocks = device_sm_count() * 4;
   conv3x3_c1_wgrad_kernel<<<blocks, 256, smem, st>>>(x, dy, dw, dbias, B, F, T, Co);
   return check_launch("conv3x3_c1_wgrad");

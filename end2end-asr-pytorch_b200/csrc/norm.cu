@@ -6,13 +6,14 @@
 namespace b200asr {
 
 constexpr int LN_WARPS = 4;
-constexpr int LN_MAXV = 8;  // float4 per lane -> d <= 1024
+constexpr int LN_MAXV = 8;  // float4 per lane -> d <= 1024 (kernels are instantiated for NV = 1, 2, 4, 6, 8)
 
 static int ln_bwd_blocks(int rows) {
-  int b = ceil_div(rows, LN_WARPS);
-  return b < 592 ? (b < 1 ? 1 : b) : 592;
+  int b = ceil_div(rows, LN_WARPS);          // one row per warp up to 2368 CTAs: latency-bound otherwise
+  return b < 2368 ? (b < 1 ? 1 : b) : 2368;
 }
 
+template <int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 add_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ gamma,
                   const float* __restrict__ beta, const float* __restrict__ post, int period,
@@ -23,10 +24,10 @@ add_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ res, co
   const int row = blockIdx.x * LN_WARPS + warp;
   if (row >= rows) return;
   const size_t base = (size_t)row * d;
-  float4 v[LN_MAXV];
+  float4 v[NV];
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; i++) {
+  for (int i = 0; i < NV; i++) {
     int col = (i * 32 + lane) * 4;
     if (col < d) {
       float4 a = *reinterpret_cast<const float4*>(x + base + col);
@@ -49,7 +50,7 @@ add_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ res, co
   const float mean = warp_sum(sum) / (float)d;
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; i++) {
+  for (int i = 0; i < NV; i++) {
     int col = (i * 32 + lane) * 4;
     if (col < d) {
       float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
@@ -61,7 +62,7 @@ add_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ res, co
   const float rs = rowscale ? rowscale[row] : 1.f;
   const float* prow = post ? post + (size_t)(row % period) * d : nullptr;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; i++) {
+  for (int i = 0; i < NV; i++) {
     int col = (i * 32 + lane) * 4;
     if (col < d) {
       float4 g = *reinterpret_cast<const float4*>(gamma + col);
@@ -81,26 +82,27 @@ add_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ res, co
   }
 }
 
+template <int NV>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, const float* __restrict__ gamma,
                   const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                   const float* __restrict__ rowscale, float* __restrict__ dz, float* __restrict__ dx,
                   float* __restrict__ partial, int rows, int d, uint32_t thresh, float inv_keep, uint64_t key) {
-  __shared__ __align__(16) float sdg[LN_WARPS][LN_MAXV * 128];
-  __shared__ __align__(16) float sdb[LN_WARPS][LN_MAXV * 128];
+  __shared__ __align__(16) float sdg[LN_WARPS][NV * 128];
+  __shared__ __align__(16) float sdb[LN_WARPS][NV * 128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 dg[LN_MAXV], db[LN_MAXV];
+  float4 dg[NV], db[NV];
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; i++) { dg[i] = make_float4(0, 0, 0, 0); db[i] = make_float4(0, 0, 0, 0); }
+  for (int i = 0; i < NV; i++) { dg[i] = make_float4(0, 0, 0, 0); db[i] = make_float4(0, 0, 0, 0); }
   const float invd = 1.f / (float)d;
   for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
     const size_t base = (size_t)row * d;
     const float mean = mean_in[row], rstd = rstd_in[row];
     const float rs = rowscale ? rowscale[row] : 1.f;
-    float4 xh[LN_MAXV], gx[LN_MAXV];
+    float4 xh[NV], gx[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; i++) {
+    for (int i = 0; i < NV; i++) {
       int col = (i * 32 + lane) * 4;
       if (col < d) {
         float4 a = *reinterpret_cast<const float4*>(z + base + col);
@@ -119,7 +121,7 @@ add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, con
     s1 = warp_sum(s1) * invd;
     s2 = warp_sum(s2) * invd;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; i++) {
+    for (int i = 0; i < NV; i++) {
       int col = (i * 32 + lane) * 4;
       if (col < d) {
         float4 o;
@@ -140,7 +142,7 @@ add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, con
     }
   }
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; i++) {
+  for (int i = 0; i < NV; i++) {
     int col = (i * 32 + lane) * 4;
     if (col < d) {
       *reinterpret_cast<float4*>(&sdg[warp][col]) = dg[i];
@@ -202,9 +204,12 @@ int b200asr_add_ln_fwd(const float* x, const float* residual, const float* gamma
                B200ASR_BAD_ALIGN, "add_ln_fwd: pointers must be 16-byte aligned");
   if (rows <= 0) return B200ASR_OK;
   uint32_t th = p_drop > 0.f ? dropout_thresh16(p_drop) : 0u;
-  add_ln_fwd_kernel<<<ceil_div(rows, LN_WARPS), LN_WARPS * 32, 0, (cudaStream_t)stream>>>(
-      x, residual, gamma, beta, post_add, post_period, row_scale, y, z, mean, rstd, rows, d, eps, th,
-      dropout_inv_keep(p_drop), dropout_key(seed, offset));
+#define LN_FWD(NVv) add_ln_fwd_kernel<NVv><<<ceil_div(rows, LN_WARPS), LN_WARPS * 32, 0, (cudaStream_t)stream>>>( \
+      x, residual, gamma, beta, post_add, post_period, row_scale, y, z, mean, rstd, rows, d, eps, th, \
+      dropout_inv_keep(p_drop), dropout_key(seed, offset))
+  const int nv = ceil_div(d, 128);
+  if (nv <= 1) LN_FWD(1); else if (nv <= 2) LN_FWD(2); else if (nv <= 4) LN_FWD(4); else if (nv <= 6) LN_FWD(6); else LN_FWD(8);
+#undef LN_FWD
   return check_launch("add_ln_fwd");
 }
 
@@ -222,8 +227,11 @@ int b200asr_add_ln_bwd(const float* dy, const float* z, const float* gamma, cons
   }
   uint32_t th = p_drop > 0.f ? dropout_thresh16(p_drop) : 0u;
   int nblk = ln_bwd_blocks(rows);
-  add_ln_bwd_kernel<<<nblk, LN_WARPS * 32, 0, st>>>(dy, z, gamma, mean, rstd, row_scale, dz, dx, (float*)partial_ws,
-                                                    rows, d, th, dropout_inv_keep(p_drop), dropout_key(seed, offset));
+#define LN_BWD(NVv) add_ln_bwd_kernel<NVv><<<nblk, LN_WARPS * 32, 0, st>>>(dy, z, gamma, mean, rstd, row_scale, dz, dx, \
+      (float*)partial_ws, rows, d, th, dropout_inv_keep(p_drop), dropout_key(seed, offset))
+  const int nv = ceil_div(d, 128);
+  if (nv <= 1) LN_BWD(1); else if (nv <= 2) LN_BWD(2); else if (nv <= 4) LN_BWD(4); else if (nv <= 6) LN_BWD(6); else LN_BWD(8);
+#undef LN_BWD
   int rc = check_launch("add_ln_bwd");
   if (rc) return rc;
   ln_bwd_finalize_kernel<<<ceil_div(d, 32), 256, 0, st>>>((const float*)partial_ws, nblk, d, dgamma, dbeta);

@@ -166,9 +166,25 @@ def linear_bwd_data(dy2, w, relu_out, prec, w_split=None):
     return dx
 
 
-def linear_bwd_weight(dy2, x2, want_bias, prec):
+def _grad_sink(param):
+    """The parameter's existing .grad if a kernel can accumulate straight into it (the flat gradient buffer of
+    optim.FlatParams), else None.  Writing there removes autograd's AccumulateGrad add kernel and a temporary per weight."""
+    g = getattr(param, "grad", None) if param is not None else None
+    if g is None or not g.is_cuda or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != param.shape:
+        return None
+    return g
+
+
+def linear_bwd_weight(dy2, x2, want_bias, prec, w_sink=None, b_sink=None):
+    """dW = dy^T x (+ column sums).  With sinks the kernels ACCUMULATE into the given .grad tensors and (None, None) is
+    returned for them, so autograd has nothing left to add."""
     M, N = dy2.shape
     K = x2.shape[1]
+    direct = w_sink is not None and (not want_bias or b_sink is not None)
+    if direct:
+        L.check(_lib().b200asr_linear_bwd_weight(L.ptr(dy2), L.ptr(x2), L.ptr(w_sink), L.ptr(b_sink) if want_bias else None, M, N, K,
+                                                 1, prec, _stream()), "linear_bwd_weight")
+        return None, None
     dw = torch.empty((N, K), device=dy2.device, dtype=torch.float32)
     db = torch.empty((N,), device=dy2.device, dtype=torch.float32) if want_bias else None
     L.check(_lib().b200asr_linear_bwd_weight(L.ptr(dy2), L.ptr(x2), L.ptr(dw), L.ptr(db), M, N, K, 0, prec,
@@ -195,6 +211,7 @@ class LinearFn(torch.autograd.Function):
         y = linear_fwd(x2, w2, b, False, ctx.prec, ws)
         ctx.save_for_backward(x2, w2, ws)
         ctx.xshape, ctx.wshape, ctx.has_bias = x.shape, w.shape, b is not None
+        ctx.params = (w, b)
         return y.view(*x.shape[:-1], w2.shape[0])
 
     @staticmethod
@@ -205,8 +222,9 @@ class LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = linear_bwd_data(dy2, w2, None, ctx.prec, ws).view(ctx.xshape)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dw, db = linear_bwd_weight(dy2, x2, ctx.has_bias, ctx.prec)
-            dw = dw.view(ctx.wshape)
+            w, b = ctx.params
+            dw, db = linear_bwd_weight(dy2, x2, ctx.has_bias, ctx.prec, _grad_sink(w), _grad_sink(b))
+            dw = dw.view(ctx.wshape) if dw is not None else None
         return dx, dw, db
 
 
@@ -225,6 +243,7 @@ class FFNFn(torch.autograd.Function):
         y = linear_fwd(h, w2m, b2, False, ctx.prec, ws2)
         ctx.save_for_backward(x2, h, w1m, w2m, ws1, ws2)
         ctx.shapes = (x.shape, w1.shape, w2.shape)
+        ctx.params = (w1, b1, w2, b2)
         return y.view(*x.shape[:-1], w2m.shape[0])
 
     @staticmethod
@@ -232,11 +251,13 @@ class FFNFn(torch.autograd.Function):
         x2, h, w1m, w2m, ws1, ws2 = ctx.saved_tensors
         xs, w1s, w2s = ctx.shapes
         dy2 = _f32c(dy).reshape(-1, w2m.shape[0])
-        dw2, db2 = linear_bwd_weight(dy2, h, True, ctx.prec)
+        w1, b1, w2, b2 = ctx.params
+        dw2, db2 = linear_bwd_weight(dy2, h, True, ctx.prec, _grad_sink(w2), _grad_sink(b2))
         dh = linear_bwd_data(dy2, w2m, h, ctx.prec, ws2)     # masked by relu'(h)
-        dw1, db1 = linear_bwd_weight(dh, x2, True, ctx.prec)
+        dw1, db1 = linear_bwd_weight(dh, x2, True, ctx.prec, _grad_sink(w1), _grad_sink(b1))
         dx = linear_bwd_data(dh, w1m, None, ctx.prec, ws1) if ctx.needs_input_grad[0] else None
-        return (dx.view(xs) if dx is not None else None), dw1.view(w1s), db1, dw2.view(w2s), db2
+        return ((dx.view(xs) if dx is not None else None), (dw1.view(w1s) if dw1 is not None else None), db1,
+                (dw2.view(w2s) if dw2 is not None else None), db2)
 
 
 # ----------------------------------------------------------------------------------------------- residual + LN
