@@ -59,27 +59,43 @@ __global__ void conv2d_bwd_data_kernel(const float* __restrict__ dy, const float
   dx[i] = acc;
 }
 
-// one CTA per weight element (co,ci,kh,kw): reduce over (b,oh,ow)
+// one CTA per (co, ci, kh): threads run along ow (coalesced dy / x reads), each keeps the KW partial sums of its columns in
+// registers while looping over (b, oh); block reduction at the end.  KW <= 16.
 __global__ void __launch_bounds__(128) conv2d_bwd_weight_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                                 float* __restrict__ dw, ConvG g) {
-  __shared__ float red[4];
+  __shared__ float red[4][16];
   int i = blockIdx.x;
-  int kw = i % g.KW; int r = i / g.KW;
-  int kh = r % g.KH; r /= g.KH;
-  int ci = r % g.Ci; int co = r / g.Ci;
-  long long n = (long long)g.B * g.OH * g.OW;
-  float acc = 0.f;
-  for (long long j = threadIdx.x; j < n; j += blockDim.x) {
-    int ow = (int)(j % g.OW); long long q = j / g.OW;
-    int oh = (int)(q % g.OH); int b = (int)(q / g.OH);
-    int ih = oh * g.SH - g.PH + kh, iw = ow * g.SW - g.PW + kw;
-    if (ih < 0 || ih >= g.H || iw < 0 || iw >= g.W) continue;
-    acc = fmaf(dy[(((size_t)b * g.Co + co) * g.OH + oh) * g.OW + ow], x[(((size_t)b * g.Ci + ci) * g.H + ih) * g.W + iw], acc);
+  const int kh = i % g.KH; i /= g.KH;
+  const int ci = i % g.Ci; const int co = i / g.Ci;
+  float acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) acc[k] = 0.f;
+  for (int b = 0; b < g.B; b++) {
+    const float* dyb = dy + ((size_t)b * g.Co + co) * g.OH * g.OW;
+    const float* xb = x + ((size_t)b * g.Ci + ci) * g.H * g.W;
+    for (int oh = 0; oh < g.OH; oh++) {
+      const int ih = oh * g.SH - g.PH + kh;
+      if (ih < 0 || ih >= g.H) continue;
+      const float* xrow = xb + (size_t)ih * g.W;
+      for (int ow = threadIdx.x; ow < g.OW; ow += blockDim.x) {
+        const float gv = dyb[(size_t)oh * g.OW + ow];
+        const int iw0 = ow * g.SW - g.PW;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          const int iw = iw0 + k;
+          if (k < g.KW && iw >= 0 && iw < g.W) acc[k] = fmaf(gv, xrow[iw], acc[k]);
+        }
+      }
+    }
   }
-  acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    float v = warp_sum(acc[k]);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
+  }
   __syncthreads();
-  if (threadIdx.x == 0) dw[i] = red[0] + red[1] + red[2] + red[3];
+  if (threadIdx.x < g.KW)
+    dw[(((size_t)co * g.Ci + ci) * g.KH + kh) * g.KW + threadIdx.x] = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
 }
 
 // one CTA per output channel: dbias[co] = sum dy
@@ -227,7 +243,8 @@ int b200asr_conv2d_bwd_weight(const float* dy, const float* x, float* dw, float*
   B200_REQUIRE(dy && x && dw, B200ASR_BAD_ARG, "conv2d_bwd_weight: null pointer");
   ConvG g; int rc = make_geom(g, B, Ci, H, W, Co, KH, KW, SH, SW, PH, PW); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  conv2d_bwd_weight_kernel<<<Co * Ci * KH * KW, 128, 0, st>>>(dy, x, dw, g);
+  B200_REQUIRE(KW <= 16, B200ASR_BAD_SHAPE, "conv2d_bwd_weight: KW=%d > 16", KW);
+  conv2d_bwd_weight_kernel<<<Co * Ci * KH, 128, 0, st>>>(dy, x, dw, g);
   rc = check_launch("conv2d_bwd_weight"); if (rc) return rc;
   if (dbias) { conv2d_bias_grad_kernel<<<Co, 256, 0, st>>>(dy, dbias, B, Co, g.OH * g.OW); return check_launch("conv2d_bias_grad"); }
   return B200ASR_OK;

@@ -160,15 +160,20 @@ add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, con
   }
 }
 
-// dgamma/dbeta = column sums of the per-CTA partials: 32 columns per CTA, 8 row lanes, smem tree
+// dgamma/dbeta = column sums of the per-CTA partials: grid (d/32, row slices); 32 columns x 8 row lanes per CTA, smem tree,
+// one atomicAdd per column and slice into the zeroed outputs (a single-slice version was latency-bound: 16 CTAs walking
+// 1600 partial rows took longer than the main kernel)
+constexpr int LN_FIN_SLICES = 16;
 __global__ void __launch_bounds__(256) ln_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int d,
                                                               float* __restrict__ dgamma, float* __restrict__ dbeta) {
   __shared__ float ra[8][33], rb[8][33];
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
+  const int per = (nblk + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * per, r1 = min(nblk, r0 + per);
   float a = 0.f, b = 0.f;
   if (c < d)
-    for (int i = rl; i < nblk; i += 8) {
+    for (int i = r0 + rl; i < r1; i += 8) {
       a += partial[(size_t)i * 2 * d + c];
       b += partial[(size_t)i * 2 * d + d + c];
     }
@@ -178,8 +183,8 @@ __global__ void __launch_bounds__(256) ln_bwd_finalize_kernel(const float* __res
     float sa = 0.f, sb = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; i++) { sa += ra[i][cl]; sb += rb[i][cl]; }
-    dgamma[c] = sa;
-    dbeta[c] = sb;
+    atomicAdd(dgamma + c, sa);
+    atomicAdd(dbeta + c, sb);
   }
 }
 
@@ -234,7 +239,9 @@ int b200asr_add_ln_bwd(const float* dy, const float* z, const float* gamma, cons
 #undef LN_BWD
   int rc = check_launch("add_ln_bwd");
   if (rc) return rc;
-  ln_bwd_finalize_kernel<<<ceil_div(d, 32), 256, 0, st>>>((const float*)partial_ws, nblk, d, dgamma, dbeta);
+  cudaMemsetAsync(dgamma, 0, sizeof(float) * d, st);
+  cudaMemsetAsync(dbeta, 0, sizeof(float) * d, st);
+  ln_bwd_finalize_kernel<<<dim3(ceil_div(d, 32), LN_FIN_SLICES), 256, 0, st>>>((const float*)partial_ws, nblk, d, dgamma, dbeta);
   return check_launch("ln_bwd_finalize");
 }
 

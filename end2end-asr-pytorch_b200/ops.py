@@ -169,7 +169,9 @@ def linear_bwd_data(dy2, w, relu_out, prec, w_split=None):
 def _grad_sink(param):
     """The parameter's existing .grad if a kernel can accumulate straight into it (the flat gradient buffer of
     optim.FlatParams), else None.  Writing there removes autograd's AccumulateGrad add kernel and a temporary per weight."""
-    g = getattr(param, "grad", None) if param is not None else None
+    if param is None or not param.is_leaf:
+        return None
+    g = param.grad
     if g is None or not g.is_cuda or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != param.shape:
         return None
     return g
