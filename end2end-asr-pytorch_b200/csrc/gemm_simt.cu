@@ -174,7 +174,8 @@ __global__ void colsum_kernel(const float* __restrict__ X, float* __restrict__ o
 
 int launch_colsum(const float* X, float* out, int M, int N, int accumulate, cudaStream_t st) {
   if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * (size_t)N, st);
-  int rows_per_cta = 512;
+  // enough CTAs to hide the load latency of a skinny reduction (51 of these run per step); atomics per column = M / rows
+  int rows_per_cta = M >= (1 << 20) ? 2048 : 128;
   dim3 grid(ceil_div(N, 32), ceil_div(M, rows_per_cta));
   colsum_kernel<<<grid, 256, 0, st>>>(X, out, M, N, rows_per_cta);
   return check_launch("colsum");

@@ -182,6 +182,56 @@ def greedy_decode_ids(self, encoder_padded_outputs, steps=300):
     return ys[:, 1:]
 
 
+def greedy_decode_cached(self, encoder_padded_outputs, steps=300):
+    """Incremental greedy decode with self- and cross-attention K/V caches: the same token ids as
+    greedy_decode_ids / the reference's greedy_search, at O(T) instead of O(T^2) work -- per step only the new position is
+    projected, its K/V rows are appended to per-layer caches, and single-query attention runs over the cache (self) and
+    over the once-projected encoder K/V (cross, no mask as in transformer.py:347)."""
+    B, Te, _ = encoder_padded_outputs.shape
+    dev = encoder_padded_outputs.device
+    was_training = self.training
+    self.eval()
+    try:
+        with torch.no_grad():
+            H = self.layers[0].self_attn.num_heads
+            dk, dv = self.layers[0].self_attn.dim_key, self.layers[0].self_attn.dim_value
+            cross, kc, vc = [], [], []
+            for layer in self.layers:
+                ca = layer.encoder_attn
+                k = ops.LinearFn.apply(encoder_padded_outputs, ca.key_linear.weight, ca.key_linear.bias).view(B, Te, H, dk).permute(0, 2, 1, 3)
+                v = ops.LinearFn.apply(encoder_padded_outputs, ca.value_linear.weight, ca.value_linear.bias).view(B, Te, H, dv).permute(0, 2, 1, 3)
+                cross.append((k, v))
+                kc.append(torch.empty((B, steps, H * dk), device=dev, dtype=torch.float32))
+                vc.append(torch.empty((B, steps, H * dv), device=dev, dtype=torch.float32))
+            ys = torch.empty((B, steps), dtype=torch.long, device=dev)
+            tok = torch.full((B, 1), SOS_TOKEN, dtype=torch.long, device=dev)
+
+            def attend(mod, x, k4, v4):
+                q = ops.LinearFn.apply(x, mod.query_linear.weight, mod.query_linear.bias).view(B, 1, H, dk).permute(0, 2, 1, 3)
+                o = ops.SdpaFn.apply(q, k4, v4, None, None, False, 1.0 / float(mod.attention.temperature), 0.0)
+                o = ops.LinearFn.apply(o.permute(0, 2, 1, 3).reshape(B, 1, H * dv), mod.output_linear.weight, mod.output_linear.bias)
+                return ops.AddLNFn.apply(o, x, mod.layer_norm.weight, mod.layer_norm.bias, None, None, mod.layer_norm.eps, 0.0)
+
+            for t in range(steps):
+                pe = self.positional_encoding.pe[0, t:t + 1]
+                x = ops.EmbedFn.apply(tok, self.trg_embedding.weight, pe, float(self.x_logit_scale), 0.0, PAD_TOKEN)
+                for li, layer in enumerate(self.layers):
+                    sa = layer.self_attn
+                    kc[li][:, t:t + 1] = ops.LinearFn.apply(x, sa.key_linear.weight, sa.key_linear.bias)
+                    vc[li][:, t:t + 1] = ops.LinearFn.apply(x, sa.value_linear.weight, sa.value_linear.bias)
+                    k4 = kc[li][:, :t + 1].view(B, t + 1, H, dk).permute(0, 2, 1, 3)
+                    v4 = vc[li][:, :t + 1].view(B, t + 1, H, dv).permute(0, 2, 1, 3)
+                    x = attend(sa, x, k4, v4)
+                    x = attend(layer.encoder_attn, x, cross[li][0], cross[li][1])
+                    x = _ffn_core(layer.pos_ffn, x)
+                logits = ops.LinearFn.apply(x.view(B, -1), self.output_linear.weight, None)
+                tok = ops.argmax_rows(logits).view(B, 1)
+                ys[:, t:t + 1] = tok
+    finally:
+        self.train(was_training)
+    return ys
+
+
 def _front_end(self, padded_input):
     """CNN front end + flatten of Transformer.forward (models/asr/transformer.py:70-76).
     Returns (feats [B,T',D], cf_order or None)."""
@@ -326,6 +376,7 @@ class Decoder(nn.Module):
 
     forward = decoder_forward
     greedy_decode_ids = greedy_decode_ids
+    greedy_decode_cached = greedy_decode_cached
 
 
 class Transformer(nn.Module):

@@ -391,6 +391,8 @@ def test_greedy_decode_token_ids_match_oracle(b200):
     ids_o, margins = O.greedy_decode(P, cfg, enc, steps=16)
     model = cuda_model(cfg, P, train=False)
     ids = model.decoder.greedy_decode_ids(enc.cuda(), steps=16).cpu()
+    ids_cached = model.decoder.greedy_decode_cached(enc.cuda(), steps=16).cpu()
+    assert torch.equal(ids_cached, ids)          # KV-cached incremental decode == full-prefix re-decode, bit for bit
     band = 1e-3 * float(enc.abs().max())
     for b in range(ids.shape[0]):
         safe = int((margins[b] > band).long().cumprod(0).sum())      # steps before the first near-tie
