@@ -11,7 +11,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200asr.so")
+LIB_PATH = os.environ.get("B200ASR_LIB", os.path.join(_HERE, "libb200asr.so"))   # override: A/B builds of the same ABI
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "b200asr.h")
 
 _lib = None

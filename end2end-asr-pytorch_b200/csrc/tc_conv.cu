@@ -683,31 +683,37 @@ struct ConvPolicy {
   struct Params { ConvEpi e; int nft, ntt, cch; };
   static __device__ __forceinline__ int num_tiles(const Params& p) { return p.nft * p.ntt * p.e.B; }
   static __device__ __forceinline__ int num_kb(const Params& p, int) { return 9 * p.cch; }
-  static __device__ __forceinline__ void decode(const Params& p, int tile, int& f0, int& t0, int& b) {
-    f0 = (tile % p.nft) * CT_F;
+  struct Tile { int f0, t0, b, tap, df, dt, cb; };      // tile origin + k cursor (tap, 32-channel block)
+  static __device__ __forceinline__ Tile tile(const Params& p, int tile) {
+    Tile t;
+    t.f0 = (tile % p.nft) * CT_F;
     const int r = tile / p.nft;
-    t0 = (r % p.ntt) * CT_T;
-    b = r / p.ntt;
+    t.t0 = (r % p.ntt) * CT_T;
+    t.b = r / p.ntt;
+    t.tap = 0; t.df = -1; t.dt = -1; t.cb = 0;
+    return t;
   }
-  static __device__ __forceinline__ void load(const Params& p, const CUtensorMap* mapA, const CUtensorMap* mapB, int tile, int kb,
-                                              uint32_t sa, uint32_t, uint32_t sb, uint32_t sb_lo, uint32_t bar) {
-    int f0, t0, b;
-    decode(p, tile, f0, t0, b);
-    const int tap = kb / p.cch, c0 = (kb - tap * p.cch) * 32;
-    const int df = tap / 3 - 1, dt = tap % 3 - 1;
-    tma_load_4d(sa, mapA, bar, c0, f0 + df, t0 + dt, b);
-    tma_load_2d(sb, mapB, bar, c0, tap * BN);
-    if (NSPLIT == 3) tma_load_2d(sb_lo, mapB, bar, c0, (9 + tap) * BN);
+  // k order: tap-major (tap = 3 * (df + 1) + (dt + 1)), 32-channel blocks inside a tap
+  static __device__ __forceinline__ void load(const Params& p, Tile& t, const CUtensorMap* mapA, const CUtensorMap* mapB,
+                                              uint32_t sa, uint32_t sb, uint32_t sb_lo, uint32_t bar, bool leader) {
+    const int c0 = t.cb * 32;
+    if (leader) {
+      tma_load_4d(sa, mapA, bar, c0, t.f0 + t.df, t.t0 + t.dt, t.b);
+      tma_load_2d(sb, mapB, bar, c0, t.tap * BN);
+      if (NSPLIT == 3) tma_load_2d(sb_lo, mapB, bar, c0, (9 + t.tap) * BN);
+    }
+    if (++t.cb == p.cch) {
+      t.cb = 0; t.tap++;
+      if (++t.dt == 2) { t.dt = -1; t.df++; }
+    }
   }
   static __device__ __forceinline__ uint64_t a_desc(uint32_t s, int ks) { return make_smem_desc(s + ks * 32, 16, 1024); }
   static __device__ __forceinline__ uint64_t b_desc(uint32_t s, int ks) { return make_smem_desc(s + ks * 32, 16, 1024); }
-  static __device__ __forceinline__ void store(const Params& p, int tile, int r, int c0, const float (&v)[32]) {
+  static __device__ __forceinline__ void store(const Params& p, const Tile& t, int r, int c0, const float (&v)[32]) {
     const ConvEpi& e = p.e;
-    int f0, t0, b;
-    decode(p, tile, f0, t0, b);
-    const int tt = t0 + r / CT_F, ff = f0 + r % CT_F;
+    const int tt = t.t0 + r / CT_F, ff = t.f0 + r % CT_F;
     if (tt >= e.T || ff >= e.F) return;
-    const size_t pix = ((size_t)b * e.T + tt) * e.F + ff;
+    const size_t pix = ((size_t)t.b * e.T + tt) * e.F + ff;
     float* orow = e.out + pix * e.Cout;
     const float* mrow = e.mask ? e.mask + pix * e.Cout : nullptr;
 #pragma unroll
@@ -743,30 +749,39 @@ struct WgradPolicy {
     tap_a = (tile % kGroups) * (128 / CI);
     tap_b = (CI == 64 && tap_a + 1 < 9) ? tap_a + 1 : tap_a;
   }
-  static __device__ __forceinline__ void load(const Params& p, const CUtensorMap* mapX, const CUtensorMap* mapDy, int tile, int kb,
-                                              uint32_t sa, uint32_t, uint32_t sb, uint32_t, uint32_t bar) {
-    int tap_a, tap_b;
-    taps(tile, tap_a, tap_b);
-    const int blk = (tile / kGroups) * p.e.blocks_per_cta + kb;
-    const int ft = blk % p.e.nft, tt = (blk / p.e.nft) % p.e.ntt, b = blk / (p.e.nft * p.e.ntt);
-    const int f0 = ft * WG_PF, t0 = tt * WG_PT;
+  struct Tile { int tap_a, tap_b, ft, tt, b, nkb; };     // tap pair + pixel-block cursor (ft fastest, then tt, then b)
+  static __device__ __forceinline__ Tile tile(const Params& p, int tile) {
+    Tile t;
+    taps(tile, t.tap_a, t.tap_b);
+    const int blk = (tile / kGroups) * p.e.blocks_per_cta;
+    t.ft = blk % p.e.nft; t.tt = (blk / p.e.nft) % p.e.ntt; t.b = blk / (p.e.nft * p.e.ntt);
+    t.nkb = num_kb(p, tile);
+    return t;
+  }
+  static __device__ __forceinline__ void load(const Params& p, Tile& t, const CUtensorMap* mapX, const CUtensorMap* mapDy,
+                                              uint32_t sa, uint32_t sb, uint32_t, uint32_t bar, bool leader) {
+    const int f0 = t.ft * WG_PF, t0 = t.tt * WG_PT;
+    if (leader) {
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
-      const int tap = (c * 32) / CI == 0 ? tap_a : tap_b;
-      tma_load_4d(sa + c * 4096, mapX, bar, (c * 32) % CI, f0 + tap / 3 - 1, t0 + tap % 3 - 1, b);
+      for (int c = 0; c < 4; c++) {
+        const int tap = (c * 32) / CI == 0 ? t.tap_a : t.tap_b;
+        tma_load_4d(sa + c * 4096, mapX, bar, (c * 32) % CI, f0 + tap / 3 - 1, t0 + tap % 3 - 1, t.b);
+      }
+#pragma unroll
+      for (int c = 0; c < BN / 32; c++) tma_load_4d(sb + c * 4096, mapDy, bar, c * 32, f0, t0, t.b);
     }
-#pragma unroll
-    for (int c = 0; c < BN / 32; c++) tma_load_4d(sb + c * 4096, mapDy, bar, c * 32, f0, t0, b);
+    if (++t.ft == p.e.nft) {
+      t.ft = 0;
+      if (++t.tt == p.e.ntt) { t.tt = 0; t.b++; }
+    }
   }
   static __device__ __forceinline__ uint64_t a_desc(uint32_t s, int ks) { return make_smem_desc(s + ks * 1024, 4096, 512, kLayoutSW128Base32B); }
   static __device__ __forceinline__ uint64_t b_desc(uint32_t s, int ks) { return make_smem_desc(s + ks * 1024, 4096, 512, kLayoutSW128Base32B); }
-  static __device__ __forceinline__ void store(const Params& p, int tile, int r, int c0, const float (&v)[32]) {
-    int tap_a, tap_b;
-    taps(tile, tap_a, tap_b);
+  static __device__ __forceinline__ void store(const Params& p, const Tile& t, int r, int c0, const float (&v)[32]) {
     const int slot = r / CI, ci = r % CI;
-    if (slot == 1 && tap_b == tap_a) return;
-    if (num_kb(p, tile) == 0) return;
-    float* orow = p.e.dwr + ((size_t)(slot == 0 ? tap_a : tap_b) * p.e.Ci + ci) * p.e.Co + c0;
+    if (slot == 1 && t.tap_b == t.tap_a) return;
+    if (t.nkb == 0) return;
+    float* orow = p.e.dwr + ((size_t)(slot == 0 ? t.tap_a : t.tap_b) * p.e.Ci + ci) * p.e.Co + c0;
 #pragma unroll
     for (int j = 0; j < 32; j++) atomicAdd(orow + j, v[j]);
   }

@@ -4,16 +4,22 @@
 //   warp 0      TMA producer            -- runs ahead across tiles through a ring of smem stages
 //   warp 1      MMA issuer + TMEM owner -- accumulates tile i into TMEM buffer (i & 1)
 //   warps 2-5   epilogue                -- drain buffer (i & 1) with tcgen05.ld while tile i+1 is being multiplied
-//   warps 6-13  3xTF32 operand split    -- A: smem -> (hi, lo) in TMEM; B: hi in place / lo in smem (only when NSPLIT == 3)
+//   warps 6-13  3xTF32 operand split    -- A: smem -> (hi, lo) in TMEM; B: hi in place / lo in smem (only when NSPLIT == 3);
+//               two groups of 4 warps take alternating k-blocks
 // so per-tile prologue/epilogue latency is hidden behind the next tile's mainloop instead of being paid 200+ times per SM.
 //
 // A Policy supplies the problem-specific parts:
 //   static constexpr int  BN, kABytes, kBBytes;  static constexpr bool kSplitA, kSplitB (operand needs the in-kernel split);
 //   static constexpr bool kAMN, kBMN (operand majors);  struct Params;
 //   static __device__ int  num_tiles(const Params&);          static __device__ int num_kb(const Params&, int tile);
-//   static __device__ void load(p, mapA, mapB, tile, kb, sa, sa_lo, sb, sb_lo, bar);   // TMA for one stage (fixed tx bytes)
+//   struct Tile;  static __device__ Tile tile(p, tile);       // tile coordinates, decoded ONCE per tile (integer divisions)
+//   static __device__ void load(p, Tile&, mapA, mapB, sa, sb, sb_lo, bar, leader);   // TMA for the next k-block of the tile
+//                              // (fixed tx bytes, issued by the leader lane only); every lane advances the k cursor in Tile
 //   static __device__ uint64_t a_desc(uint32_t saddr, int ks); static __device__ uint64_t b_desc(uint32_t saddr, int ks);
-//   static __device__ void store(p, tile, row, col0, const float (&v)[32]);            // 32 accumulator columns of one row
+//   static __device__ void store(p, const Tile&, row, col0, const float (&v)[32]);     // 32 accumulator columns of one row
+// The producer is ONE thread: anything it does per k-block is on the critical path of the whole SM (the first version
+// re-derived (b, t, f, tap) with integer divisions for every k-block -- ~1000 clk each -- and that, not the tensor pipe,
+// set the pace; see profiles/engine_ConvPolicy_r1.md).
 #pragma once
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -24,6 +30,9 @@ namespace tc {
 constexpr int ENG_THREADS_X1 = 192;     // TMA, MMA, 4 epilogue warps
 constexpr int ENG_THREADS_X3 = 448;     // + 8 split warps
 constexpr int ENG_SPLIT_THREADS = 256;
+#ifndef ENG_SPLIT_GROUPS
+#define ENG_SPLIT_GROUPS 2              // the 8 split warps work as this many groups on alternating k-blocks
+#endif
 
 // 3xTF32 keeps the A operand in TENSOR MEMORY: the split warps read the raw fp32 tile from smem once and write
 // hi / lo straight into TMEM (tcgen05.st), and the MMAs run in the TS form (A from TMEM, B from smem).  Shared memory then
@@ -68,7 +77,7 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   const int ntiles = Policy::num_tiles(p);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; s++) { mbar_init(full_bar(s), 1); mbar_init(xfm_bar(s), ENG_SPLIT_THREADS); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < S; s++) { mbar_init(full_bar(s), 1); mbar_init(xfm_bar(s), ENG_SPLIT_THREADS / ENG_SPLIT_GROUPS); mbar_init(empty_bar(s), 1); }
     for (int b = 0; b < 2; b++) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 128); }
     fence_barrier_init();
     tma_prefetch_desc(&mapA);
@@ -81,37 +90,39 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- TMA producer
-      uint32_t kbg = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int nkb = Policy::num_kb(p, tile);
-        for (int kb = 0; kb < nkb; kb++, kbg++) {
-          const int s = kbg % S;
-          mbar_wait(empty_bar(s), ((kbg / S) & 1) ^ 1);
-          const uint32_t sa = smem_base + s * Cfg::kStageBytes;
-          mbar_expect_tx(full_bar(s), Cfg::kTxBytes);
-          Policy::load(p, &mapA, &mapB, tile, kb, sa, 0u, sa + Cfg::kOffBhi, sa + Cfg::kOffBlo, full_bar(s));
-        }
+    // ------------------------------------------------------------------ TMA producer (whole warp loops, one lane issues)
+    const bool leader = elect_one();
+    uint32_t kbg = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int nkb = Policy::num_kb(p, tile);
+      typename Policy::Tile tc = Policy::tile(p, tile);
+      for (int kb = 0; kb < nkb; kb++, kbg++) {
+        const int s = kbg % S;
+        mbar_wait(empty_bar(s), ((kbg / S) & 1) ^ 1);
+        const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+        if (leader) mbar_expect_tx(full_bar(s), Cfg::kTxBytes);
+        Policy::load(p, tc, &mapA, &mapB, sa, sa + Cfg::kOffBhi, sa + Cfg::kOffBlo, full_bar(s), leader);
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- MMA issuer
-      constexpr uint32_t idesc = make_idesc_tf32(128, BN, Policy::kAMN, Policy::kBMN);
-      constexpr bool kNeedXfm = NSPLIT == 3;
-      uint32_t kbg = 0, tcount = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
-        const int nkb = Policy::num_kb(p, tile);
-        const uint32_t buf = tcount & 1;
-        mbar_wait(tempty_bar(buf), ((tcount >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+    // ------------------------------------------------------------------ MMA issuer (whole warp loops, one lane issues)
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = make_idesc_tf32(128, BN, Policy::kAMN, Policy::kBMN);
+    constexpr bool kNeedXfm = NSPLIT == 3;
+    uint32_t kbg = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
+      const int nkb = Policy::num_kb(p, tile);
+      const uint32_t buf = tcount & 1;
+      mbar_wait(tempty_bar(buf), ((tcount >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * BN;
+      for (int kb = 0; kb < nkb; kb++, kbg++) {
+        const int s = kbg % S;
+        mbar_wait(kNeedXfm ? xfm_bar(s) : full_bar(s), (kbg / S) & 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * BN;
-        for (int kb = 0; kb < nkb; kb++, kbg++) {
-          const int s = kbg % S;
-          mbar_wait(kNeedXfm ? xfm_bar(s) : full_bar(s), (kbg / S) & 1);
-          tc_fence_after();
-          const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+        const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+        if (leader) {
 #pragma unroll
           for (int ks = 0; ks < 4; ks++) {
             const uint64_t b_hi = Policy::b_desc(sa + Cfg::kOffBhi, ks);
@@ -129,8 +140,10 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           }
           umma_commit(empty_bar(s));
         }
-        umma_commit(tfull_bar(buf));
+        __syncwarp();
       }
+      if (leader) umma_commit(tfull_bar(buf));
+      __syncwarp();
     }
   } else if (warp < 6) {
     // ------------------------------------------------------------------ epilogue (warps 2-5: TMEM lane quarters 2,3,0,1)
@@ -140,6 +153,7 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
       const uint32_t buf = tcount & 1;
       const int nkb = Policy::num_kb(p, tile);
+      const typename Policy::Tile tc = Policy::tile(p, tile);
       mbar_wait(tfull_bar(buf), (tcount >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -153,29 +167,35 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           tc_fence_before();
           mbar_arrive(tempty_bar(buf));
         }
-        Policy::store(p, tile, row, c * 32, v);
+        Policy::store(p, tc, row, c * 32, v);
       }
     }
   } else {
     // ------------------------------------------------------------------ operand split warps (3xTF32 only)
     if (NSPLIT == 3) {
-      const int t = threadIdx.x - 192;
+      // The smem -> registers -> TMEM chain of one k-block is a serial latency (LDS, tcgen05.st, wait::st, arrive), so the
+      // warps are divided into groups that take alternating k-blocks: each thread handles a wider slice less often and the
+      // chains of consecutive k-blocks overlap.
+      constexpr int G = ENG_SPLIT_GROUPS, WPG = 8 / G, KPT = 128 / WPG;   // warps per group, k columns per thread
+      const int group = (warp - 6) / WPG;
+      const int kpart = ((warp - 6) % WPG) >> 2;    // which KPT-wide slice of the 32-deep block
+      const int t = threadIdx.x - 192 - group * WPG * 32;
       const int quarter = warp & 3;                 // TMEM lanes this warp may touch
-      const int khalf = (warp - 6) >> 2;            // k columns [16*khalf, +16) of the 32-deep block
       const int row = quarter * 32 + lane;          // A-tile row owned by this thread
       uint32_t kbg = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int nkb = Policy::num_kb(p, tile);
         for (int kb = 0; kb < nkb; kb++, kbg++) {
+          if ((int)(kbg % G) != group) continue;
           const int s = kbg % S;
           mbar_wait(full_bar(s), (kbg / S) & 1);
           const uint8_t* araw = gen_base + s * Cfg::kStageBytes;
-          float hi[16], lo[16];
+          float hi[KPT], lo[KPT];
           if (!Policy::kAMN) {
             // K-major tile: row = 128 B, 16-byte chunk j stored at chunk (j ^ (row & 7)) (128B swizzle)
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-              const int chunk = (khalf * 4 + j) ^ (row & 7);
+            for (int j = 0; j < KPT / 4; j++) {
+              const int chunk = (kpart * (KPT / 4) + j) ^ (row & 7);
               const float4 x = *reinterpret_cast<const float4*>(araw + row * 128 + chunk * 16);
               hi[j * 4 + 0] = tf32_rn(x.x); lo[j * 4 + 0] = x.x - hi[j * 4 + 0];
               hi[j * 4 + 1] = tf32_rn(x.y); lo[j * 4 + 1] = x.y - hi[j * 4 + 1];
@@ -187,18 +207,21 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const uint8_t* cbase = araw + (row >> 5) * 4096 + (row & 7) * 4;
             const int atom = (row & 31) >> 3;
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-              const int k = khalf * 16 + j;
+            for (int j = 0; j < KPT; j++) {
+              const int k = kpart * KPT + j;
               const float x = *reinterpret_cast<const float*>(cbase + k * 128 + ((atom ^ (k & 3)) << 5));
               hi[j] = tf32_rn(x); lo[j] = x - hi[j];
             }
           }
-          const uint32_t acol = tmem_base + ((uint32_t)(quarter * 32) << 16) + Cfg::kAccCols + s * 64 + khalf * 16;
-          tmem_st16(acol, hi);
-          tmem_st16(acol + 32, lo);
+          const uint32_t acol = tmem_base + ((uint32_t)(quarter * 32) << 16) + Cfg::kAccCols + s * 64 + kpart * KPT;
+#pragma unroll
+          for (int i = 0; i < KPT / 16; i++) {
+            tmem_st16(acol + i * 16, hi + i * 16);
+            tmem_st16(acol + 32 + i * 16, lo + i * 16);
+          }
           if (Policy::kSplitB) {
             float4* stage = reinterpret_cast<float4*>(gen_base + s * Cfg::kStageBytes);
-            split_tf32_inplace(stage + Cfg::kOffBhi / 16, stage + Cfg::kOffBlo / 16, Policy::kBBytes / 16, t, ENG_SPLIT_THREADS);
+            split_tf32_inplace(stage + Cfg::kOffBhi / 16, stage + Cfg::kOffBlo / 16, Policy::kBBytes / 16, t, ENG_SPLIT_THREADS / G);
             fence_proxy_async_smem();
           }
           tmem_wait_st();

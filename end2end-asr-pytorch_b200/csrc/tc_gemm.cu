@@ -265,20 +265,24 @@ struct GemmPolicy {
   static constexpr bool kSplitA = true, kSplitB = !PRESPLIT, kAMN = A_MN, kBMN = B_MN;
   struct Params { EpiP e; int tiles_m, tiles_n, b_rows; };
   static __device__ __forceinline__ int num_tiles(const Params& p) { return p.tiles_m * p.tiles_n * p.e.splits; }
-  static __device__ __forceinline__ void decode(const Params& p, int tile, int& m0, int& n0, int& z) {
+  struct Tile { int m0, n0, z, k0; };                    // tile origin, split-K slice, k cursor
+  static __device__ __forceinline__ Tile tile(const Params& p, int tile) {
+    Tile t;
     const int n = tile % p.tiles_n, r = tile / p.tiles_n;
-    m0 = (r % p.tiles_m) * GBM; n0 = n * GBN; z = r / p.tiles_m;
+    t.m0 = (r % p.tiles_m) * GBM; t.n0 = n * GBN; t.z = r / p.tiles_m;
+    t.k0 = t.z * p.e.klen;
+    return t;
   }
   static __device__ __forceinline__ int num_kb(const Params& p, int tile) {
     const int z = tile / (p.tiles_n * p.tiles_m);
     const int kbeg = z * p.e.klen, kend = min(p.e.K, kbeg + p.e.klen);
     return (kend - kbeg + GBK - 1) / GBK;
   }
-  static __device__ __forceinline__ void load(const Params& p, const CUtensorMap* mapA, const CUtensorMap* mapB, int tile, int kb,
-                                              uint32_t sa, uint32_t, uint32_t sb, uint32_t sb_lo, uint32_t bar) {
-    int m0, n0, z;
-    decode(p, tile, m0, n0, z);
-    const int k0 = z * p.e.klen + kb * GBK;
+  static __device__ __forceinline__ void load(const Params& p, Tile& t, const CUtensorMap* mapA, const CUtensorMap* mapB,
+                                              uint32_t sa, uint32_t sb, uint32_t sb_lo, uint32_t bar, bool leader) {
+    const int k0 = t.k0, m0 = t.m0, n0 = t.n0;
+    t.k0 += GBK;
+    if (!leader) return;
     if (!A_MN) tma_load_2d(sa, mapA, bar, k0, m0);
     else
 #pragma unroll
@@ -300,10 +304,9 @@ struct GemmPolicy {
   static __device__ __forceinline__ uint64_t b_desc(uint32_t s, int ks) {
     return B_MN ? make_smem_desc(s + ks * 1024, 4096, 512, kLayoutSW128Base32B) : make_smem_desc(s + ks * 32, 16, 1024);
   }
-  static __device__ __forceinline__ void store(const Params& p, int tile, int r, int c0, const float (&v)[32]) {
+  static __device__ __forceinline__ void store(const Params& p, const Tile& t, int r, int c0, const float (&v)[32]) {
     const EpiP& e = p.e;
-    int m0, n0, z;
-    decode(p, tile, m0, n0, z);
+    const int m0 = t.m0, n0 = t.n0, z = t.z;
     const int row = m0 + r;
     if (row >= e.M) return;
     const int col0 = n0 + c0;
