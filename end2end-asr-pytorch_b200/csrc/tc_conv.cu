@@ -716,20 +716,25 @@ struct ConvPolicy {
     const size_t pix = ((size_t)t.b * e.T + tt) * e.F + ff;
     float* orow = e.out + pix * e.Cout;
     const float* mrow = e.mask ? e.mask + pix * e.Cout : nullptr;
+    // all loads of a 16-channel half before its first store (see GemmPolicy::store)
 #pragma unroll
-    for (int j4 = 0; j4 < 8; j4++) {
-      const int col = c0 + j4 * 4;
-      float o[4] = {v[j4 * 4 + 0], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]};
-      if (e.bias) {
-        const float4 bb = *reinterpret_cast<const float4*>(e.bias + col);
-        o[0] += bb.x; o[1] += bb.y; o[2] += bb.z; o[3] += bb.w;
+    for (int half = 0; half < 2; half++) {
+      float4 bb[4], mm[4];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int col = c0 + half * 16 + q * 4;
+        bb[q] = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        mm[q] = mrow ? __ldg(reinterpret_cast<const float4*>(mrow + col)) : make_float4(1.f, 1.f, 1.f, 1.f);
       }
-      if (e.relu) { o[0] = fmaxf(o[0], 0.f); o[1] = fmaxf(o[1], 0.f); o[2] = fmaxf(o[2], 0.f); o[3] = fmaxf(o[3], 0.f); }
-      if (mrow) {
-        const float4 m = *reinterpret_cast<const float4*>(mrow + col);
-        o[0] = m.x > 0.f ? o[0] : 0.f; o[1] = m.y > 0.f ? o[1] : 0.f; o[2] = m.z > 0.f ? o[2] : 0.f; o[3] = m.w > 0.f ? o[3] : 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int col = c0 + half * 16 + q * 4, j = half * 16 + q * 4;
+        float o[4] = {v[j] + bb[q].x, v[j + 1] + bb[q].y, v[j + 2] + bb[q].z, v[j + 3] + bb[q].w};
+        if (e.relu) { o[0] = fmaxf(o[0], 0.f); o[1] = fmaxf(o[1], 0.f); o[2] = fmaxf(o[2], 0.f); o[3] = fmaxf(o[3], 0.f); }
+        o[0] = mm[q].x > 0.f ? o[0] : 0.f; o[1] = mm[q].y > 0.f ? o[1] : 0.f;
+        o[2] = mm[q].z > 0.f ? o[2] : 0.f; o[3] = mm[q].w > 0.f ? o[3] : 0.f;
+        *reinterpret_cast<float4*>(orow + col) = make_float4(o[0], o[1], o[2], o[3]);
       }
-      *reinterpret_cast<float4*>(orow + col) = make_float4(o[0], o[1], o[2], o[3]);
     }
   }
 };

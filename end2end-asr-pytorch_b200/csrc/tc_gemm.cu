@@ -321,6 +321,36 @@ struct GemmPolicy {
       return;
     }
     const bool vec_ok = ((e.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0);
+    if (vec_ok && (e.N & 3) == 0 && (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(e.relu_mask) & 15) == 0) {
+      // Fast path: ALL the global loads of a 16-column half (bias, ReLU mask, old C) are issued before the first store, so
+      // the one epilogue warp of this SM sub-partition pays the load latency twice per chunk instead of once per float4
+      // (loads cannot be hoisted above stores through possibly-aliasing pointers; with K = 512 the interleaved version
+      // made the epilogue, ~20k clk per 128x128 tile, longer than the 12k clk mainloop).
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        float4 bb[4], mm[4], cc[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int col = col0 + half * 16 + q * 4;
+          const bool ok = col < e.N;
+          bb[q] = (e.bias && ok) ? __ldg(reinterpret_cast<const float4*>(e.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          mm[q] = (mrow && ok) ? __ldg(reinterpret_cast<const float4*>(mrow + col)) : make_float4(1.f, 1.f, 1.f, 1.f);
+          cc[q] = (e.accumulate && ok) ? *reinterpret_cast<const float4*>(crow + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int col = col0 + half * 16 + q * 4;
+          if (col >= e.N) break;
+          const int j = half * 16 + q * 4;
+          float o[4] = {v[j] + bb[q].x, v[j + 1] + bb[q].y, v[j + 2] + bb[q].z, v[j + 3] + bb[q].w};
+          if (e.relu) { o[0] = fmaxf(o[0], 0.f); o[1] = fmaxf(o[1], 0.f); o[2] = fmaxf(o[2], 0.f); o[3] = fmaxf(o[3], 0.f); }
+          o[0] = mm[q].x > 0.f ? o[0] : 0.f; o[1] = mm[q].y > 0.f ? o[1] : 0.f;
+          o[2] = mm[q].z > 0.f ? o[2] : 0.f; o[3] = mm[q].w > 0.f ? o[3] : 0.f;
+          *reinterpret_cast<float4*>(crow + col) = make_float4(o[0] + cc[q].x, o[1] + cc[q].y, o[2] + cc[q].z, o[3] + cc[q].w);
+        }
+      }
+      return;
+    }
 #pragma unroll
     for (int j4 = 0; j4 < 8; j4++) {
       const int col = col0 + j4 * 4;
