@@ -100,6 +100,12 @@ def algorithmic_flops(name, a):
     if name == "sdpa_bwd":
         B, H, Tq, Tk, dk, dv = a[25:31]
         return 2.0 * 2.0 * B * H * Tq * Tk * (dk + dv)      # four GEMMs (recompute of QK^T not counted)
+    if name == "sdpa_mat_fwd":      # q,k,v + 9 strides + key_pad, dense, causal, out + 3 strides, probs, probs_drop, then dims
+        B, H, Tq, Tk, dk, dv = a[21:27]
+        return 2.0 * B * H * Tq * Tk * (dk + dv)
+    if name == "sdpa_mat_bwd":      # dout,q,k,v + 12 strides + 6 pointers, then dims
+        B, H, Tq, Tk, dk, dv = a[22:28]
+        return 2.0 * 2.0 * B * H * Tq * Tk * (dk + dv)
     return 0.0
 
 

@@ -43,6 +43,10 @@ int make_tensor_map_f32(CUtensorMap* map, const void* base, int rank, const uint
   cuuint32_t bdim[5], estr[5];
   for (int i = 0; i < rank; i++) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
   for (int i = 1; i < rank; i++) gstride[i - 1] = strides_elems[i - 1] * sizeof(float);
+  // the driver entry point needs the primary context current on THIS thread (autograd runs backward on its own threads,
+  // and a thread that has only launched through the runtime so far may not have it bound yet): cudaFree(0) binds it
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
   CUresult r = enc(map, tf32_dtype ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstride, bdim, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, atom32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

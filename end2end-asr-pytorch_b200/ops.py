@@ -19,18 +19,19 @@ _PREC_NAMES = {"fp32": L.PREC_FP32, "tf32": L.PREC_TF32, "tf32x3": L.PREC_TF32X3
 class _Config:
     """Arithmetic mode per kernel family (include/b200asr.h `precision`).
 
-    Default = the fp32-grade mix: GEMMs and convolutions on tcgen05 with the 3xTF32 split (measured at the cfg2
-    architecture against an fp64 oracle: logits 1.3e-5, loss 4e-8, median gradient error 7e-5 -- tools/parity_cfg2.py),
-    attention on the exact-fp32 CUDA-core kernels.  Single-pass TF32 ("tf32") is available per family; with TF32
-    convolutions the logits stay within 1e-3 (2.6e-4) but gradients drift to ~6e-3, so it is not the default.  The
-    tcgen05 attention forward ("tf32") must be paired with a tensor-core backward to stay self-consistent
-    (its O/LSE feed the backward's delta = rowsum(dO*O)); until that exists the default keeps attention in fp32."""
+    Default = the fp32-grade mix, everything on tcgen05 with the 3xTF32 split: GEMMs, convolutions and the attention
+    contractions (materialised path: batched GEMMs around exact fp32 softmax kernels, attention_mat.cu).  Measured at
+    the cfg2 architecture against an fp64 oracle (tools/parity_cfg2.py): logits ~1e-5, median gradient error ~1e-4.
+    Alternatives per family: "fp32" = CUDA-core kernels (exact fp32; attention = the flash-style kernel, which is also
+    what shapes outside the tensor-core shape rules run on), "tf32" = single-pass TF32 (convolutions: logits 3e-4 but
+    gradients ~6e-3; attention = the single-kernel flash forward/backward with S/P resident in TMEM, gradients ~3e-3
+    because dP - delta cancels in TF32) -- neither meets the 1e-3 gradient bar, so they are opt-in only."""
 
     def __init__(self):
         self.linear = _PREC_NAMES[os.environ.get("B200ASR_LINEAR", "tf32x3")]
         self.conv = _PREC_NAMES[os.environ.get("B200ASR_CONV", "tf32x3")]
         self.conv_wgrad = _PREC_NAMES[os.environ.get("B200ASR_CONV_WGRAD", "tf32x3")]
-        self.attn = _PREC_NAMES[os.environ.get("B200ASR_ATTN", "fp32")]
+        self.attn = _PREC_NAMES[os.environ.get("B200ASR_ATTN", "tf32x3")]
         self.attn_bwd = _PREC_NAMES[os.environ.get("B200ASR_ATTN_BWD", "fp32")]
 
     def set(self, linear=None, conv=None, attn=None, conv_wgrad=None, attn_bwd=None):
@@ -330,23 +331,43 @@ class SdpaFn(torch.autograd.Function):
             out = torch.empty((H, B, Tq, dv), device=q.device, dtype=torch.float32).permute(1, 0, 2, 3)
         else:                   # token-major memory [B,Tq,H,dv]: the head merge of common_layers.py:194-195 is a view
             out = torch.empty((B, Tq, H, dv), device=q.device, dtype=torch.float32).permute(0, 2, 1, 3)
-        lse = torch.empty((B, H, Tq), device=q.device, dtype=torch.float32)
         seed, off = rng.next() if p_drop > 0.0 else (0, 0)
-        # shape rule (not a fallback): the tcgen05 kernel keeps the whole score row in TMEM (Tk <= 448, d in {32,64})
-        prec = config.attn if (Tk <= 448 and dk in (32, 64) and dv in (32, 64)) else L.PREC_FP32
         qs, ks, vs, os_ = _bhtd_strides(q), _bhtd_strides(k), _bhtd_strides(v), _bhtd_strides(out)
+        # shape rules (not fallbacks): the materialised 3xTF32 path needs head dims that are whole
+        # 32-float k-blocks and rows of at most 2048 keys; the TF32 flash kernel keeps the score row in TMEM
+        # (Tk <= 448, d in {32,64}); everything else runs on the fp32 CUDA-core kernel
+        prec = config.attn
+        if prec == L.PREC_TF32X3 and not (dk % 32 == 0 and dv % 32 == 0 and Tk <= 2048):
+            prec = L.PREC_FP32
+        if prec == L.PREC_TF32 and not (Tk <= 448 and dk in (32, 64) and dv in (32, 64)):
+            prec = L.PREC_FP32
+        if prec == L.PREC_TF32X3:
+            n = _lib().b200asr_sdpa_mat_ws_bytes(B, H, Tq, Tk) // 4
+            probs = torch.empty(n, device=q.device, dtype=torch.float32)
+            probs_drop = torch.empty(n, device=q.device, dtype=torch.float32) if p_drop > 0.0 else None
+            L.check(_lib().b200asr_sdpa_mat_fwd(L.ptr(q), L.ptr(k), L.ptr(v), *qs, *ks, *vs, L.ptr(key_pad), L.ptr(dense_mask),
+                                                int(causal), L.ptr(out), *os_, L.ptr(probs), L.ptr(probs_drop), B, H, Tq, Tk,
+                                                dk, dv, float(scale), float(p_drop), seed, off, prec, _stream()), "sdpa_mat_fwd")
+            ctx.save_for_backward(q, k, v, out, probs, probs_drop)
+            ctx.meta = (int(causal), float(scale), float(p_drop), seed, off, prec)
+            ctx.mat = True
+            return out
+        lse = torch.empty((B, H, Tq), device=q.device, dtype=torch.float32)
         L.check(_lib().b200asr_sdpa_fwd(L.ptr(q), L.ptr(k), L.ptr(v), *qs, *ks, *vs, L.ptr(key_pad), L.ptr(dense_mask),
                                         int(causal), L.ptr(out), *os_, L.ptr(lse), B, H, Tq, Tk, dk, dv, float(scale),
                                         float(p_drop), seed, off, prec, _stream()), "sdpa_fwd")
         ctx.save_for_backward(q, k, v, out, lse, key_pad, dense_mask)
         bwd_prec = config.attn_bwd if (dk in (32, 64) and dv in (32, 64)) else L.PREC_FP32
+        if bwd_prec == L.PREC_TF32X3:
+            bwd_prec = L.PREC_FP32       # the flash-style backward exists as fp32 (CUDA cores) and TF32 (tcgen05) only
         ctx.meta = (int(causal), float(scale), float(p_drop), seed, off, bwd_prec)
+        ctx.mat = False
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        q, k, v, out, lse, key_pad, dense_mask = ctx.saved_tensors
         causal, scale, p_drop, seed, off, prec = ctx.meta
+        q, k, v, out = ctx.saved_tensors[:4]
         B, H, Tq, dk = q.shape
         Tk, dv = k.shape[2], v.shape[3]
         if dout.stride() != out.stride():
@@ -356,8 +377,16 @@ class SdpaFn(torch.autograd.Function):
         dvv = torch.empty_strided(v.shape, v.stride(), device=q.device, dtype=torch.float32) if _dense_like(v) else None
         if dq is None or dkk is None or dvv is None:
             raise RuntimeError("sdpa backward: q/k/v views must be dense permutations of a contiguous tensor")
-        delta = torch.empty((B, H, Tq), device=q.device, dtype=torch.float32)
         qs, ks, vs, os_ = _bhtd_strides(q), _bhtd_strides(k), _bhtd_strides(v), _bhtd_strides(out)
+        if ctx.mat:
+            probs, probs_drop = ctx.saved_tensors[4:6]
+            dp = torch.empty_like(probs)
+            L.check(_lib().b200asr_sdpa_mat_bwd(L.ptr(dout), L.ptr(q), L.ptr(k), L.ptr(v), *qs, *ks, *vs, *os_, L.ptr(probs),
+                                                L.ptr(probs_drop), L.ptr(dq), L.ptr(dkk), L.ptr(dvv), L.ptr(dp), B, H, Tq, Tk,
+                                                dk, dv, scale, p_drop, seed, off, prec, _stream()), "sdpa_mat_bwd")
+            return dq, dkk, dvv, None, None, None, None, None, None
+        lse, key_pad, dense_mask = ctx.saved_tensors[4:7]
+        delta = torch.empty((B, H, Tq), device=q.device, dtype=torch.float32)
         L.check(_lib().b200asr_sdpa_bwd(L.ptr(dout), L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(out), L.ptr(lse), *qs, *ks, *vs, *os_,
                                         L.ptr(key_pad), L.ptr(dense_mask), causal, L.ptr(dq), L.ptr(dkk), L.ptr(dvv),
                                         L.ptr(delta), B, H, Tq, Tk, dk, dv, scale, p_drop, seed, off, prec, _stream()),

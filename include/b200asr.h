@@ -117,6 +117,28 @@ int b200asr_sdpa_bwd(const float* dout, const float* q, const float* k, const fl
                      float* delta_ws, int B, int H, int Tq, int Tk, int dk, int dv, float scale, float p_drop,
                      uint64_t seed, uint64_t offset, int precision, b200asr_stream_t stream);
 
+/* Materialised attention (precision 1 = TF32, 3 = 3xTF32): the same contract as b200asr_sdpa_fwd/_bwd
+ * (models/common_layers.py:211-225; head views addressed by strides; dropout drawn from the same counter stream, so
+ * both paths produce identical masks), computed op for op like the reference -- bmm, masked softmax, dropout, bmm --
+ * with the bmm's as batched tcgen05 GEMMs and the softmax (and its backward) as exact fp32 row kernels.
+ * probs / probs_drop / dp_ws: caller-owned [B,H,Tq,round_up(Tk,4)] float buffers of b200asr_sdpa_mat_ws_bytes bytes;
+ * probs (softmax output) and, when p_drop > 0, probs_drop (after dropout) must be kept for the backward call;
+ * probs_drop may be NULL when p_drop == 0.  dk, dv multiples of 32; Tk <= 2048. */
+size_t b200asr_sdpa_mat_ws_bytes(int B, int H, int Tq, int Tk);
+int b200asr_sdpa_mat_fwd(const float* q, const float* k, const float* v, long long q_bs, long long q_hs,
+                         long long q_rs, long long k_bs, long long k_hs, long long k_rs, long long v_bs,
+                         long long v_hs, long long v_rs, const uint8_t* key_pad, const uint8_t* dense_mask,
+                         int causal, float* out, long long o_bs, long long o_hs, long long o_rs, float* probs,
+                         float* probs_drop, int B, int H, int Tq, int Tk, int dk, int dv, float scale,
+                         float p_drop, uint64_t seed, uint64_t offset, int precision, b200asr_stream_t stream);
+/* dq/dk/dv use the strides of q/k/v and are overwritten; dout uses the strides of out */
+int b200asr_sdpa_mat_bwd(const float* dout, const float* q, const float* k, const float* v, long long q_bs,
+                         long long q_hs, long long q_rs, long long k_bs, long long k_hs, long long k_rs,
+                         long long v_bs, long long v_hs, long long v_rs, long long o_bs, long long o_hs,
+                         long long o_rs, const float* probs, const float* probs_drop, float* dq, float* dk_out,
+                         float* dv_out, float* dp_ws, int B, int H, int Tq, int Tk, int dk, int dv, float scale,
+                         float p_drop, uint64_t seed, uint64_t offset, int precision, b200asr_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * VGG front end (models/asr/transformer.py:42-53).  Activations are kept channels-last with time as the
  * outer spatial axis, [B,T,F,C], so the flatten/transpose of :74-76 becomes a free view [B*T, F*C]

@@ -132,6 +132,72 @@ def test_attention_tensor_core(L, B, H, Tq, Tk, dk, dv, mode, bwd):
         assert rel_err(got, ref) < 3e-3
 
 
+@pytest.mark.parametrize("B,H,Tq,Tk,dk,dv,mode", [
+    (2, 2, 50, 50, 64, 64, "keypad"), (3, 4, 13, 13, 32, 32, "causal+keypad"), (2, 8, 100, 200, 64, 64, "keypad"),
+    (2, 3, 70, 70, 64, 32, "dense"), (1, 2, 129, 65, 128, 128, "none"), (2, 2, 100, 100, 64, 64, "causal"),
+    (1, 1, 200, 200, 64, 64, "keypad"), (1, 2, 300, 450, 64, 64, "keypad"), (2, 2, 257, 401, 32, 64, "none"),
+    (1, 2, 40, 1030, 64, 64, "keypad"),
+])
+def test_attention_materialised_3xtf32(L, B, H, Tq, Tk, dk, dv, mode):
+    """bmm -> masked softmax -> bmm on batched 3xTF32 GEMMs (attention_mat.cu): fp32-grade against the fp64-free oracle
+    at the same tolerance as the exact-fp32 CUDA-core kernel (ragged Tk incl. Tk % 4 != 0 -> padded row pitch)."""
+    import importlib
+    import b200asr
+    from tests.test_gpu_parity import _attention_case
+    ops = importlib.import_module(b200asr.__name__ + ".ops")
+    old = ops.config.attn
+    ops.config.set(attn="tf32x3")
+    try:
+        pairs = _attention_case(ops, B, H, Tq, Tk, dk, dv, mode)
+    finally:
+        ops.config.attn = old
+    for got, ref in pairs:
+        assert rel_err(got, ref) < 2e-5
+
+
+@pytest.mark.parametrize("Tq,Tk,causal", [(40, 40, True), (33, 70, False), (64, 101, False)])
+def test_attention_materialised_dropout_matches_cuda_core_kernel(L, Tq, Tk, causal):
+    """Both attention paths index the same counter-based dropout stream: with the same (seed, offset) the materialised
+    3xTF32 path and the fp32 flash kernel drop the same probabilities, so outputs and all three gradients agree."""
+    import importlib
+    import b200asr
+    ops = importlib.import_module(b200asr.__name__ + ".ops")
+    B, H, d = 2, 3, 64
+    g = torch.Generator().manual_seed(Tq + Tk)
+    base = [torch.randn(B, H, t, d, generator=g).cuda() for t in (Tq, Tk, Tk)]
+    do = torch.randn(B, H, Tq, d, generator=g).cuda()
+    key_pad = (torch.arange(Tk)[None, :] >= torch.tensor([Tk, Tk - 5])[:, None]).to(torch.uint8).cuda()
+    outs = {}
+    old = ops.config.attn
+    try:
+        for mode in ("fp32", "tf32x3"):
+            ops.config.set(attn=mode)
+            ops.rng.seed, ops.rng.offset = 77, 5
+            q, k, v = (t.clone().requires_grad_(True) for t in base)
+            o = ops.SdpaFn.apply(q, k, v, key_pad, None, causal, 0.125, 0.3)
+            o.backward(do)
+            outs[mode] = (o.detach(), q.grad, k.grad, v.grad)
+    finally:
+        ops.config.attn = old
+    assert float((outs["fp32"][0] == 0).float().mean()) < 0.05        # only the first causal rows can lose every key
+    for a, b in zip(outs["tf32x3"], outs["fp32"]):
+        assert rel_err(a, b) < 2e-5
+
+
+def test_attention_materialised_fully_masked_row_is_nan(L):
+    import importlib
+    import b200asr
+    ops = importlib.import_module(b200asr.__name__ + ".ops")
+    q = torch.randn(1, 1, 4, 32).cuda(); k = torch.randn(1, 1, 6, 32).cuda(); v = torch.randn(1, 1, 6, 32).cuda()
+    old = ops.config.attn
+    ops.config.set(attn="tf32x3")
+    try:
+        o = ops.SdpaFn.apply(q, k, v, torch.ones(1, 6, dtype=torch.uint8).cuda(), None, False, 0.25, 0.0)
+    finally:
+        ops.config.attn = old
+    assert torch.isnan(o).all()
+
+
 def test_attention_tensor_core_rejects_long_keys(L):
     lib = L.load()
     q = torch.randn(1, 1, 64, 64, device="cuda"); k = torch.randn(1, 1, 500, 64, device="cuda"); v = torch.randn(1, 1, 500, 64, device="cuda")

@@ -28,7 +28,8 @@ print("oracle fp64+fp32 %.1fs; fp32 oracle vs fp64: pred %.2e loss %.2e grads %.
     max(grads_rel_err(grads32, {k: v.float() for k, v in grads64.items()}).values())))
 real = gold.ne(O.PAD)
 model = cuda_model(cfg, P)
-mixes = [("fp32", "fp32", "fp32", "fp32", "fp32"), ("tf32x3", "tf32x3", "tf32x3", "fp32", "fp32"),
+mixes = [("fp32", "fp32", "fp32", "fp32", "fp32"), ("tf32x3", "tf32x3", "tf32x3", "tf32x3", "fp32"),   # 2nd = package default
+         ("fp32", "fp32", "fp32", "tf32x3", "fp32"), ("tf32x3", "tf32x3", "tf32x3", "fp32", "fp32"),
          ("tf32x3", "tf32x3", "tf32x3", "tf32", "tf32"), ("tf32x3", "tf32x3", "tf32x3", "tf32", "fp32"),
          ("fp32", "fp32", "fp32", "tf32", "tf32"), ("tf32x3", "tf32", "tf32", "tf32", "tf32"), ("tf32", "tf32", "tf32", "tf32", "tf32")]
 for lin, conv, convw, attn, attnb in mixes:
