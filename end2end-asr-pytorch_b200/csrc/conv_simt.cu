@@ -593,14 +593,15 @@ int b200asr_conv3x3_bwd_weight(const float* dy, const float* x, float* dw, float
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(ws, 0, sizeof(float) * 9 * (size_t)Ci * Co, st);
   int rc;
+  int bias_done = 0;
   if (precision == B200ASR_PREC_FP32) rc = conv3x3_wgrad_simt(x, dy, (float*)ws, B, T, F, Ci, Co, st);
-  else rc = conv3x3_wgrad_tc(x, dy, (float*)ws, B, T, F, Ci, Co, precision, st);
+  else rc = conv3x3_wgrad_tc(x, dy, (float*)ws, B, T, F, Ci, Co, precision, st, dbias, &bias_done);
   if (rc) return rc;
   int total = 9 * Ci * Co;
   conv_unpack_wgrad_kernel<<<ceil_div(total, 256), 256, 0, st>>>((const float*)ws, dw, Ci, Co);
   rc = check_launch("conv_unpack_wgrad");
   if (rc) return rc;
-  if (dbias) {
+  if (dbias && !bias_done) {
     long long P = (long long)B * T * F;
     B200_REQUIRE(P < (1LL << 31), B200ASR_BAD_SHAPE, "conv3x3_bwd_weight: too many pixels");
     return launch_colsum(dy, dbias, (int)P, Co, 0, st);

@@ -14,7 +14,10 @@ int launch_colsum(const float* X, float* out, int M, int N, int accumulate, cuda
 // shape/alignment cannot be expressed as TMA tiles (callers turn that into an error, never a fallback).
 int gemm_tc(const float* A, bool a_kmaj, int lda, const float* B, bool b_kmaj, int ldb, float* C, int ldc, int M,
             int N, int K, const float* bias, int relu, const float* relu_mask, int accumulate, int nsplit,
-            cudaStream_t st, const float* b_split = nullptr, int b_rows = 0);
+            cudaStream_t st, const float* b_split = nullptr, int b_rows = 0, float* rowsum = nullptr);
+// rowsum: optional [M] += sum_k A(m,k), fused into the kernel when both operands are MN-major and nsplit == 3 (the
+// bias gradient of the weight-gradient GEMM); gemm_tc_fuses_rowsum() tells the caller whether it will be.
+bool gemm_tc_fuses_rowsum(bool a_kmaj, bool b_kmaj, int nsplit);
 // b_split: B operand pre-split as [2][b_rows][ldb] (hi | lo), 3xTF32 only -- the kernel then skips its own B split.
 
 // Batched tcgen05 GEMM (tc_bgemm.cu): C_z[M,N] = alpha * A_z B_z for z = (batch, head), operands addressed in place.
@@ -30,6 +33,7 @@ int bgemm_tc(const BOperand& A, bool a_kmaj, const BOperand& B, bool b_kmaj, flo
 int conv3x3_tc(const float* in, const float* wr, const float* bias, const float* mask, float* out, int B, int T, int F,
                int Cin, int Cout, int relu, int precision, cudaStream_t st);
 int conv3x3_wgrad_tc(const float* x, const float* dy, float* dwr, int B, int T, int F, int Ci, int Co, int precision,
-                     cudaStream_t st);
+                     cudaStream_t st, float* dbias = nullptr, int* dbias_done = nullptr);
+// dbias: optional [Co] bias gradient; *dbias_done = 1 when the kernel produced it (3xTF32), else the caller must
 
 }  // namespace b200asr

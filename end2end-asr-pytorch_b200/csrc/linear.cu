@@ -7,12 +7,12 @@ using namespace b200asr;
 
 static int gemm_dispatch(const float* A, bool ak, int lda, const float* B, bool bk, int ldb, float* C, int ldc, int M,
                          int N, int K, const float* bias, int relu, const float* mask, int accumulate, bool allow_split,
-                         int precision, cudaStream_t st, const float* b_split = nullptr, int b_rows = 0) {
+                         int precision, cudaStream_t st, const float* b_split = nullptr, int b_rows = 0, float* rowsum = nullptr) {
   if (precision == B200ASR_PREC_FP32)
     return gemm_simt(A, ak, lda, B, bk, ldb, C, ldc, M, N, K, bias, relu, mask, accumulate, allow_split, st);
   if (precision == B200ASR_PREC_TF32 || precision == B200ASR_PREC_TF32X3)
     return gemm_tc(A, ak, lda, B, bk, ldb, C, ldc, M, N, K, bias, relu, mask, accumulate, precision, st,
-                   precision == B200ASR_PREC_TF32X3 ? b_split : nullptr, b_rows);
+                   precision == B200ASR_PREC_TF32X3 ? b_split : nullptr, b_rows, rowsum);
   set_error("unknown precision %d", precision);
   return B200ASR_BAD_ARG;
 }
@@ -39,9 +39,14 @@ int b200asr_linear_bwd_weight(const float* dy, const float* x, float* dw, float*
   B200_REQUIRE(dy && x && dw && M >= 0 && N > 0 && K > 0, B200ASR_BAD_ARG, "linear_bwd_weight: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   // dw[n,k] = sum_m dy[m,n] x[m,k]: contraction over m; A(n,m) = dy[m*N + n], B(m,k) = x[m*K + k]
-  int rc = gemm_dispatch(dy, false, N, x, false, K, dw, K, N, K, M, nullptr, 0, nullptr, accumulate, true, precision, st);
+  // db[n] = sum_m dy[m,n] = row sums of A: the 3xTF32 kernel produces them from the tiles it stages (one launch and one
+  // HBM pass over dy less); other precisions run the column-sum kernel
+  const bool fuse = dbias && precision == B200ASR_PREC_TF32X3 && gemm_tc_fuses_rowsum(false, false, 3) && M > 0;
+  if (fuse && !accumulate) cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)N, st);
+  int rc = gemm_dispatch(dy, false, N, x, false, K, dw, K, N, K, M, nullptr, 0, nullptr, accumulate, true, precision, st,
+                         nullptr, 0, fuse ? dbias : nullptr);
   if (rc) return rc;
-  if (dbias) return launch_colsum(dy, dbias, M, N, accumulate, st);
+  if (dbias && !fuse) return launch_colsum(dy, dbias, M, N, accumulate, st);
   return B200ASR_OK;
 }
 

@@ -18,6 +18,7 @@ template <bool A_MN, bool B_MN, int BN_>
 struct BGemmPolicy {
   static constexpr int BN = BN_, kABytes = 128 * 128, kBBytes = BN_ * 128;
   static constexpr bool kSplitA = true, kSplitB = true, kAMN = A_MN, kBMN = B_MN;
+  static constexpr bool kSumA = false, kSumB = false;
   struct Params {
     float* C;
     long long c_bs, c_hs;     // element offsets of (batch, head) in C

@@ -17,6 +17,10 @@
 //                              // (fixed tx bytes, issued by the leader lane only); every lane advances the k cursor in Tile
 //   static __device__ uint64_t a_desc(uint32_t saddr, int ks); static __device__ uint64_t b_desc(uint32_t saddr, int ks);
 //   static __device__ void store(p, const Tile&, row, col0, const float (&v)[32]);     // 32 accumulator columns of one row
+//   static constexpr bool kSumA, kSumB;   // fused reductions over the contraction index done by the split warps (3xTF32
+//       only): kSumA = row sums of an MN-major A tile, kSumB = column sums of an MN-major B tile (bias gradients of the
+//       weight-gradient GEMMs -- the operand is in shared memory anyway, a separate column-sum pass re-reads it from HBM)
+//   static __device__ bool want_sums(p, Tile);  void sum_a_store(p, Tile, row, v);  void sum_b_store(p, Tile, col, float4 v);
 // The producer is ONE thread: anything it does per k-block is on the critical path of the whole SM (the first version
 // re-derived (b, t, f, tap) with integer divisions for every k-block -- ~1000 clk each -- and that, not the tensor pipe,
 // set the pace; see profiles/engine_ConvPolicy_r1.md).
@@ -185,6 +189,16 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       uint32_t kbg = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int nkb = Policy::num_kb(p, tile);
+        constexpr bool kSums = Policy::kSumA || Policy::kSumB;
+        static_assert(!Policy::kSumA || Policy::kAMN, "row sums need an MN-major A tile (thread = row)");
+        static_assert(!Policy::kSumB || (Policy::kBMN && Policy::kSplitB), "column sums need an MN-major B tile split in the kernel");
+        typename Policy::Tile stc;
+        bool want = false;
+        if constexpr (kSums) { stc = Policy::tile(p, tile); want = Policy::want_sums(p, stc); }
+        float asum = 0.f;
+        float4 bsum[BN / 32];
+#pragma unroll
+        for (int c = 0; c < BN / 32; c++) bsum[c] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int kb = 0; kb < nkb; kb++, kbg++) {
           if ((int)(kbg % G) != group) continue;
           const int s = kbg % S;
@@ -211,6 +225,7 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               const int k = kpart * KPT + j;
               const float x = *reinterpret_cast<const float*>(cbase + k * 128 + ((atom ^ (k & 3)) << 5));
               hi[j] = tf32_rn(x); lo[j] = x - hi[j];
+              if constexpr (Policy::kSumA) asum += x;
             }
           }
           const uint32_t acol = tmem_base + ((uint32_t)(quarter * 32) << 16) + Cfg::kAccCols + s * 64 + kpart * KPT;
@@ -221,12 +236,47 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           }
           if (Policy::kSplitB) {
             float4* stage = reinterpret_cast<float4*>(gen_base + s * Cfg::kStageBytes);
-            split_tf32_inplace(stage + Cfg::kOffBhi / 16, stage + Cfg::kOffBlo / 16, Policy::kBBytes / 16, t, ENG_SPLIT_THREADS / G);
+            if constexpr (Policy::kSumB) {
+              // same elementwise split, plus per-thread partial column sums: float4 i of the tile sits in 4 KB chunk i / 256
+              // (32 columns), k-line (i % 256) / 8, 16-byte slot i % 8; with NT threads striding by NT (a divisor of 256)
+              // a thread keeps its slot and its k & 3, hence its 4 columns within every chunk (see sum_b_col below)
+              constexpr int NT = ENG_SPLIT_THREADS / G, NF4 = Policy::kBBytes / 16;
+              float4* bh = stage + Cfg::kOffBhi / 16;
+              float4* bl = stage + Cfg::kOffBlo / 16;
+#pragma unroll
+              for (int j = 0; j < NF4 / NT; j++) {
+                const int idx = t + j * NT;
+                const float4 x = bh[idx];
+                float4 h, l;
+                h.x = tf32_rn(x.x); l.x = x.x - h.x;
+                h.y = tf32_rn(x.y); l.y = x.y - h.y;
+                h.z = tf32_rn(x.z); l.z = x.z - h.z;
+                h.w = tf32_rn(x.w); l.w = x.w - h.w;
+                bh[idx] = h;
+                bl[idx] = l;
+                float4& acc = bsum[(j * NT) / 256];
+                acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+              }
+            } else {
+              split_tf32_inplace(stage + Cfg::kOffBhi / 16, stage + Cfg::kOffBlo / 16, Policy::kBBytes / 16, t, ENG_SPLIT_THREADS / G);
+            }
             fence_proxy_async_smem();
           }
           tmem_wait_st();
           tc_fence_before();
           mbar_arrive(xfm_bar(s));
+        }
+        if constexpr (kSums) {
+          if (want) {
+            if constexpr (Policy::kSumA) Policy::sum_a_store(p, stc, row, asum);
+            if constexpr (Policy::kSumB) {
+              // logical 32-byte atom = physical atom ^ (k & 3) (SWIZZLE_128B_ATOM_32B); k & 3 = (t / 8) & 3 for every j
+              const int slot = t & 7, kph = (t >> 3) & 3;
+              const int col_in_chunk = (((slot >> 1) ^ kph) << 3) + ((slot & 1) << 2);
+#pragma unroll
+              for (int c = 0; c < BN / 32; c++) Policy::sum_b_store(p, stc, c * 32 + col_in_chunk, bsum[c]);
+            }
+          }
         }
       }
     }

@@ -1,17 +1,18 @@
 // tcgen05 GEMM for sm_100a: C[M,N] = sum_k A(m,k) B(k,n), fp32 in HBM, TF32 tensor-core math, fp32 accumulators in TMEM.
+// A policy of the persistent tile engine (tc_engine.cuh):
 //
-//   * operands arrive by TMA (cp.async.bulk.tensor; 128B swizzle, 32-byte-atom variant for MN-major tiles) straight from the fp32 row-major tensors; either
-//     operand may be K-major (contraction contiguous) or MN-major (rows contiguous) -- forward, data-gradient and
-//     weight-gradient GEMMs all run without a transpose pass;
-//   * one CTA = one 128x128 output tile, 32-deep k-blocks, multi-stage mbarrier ring;
-//     warp 0 = TMA producer, warp 1 = MMA issuer (single thread) + TMEM owner, warps 2-9 = operand split + epilogue;
+//   * operands arrive by TMA (cp.async.bulk.tensor; 128B swizzle, 32-byte-atom variant for MN-major tiles) straight from
+//     the fp32 row-major tensors; either operand may be K-major (contraction contiguous) or MN-major (rows contiguous) --
+//     forward, data-gradient and weight-gradient GEMMs all run without a transpose pass;
+//   * 128x128 output tiles, 32-deep k-blocks; tile = (m-tile, n-tile, k-split), n fastest so that the CTAs that run
+//     concurrently share the same A rows through L2;
 //   * NSPLIT = 1: kind::tf32 once; the tensor maps use the TFLOAT32 data type, so the copy engine rounds fp32 -> tf32
 //     to nearest in flight (measured: 4-5x lower error than letting the tensor core truncate the fp32 operands);
-//     NSPLIT = 3: "3xTF32" -- the transform warps split every staged tile in place into hi = rna_tf32(x) and
-//     lo = x - hi, and the issuer runs lo*hi + hi*lo + hi*hi per k-step, which recovers fp32-grade products
-//     (error ~2^-21 relative) at three MMAs per step;
+//     NSPLIT = 3: "3xTF32" -- hi = rn_tf32(x), lo = x - hi, and lo*hi + hi*lo + hi*hi per k-step, which recovers
+//     fp32-grade products (error ~2^-21 relative) at three MMAs per step; weights can arrive pre-split (PRESPLIT);
 //   * epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> bias / ReLU / ReLU-mask / accumulate -> global;
-//     split-K (grid.z) with fp32 atomics for the skinny weight-gradient shapes.
+//     split-K with fp32 atomics for the skinny weight-gradient shapes; the weight-gradient instantiation (both operands
+//     MN-major) also produces the bias gradient = row sums of its A operand dy^T from the tiles it stages anyway.
 #include "../../include/b200asr.h"
 #include "common.cuh"
 #include "kernels.h"
@@ -57,17 +58,6 @@ int make_tensor_map_f32(CUtensorMap* map, const void* base, int rank, const uint
 
 constexpr int GBM = 128, GBN = 128, GBK = 32;            // tile; k-block in fp32 elements (= 128 bytes)
 constexpr int TILE_BYTES = GBM * GBK * 4;                // 16 KB per operand per stage
-constexpr int GEMM_THREADS = 320;                       // warp 0 TMA, warp 1 MMA, warps 2-9 split + epilogue
-constexpr int GEMM_WORKERS = 256;
-
-template <int NSPLIT> struct GemmCfg {
-  static constexpr int kStages = NSPLIT == 1 ? 6 : 3;
-  static constexpr int kStageBytes = NSPLIT == 1 ? 2 * TILE_BYTES : 4 * TILE_BYTES;   // A_hi [A_lo] B_hi [B_lo]
-  static constexpr int kOffAlo = TILE_BYTES;
-  static constexpr int kOffBhi = NSPLIT == 1 ? TILE_BYTES : 2 * TILE_BYTES;
-  static constexpr int kOffBlo = 3 * TILE_BYTES;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-};
 
 struct EpiP {
   float* C;
@@ -75,190 +65,8 @@ struct EpiP {
   const float* bias;
   const float* relu_mask;
   int relu, accumulate, splits, klen;
+  float* rowsum;           // [M] += sum_k A(m,k) (bias gradient of the weight-gradient GEMM), or nullptr
 };
-
-template <bool A_MN, bool B_MN, int NSPLIT>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const EpiP e) {
-  using Cfg = GemmCfg<NSPLIT>;
-  constexpr int S = Cfg::kStages;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + S * Cfg::kStageBytes;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto xfm_bar = [&](int s) { return bar_base + 8u * (S + s); };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * S + s); };
-  const uint32_t accum_bar = bar_base + 8u * (3 * S);
-  const uint32_t tmem_slot = bar_base + 8u * (3 * S + 1);
-  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));       // generic pointer to the aligned region
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
-  const int kbeg = blockIdx.z * e.klen;
-  const int kend = min(e.K, kbeg + e.klen);
-  const int nkb = (kend - kbeg + GBK - 1) / GBK;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < S; s++) { mbar_init(full_bar(s), 1); mbar_init(xfm_bar(s), GEMM_WORKERS); mbar_init(empty_bar(s), 1); }
-    mbar_init(accum_bar, 1);
-    fence_barrier_init();
-    tma_prefetch_desc(&mapA);
-    tma_prefetch_desc(&mapB);
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, GBN);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
-
-  if (warp == 0) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ TMA producer
-      for (int kb = 0; kb < nkb; kb++) {
-        const int s = kb % S;
-        const uint32_t ph = (kb / S) & 1;
-        mbar_wait(empty_bar(s), ph ^ 1);
-        const uint32_t sa = smem_base + s * Cfg::kStageBytes;
-        const uint32_t sb = sa + Cfg::kOffBhi;
-        mbar_expect_tx(full_bar(s), 2 * TILE_BYTES);
-        const int k0 = kbeg + kb * GBK;
-        if (!A_MN) tma_load_2d(sa, &mapA, full_bar(s), k0, m0);
-        else
-#pragma unroll
-          for (int c = 0; c < 4; c++) tma_load_2d(sa + c * 4096, &mapA, full_bar(s), m0 + 32 * c, k0);
-        if (!B_MN) tma_load_2d(sb, &mapB, full_bar(s), k0, n0);
-        else
-#pragma unroll
-          for (int c = 0; c < 4; c++) tma_load_2d(sb + c * 4096, &mapB, full_bar(s), n0 + 32 * c, k0);
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ MMA issuer
-      constexpr uint32_t idesc = make_idesc_tf32(GBM, GBN, A_MN, B_MN);
-      for (int kb = 0; kb < nkb; kb++) {
-        const int s = kb % S;
-        const uint32_t ph = (kb / S) & 1;
-        mbar_wait(NSPLIT == 1 ? full_bar(s) : xfm_bar(s), ph);
-        tc_fence_after();
-        const uint32_t sa = smem_base + s * Cfg::kStageBytes;
-        const uint32_t sb = sa + Cfg::kOffBhi;
-#pragma unroll
-        for (int ks = 0; ks < GBK / 8; ks++) {
-          const uint32_t aoff = A_MN ? ks * 1024 : ks * 32;
-          const uint32_t boff = B_MN ? ks * 1024 : ks * 32;
-          constexpr uint32_t a_lbo = A_MN ? 4096 : 16, a_sbo = A_MN ? 512 : 1024, a_lt = A_MN ? kLayoutSW128Base32B : kLayoutSW128;
-          constexpr uint32_t b_lbo = B_MN ? 4096 : 16, b_sbo = B_MN ? 512 : 1024, b_lt = B_MN ? kLayoutSW128Base32B : kLayoutSW128;
-          const uint64_t a_hi = make_smem_desc(sa + aoff, a_lbo, a_sbo, a_lt);
-          const uint64_t b_hi = make_smem_desc(sb + boff, b_lbo, b_sbo, b_lt);
-          const uint32_t acc0 = (kb | ks) != 0 ? 1u : 0u;
-          if (NSPLIT == 1) {
-            umma_tf32(tmem_base, a_hi, b_hi, idesc, acc0);
-          } else {
-            const uint64_t a_lo = make_smem_desc(sa + Cfg::kOffAlo + aoff, a_lbo, a_sbo, a_lt);
-            const uint64_t b_lo = make_smem_desc(sa + Cfg::kOffBlo + boff, b_lbo, b_sbo, b_lt);
-            umma_tf32(tmem_base, a_lo, b_hi, idesc, acc0);
-            umma_tf32(tmem_base, a_hi, b_lo, idesc, 1u);
-            umma_tf32(tmem_base, a_hi, b_hi, idesc, 1u);
-          }
-        }
-        umma_commit(empty_bar(s));                 // stage reusable once these MMAs have read it
-      }
-      umma_commit(accum_bar);                      // accumulators complete
-    }
-  } else {
-    const int t = threadIdx.x - 64;                // 0..255
-    if (NSPLIT == 3) {
-      // ---------------------------------------------------------------- operand split: x -> (rna_tf32(x), x - hi)
-      for (int kb = 0; kb < nkb; kb++) {
-        const int s = kb % S;
-        const uint32_t ph = (kb / S) & 1;
-        mbar_wait(full_bar(s), ph);
-        float4* stage = reinterpret_cast<float4*>(gen_base + s * Cfg::kStageBytes);
-#pragma unroll
-        for (int op = 0; op < 2; op++) {
-          float4* hi = stage + (op == 0 ? 0 : Cfg::kOffBhi / 16);
-          float4* lo = stage + (op == 0 ? Cfg::kOffAlo / 16 : Cfg::kOffBlo / 16);
-          split_tf32_inplace(hi, lo, TILE_BYTES / 16, t, GEMM_WORKERS);
-        }
-        fence_proxy_async_smem();                  // generic-proxy writes -> visible to tcgen05.mma (async proxy)
-        mbar_arrive(xfm_bar(s));
-      }
-    }
-    // ------------------------------------------------------------------ epilogue
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    const int quarter = warp & 3;                  // TMEM lanes [32*quarter, +32) belong to this warp
-    const int half = (warp - 2) >> 2;              // two warps share a lane quarter and take alternate 32-column chunks
-    const int row = m0 + quarter * 32 + lane;
-    const bool atomic = e.splits > 1;
-    const bool first = blockIdx.z == 0;
-    const bool vec_ok = ((e.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0);
-#pragma unroll 1
-    for (int c = half; c < GBN / 32; c += 2) {
-      float v[32];
-      if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), v);
-      else
-#pragma unroll
-        for (int j = 0; j < 32; j++) v[j] = 0.f;
-      if (row >= e.M) continue;
-      const int col0 = n0 + c * 32;
-      float* crow = e.C + (size_t)row * e.ldc;
-      const float* mrow = e.relu_mask ? e.relu_mask + (size_t)row * e.ldc : nullptr;
-      if (atomic) {
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-          const int col = col0 + j;
-          if (col < e.N) atomicAdd(crow + col, v[j] + ((e.bias && first) ? e.bias[col] : 0.f));
-        }
-      } else {
-#pragma unroll
-        for (int j4 = 0; j4 < 8; j4++) {
-          const int col = col0 + j4 * 4;
-          if (col >= e.N) break;
-          float o[4] = {v[j4 * 4 + 0], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]};
-          const bool full4 = vec_ok && (col + 3 < e.N);
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            if (col + j < e.N) {
-              if (e.bias) o[j] += e.bias[col + j];
-              if (e.relu) o[j] = fmaxf(o[j], 0.f);
-              if (mrow) o[j] = mrow[col + j] > 0.f ? o[j] : 0.f;
-              if (e.accumulate) o[j] += crow[col + j];
-            }
-          }
-          if (full4) *reinterpret_cast<float4*>(crow + col) = make_float4(o[0], o[1], o[2], o[3]);
-          else
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-              if (col + j < e.N) crow[col + j] = o[j];
-        }
-      }
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tc_fence_after();
-    tmem_dealloc(tmem_base, GBN);
-  }
-}
-
-template <bool A_MN, bool B_MN, int NSPLIT>
-static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const EpiP& e, cudaStream_t st) {
-  using Cfg = GemmCfg<NSPLIT>;
-  auto* kern = tc_gemm_kernel<A_MN, B_MN, NSPLIT>;
-  static bool attr_set = false;   // per instantiation
-  if (!attr_set) {
-    cudaError_t r = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (r != cudaSuccess) { set_error("tc_gemm: cannot reserve %d bytes of shared memory: %s", Cfg::kSmemBytes, cudaGetErrorString(r)); return B200ASR_CUDA_ERROR; }
-    attr_set = true;
-  }
-  dim3 grid(ceil_div(e.N, GBN), ceil_div(e.M, GBM), e.splits);
-  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, st>>>(ma, mb, e);
-  return check_launch("tc_gemm");
-}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // GEMM policy for the persistent engine (tc_engine.cuh): tile = (m-tile, n-tile, k-split), n fastest so that the CTAs that
@@ -267,6 +75,7 @@ template <bool A_MN, bool B_MN, bool PRESPLIT = false>
 struct GemmPolicy {
   static constexpr int BN = GBN, kABytes = TILE_BYTES, kBBytes = TILE_BYTES;
   static constexpr bool kSplitA = true, kSplitB = !PRESPLIT, kAMN = A_MN, kBMN = B_MN;
+  static constexpr bool kSumA = A_MN && B_MN && !PRESPLIT, kSumB = false;
   struct Params { EpiP e; int tiles_m, tiles_n, b_rows; };
   static __device__ __forceinline__ int num_tiles(const Params& p) { return p.tiles_m * p.tiles_n * p.e.splits; }
   struct Tile { int m0, n0, z, k0; };                    // tile origin, split-K slice, k cursor
@@ -301,6 +110,11 @@ struct GemmPolicy {
 #pragma unroll
         for (int c = 0; c < 4; c++) tma_load_2d(dst + c * 4096, mapB, bar, n0 + 32 * c, k0 + roff);
     }
+  }
+  // every (row, k) of A is staged once by the n-tile-0 tiles (over all k-splits)
+  static __device__ __forceinline__ bool want_sums(const Params& p, const Tile& t) { return p.e.rowsum != nullptr && t.n0 == 0; }
+  static __device__ __forceinline__ void sum_a_store(const Params& p, const Tile& t, int r, float v) {
+    if (t.m0 + r < p.e.M) atomicAdd(p.e.rowsum + t.m0 + r, v);
   }
   static __device__ __forceinline__ uint64_t a_desc(uint32_t s, int ks) {
     return A_MN ? make_smem_desc(s + ks * 1024, 4096, 512, kLayoutSW128Base32B) : make_smem_desc(s + ks * 32, 16, 1024);
@@ -387,12 +201,13 @@ static int launch_persistent(const CUtensorMap& ma, const CUtensorMap& mb, const
 
 }  // namespace tc
 
+bool gemm_tc_fuses_rowsum(bool a_kmaj, bool b_kmaj, int nsplit) { return !a_kmaj && !b_kmaj && nsplit == 3; }
+
 int gemm_tc(const float* A, bool a_kmaj, int lda, const float* B, bool b_kmaj, int ldb, float* C, int ldc, int M, int N,
             int K, const float* bias, int relu, const float* relu_mask, int accumulate, int nsplit, cudaStream_t st,
-            const float* b_split, int b_rows) {
+            const float* b_split, int b_rows, float* rowsum) {
   using namespace tc;
-  static const int engine = [] { const char* v = getenv("B200ASR_ENGINE"); return v ? atoi(v) : 1; }();
-  const bool presplit = b_split != nullptr && nsplit == 3 && engine && a_kmaj;   // fwd (B K-major) and dgrad (B MN-major)
+  const bool presplit = b_split != nullptr && nsplit == 3 && a_kmaj;   // fwd (B K-major) and dgrad (B MN-major)
   if (presplit) B = b_split;
   if (M <= 0 || N <= 0) return B200ASR_OK;
   B200_REQUIRE(nsplit == 1 || nsplit == 3, B200ASR_BAD_ARG, "gemm_tc: nsplit must be 1 or 3");
@@ -418,21 +233,22 @@ int gemm_tc(const float* A, bool a_kmaj, int lda, const float* B, bool b_kmaj, i
     rc = make_tensor_map_f32(&mb, B, 2, dims, strides, box, !b_kmaj, nsplit == 1);
     if (rc) return rc;
   }
-  EpiP e{C, ldc, M, N, K, bias, relu_mask, relu, accumulate, 1, ceil_div(K, GBK) * GBK};
+  B200_REQUIRE(!rowsum || gemm_tc_fuses_rowsum(a_kmaj, b_kmaj, nsplit), B200ASR_BAD_ARG, "gemm_tc: row sums are fused only into the MN/MN 3xTF32 kernel");
+  EpiP e{C, ldc, M, N, K, bias, relu_mask, relu, accumulate, 1, ceil_div(K, GBK) * GBK, rowsum};
   const int tiles = ceil_div(M, GBM) * ceil_div(N, GBN);
   if (!relu && !relu_mask && K >= 1024 && tiles * 2 <= device_sm_count()) {
     // Split-K only for skinny outputs (weight gradients: few tiles, long contraction).  A general "split against wave
     // quantisation" rule was measured and lost: the zero-fill plus the per-element atomic epilogue cost more than the
     // idle SMs of the last round (linear fwd 3.5 -> 4.9 ms per step at cfg2).
     const int sms = device_sm_count();
-    int splits = min(min(sms / tiles, K / 256), engine ? 16 : 32);
+    int splits = min(min(sms / tiles, K / 256), 16);
     if (splits > 1) {
       e.klen = ceil_div(ceil_div(K, splits), GBK) * GBK;
       e.splits = ceil_div(K, e.klen);
     }
   }
   if (e.splits > 1 && !accumulate) cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * ldc, st);
-#define GO(AM, BM_, NS) return engine ? launch_persistent<AM, BM_, NS>(ma, mb, e, st) : launch<AM, BM_, NS>(ma, mb, e, st)
+#define GO(AM, BM_, NS) return launch_persistent<AM, BM_, NS>(ma, mb, e, st)
   const bool a_mn = !a_kmaj, b_mn = !b_kmaj;
   if (presplit) {
     if (!b_mn) return launch_persistent<false, false, 3, true>(ma, mb, e, st, b_rows);
