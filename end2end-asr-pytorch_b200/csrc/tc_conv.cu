@@ -205,6 +205,10 @@ int conv3x3_tc(const float* in, const float* wk, const float* bias, const float*
                "conv3x3_tc: needs Cin %% 32 == 0 and Cout in {64,128} (Cin=%d Cout=%d)", Cin, Cout);
   B200_REQUIRE(aligned16(in) && aligned16(wk) && aligned16(out) && (!bias || aligned16(bias)) && (!mask || aligned16(mask)),
                B200ASR_BAD_ALIGN, "conv3x3_tc: pointers must be 16-byte aligned");
+  if (precision == 3) {
+    static const int halo = [] { const char* v = getenv("B200ASR_CONV_HALO"); return v ? atoi(v) : 1; }();
+    if (halo) return conv3x3_tc_halo(in, wk, bias, mask, out, B, T, F, Cin, Cout, relu, st);
+  }
   CUtensorMap ma, mb;
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)F, (uint64_t)T, (uint64_t)B};

@@ -47,7 +47,12 @@ template <class Policy, int NSPLIT> struct EngineCfg {
   static constexpr int kStageBytes = NSPLIT == 1 ? (Policy::kABytes + Policy::kBBytes) : (Policy::kABytes + 2 * Policy::kBBytes);
   static constexpr int kMaxByTmem = NSPLIT == 1 ? 8 : (512 - 2 * Policy::BN) / 64;          // 64 TMEM columns of A per stage
   static constexpr int kBySmem = (200 * 1024) / kStageBytes;
-  static constexpr int kStages = kBySmem < kMaxByTmem ? (kBySmem > 8 ? 8 : kBySmem) : (kMaxByTmem > 8 ? 8 : kMaxByTmem);
+#ifndef ENG_MAX_STAGES
+#define ENG_MAX_STAGES 8
+#endif
+  static constexpr int kStagesRaw = kBySmem < kMaxByTmem ? kBySmem : kMaxByTmem;
+  static constexpr int kStagesCap = kStagesRaw > ENG_MAX_STAGES ? ENG_MAX_STAGES : kStagesRaw;
+  static constexpr int kStages = NSPLIT == 1 ? kStagesCap : kStagesCap - kStagesCap % ENG_SPLIT_GROUPS;
   static constexpr int kOffBhi = Policy::kABytes;
   static constexpr int kOffBlo = kOffBhi + Policy::kBBytes;
   static constexpr int kBarOff = kStages * kStageBytes;
@@ -57,6 +62,10 @@ template <class Policy, int NSPLIT> struct EngineCfg {
   static constexpr int kTxBytes = Policy::kABytes + Policy::kBBytes +
                                   (NSPLIT == 3 && !Policy::kSplitB ? Policy::kBBytes : 0);   // pre-split B arrives as hi+lo
   static_assert(kStages >= 2, "stage too large");
+  // Each split group must see EVERY phase of the full barriers it waits on: mbarrier parity waits only distinguish the
+  // current phase from the one before, so a group that skipped a phase of a stage could take a stale completion for the
+  // one it is waiting for.  With the stage count a multiple of the group count a stage always belongs to one group.
+  static_assert(NSPLIT == 1 || kStages % ENG_SPLIT_GROUPS == 0, "stage count must be a multiple of the split-group count");
 };
 
 template <class Policy, int NSPLIT>
@@ -111,40 +120,56 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (whole warp loops, one lane issues)
+    // The issuing thread's own instruction stream is on the critical path: the tensor pipe's queue holds only a few MMAs,
+    // so whatever it executes between the last MMA of one k-block and the first of the next (barrier poll, descriptor
+    // arithmetic) must be shorter than the time that queue takes to drain -- ~130 clk with N = 64.  Descriptors are
+    // therefore built ONCE per CTA and advanced by adding to their 14-bit address field (shared memory is < 256 KB, so
+    // the field never carries into the stride fields above it); stage index and phase are running counters.
     const bool leader = elect_one();
     constexpr uint32_t idesc = make_idesc_tf32(128, BN, Policy::kAMN, Policy::kBMN);
+    constexpr uint32_t idesc_ts = make_idesc_tf32(128, BN, false, Policy::kBMN);
     constexpr bool kNeedXfm = NSPLIT == 3;
-    uint32_t kbg = 0, tcount = 0;
+    constexpr uint32_t kStageStep = Cfg::kStageBytes >> 4, kLoStep = Policy::kBBytes >> 4;
+    const uint64_t bd0 = Policy::b_desc(smem_base + Cfg::kOffBhi, 0), ad0 = Policy::a_desc(smem_base, 0);
+    const uint32_t b_ks = (uint32_t)(Policy::b_desc(0, 1) - Policy::b_desc(0, 0));     // address-field step per 8-deep k-step
+    const uint32_t a_ks = (uint32_t)(Policy::a_desc(0, 1) - Policy::a_desc(0, 0));
+    const uint32_t bd_hi = (uint32_t)(bd0 >> 32), ad_hi = (uint32_t)(ad0 >> 32);
+    auto mk = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; };
+    uint32_t s = 0, ph = 0, tcount = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, tcount++) {
       const int nkb = Policy::num_kb(p, tile);
       const uint32_t buf = tcount & 1;
       mbar_wait(tempty_bar(buf), ((tcount >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + buf * BN;
-      for (int kb = 0; kb < nkb; kb++, kbg++) {
-        const int s = kbg % S;
-        mbar_wait(kNeedXfm ? xfm_bar(s) : full_bar(s), (kbg / S) & 1);
+      for (int kb = 0; kb < nkb; kb++) {
+        mbar_wait(kNeedXfm ? xfm_bar(s) : full_bar(s), ph);
         tc_fence_after();
-        const uint32_t sa = smem_base + s * Cfg::kStageBytes;
         if (leader) {
+          const uint32_t b_lo32 = (uint32_t)bd0 + s * kStageStep, a_lo32 = (uint32_t)ad0 + s * kStageStep;
+          const uint32_t a_t = tmem_base + Cfg::kAccCols + s * 64;
 #pragma unroll
           for (int ks = 0; ks < 4; ks++) {
-            const uint64_t b_hi = Policy::b_desc(sa + Cfg::kOffBhi, ks);
+            const uint64_t b_hi = mk(bd_hi, b_lo32 + ks * b_ks);
             const uint32_t acc0 = (kb | ks) != 0 ? 1u : 0u;
             if (NSPLIT == 1) {
-              umma_tf32(d_tmem, Policy::a_desc(sa, ks), b_hi, idesc, acc0);
+              umma_tf32(d_tmem, mk(ad_hi, a_lo32 + ks * a_ks), b_hi, idesc, acc0);
             } else {
-              constexpr uint32_t idesc_ts = make_idesc_tf32(128, BN, false, Policy::kBMN);
-              const uint64_t b_lo = Policy::b_desc(sa + Cfg::kOffBlo, ks);
-              const uint32_t a_hi = tmem_base + Cfg::kAccCols + s * 64 + ks * 8, a_lo = a_hi + 32;
+              const uint64_t b_lo = mk(bd_hi, b_lo32 + kLoStep + ks * b_ks);
+              const uint32_t a_hi = a_t + ks * 8, a_lo = a_hi + 32;
+#ifdef ENG_DBG_ONE_MMA      // timing experiment only (wrong results): one of the three products
+              umma_tf32_ts(d_tmem, a_hi, b_hi, idesc_ts, acc0);
+#else
               umma_tf32_ts(d_tmem, a_lo, b_hi, idesc_ts, acc0);
               umma_tf32_ts(d_tmem, a_hi, b_lo, idesc_ts, 1u);
               umma_tf32_ts(d_tmem, a_hi, b_hi, idesc_ts, 1u);
+#endif
             }
           }
           umma_commit(empty_bar(s));
         }
         __syncwarp();
+        if (++s == S) { s = 0; ph ^= 1; }
       }
       if (leader) umma_commit(tfull_bar(buf));
       __syncwarp();
