@@ -44,12 +44,12 @@ class ClockSampler:
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.first = [], None, index, 0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -58,6 +58,9 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
+
+    def mark(self):
+        self.first = len(self.rows)
 
     def stop(self):
         if not self.proc:
@@ -68,7 +71,8 @@ class ClockSampler:
         except Exception:
             pass
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = self.rows[self.first:] or self.rows[-3:]     # a very short timed region can fall between two samples
+        for r in rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
             except Exception:
@@ -204,12 +208,13 @@ def run_b200(args, rank, local_rank, world):
         return ms
 
     # ---- device-resident timed region (no instrumentation)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()          # nvidia-smi takes a few 100 ms to produce its first row: start it before the warm-up ...
     for _ in range(args.warmup):
         dp.step(src_d, lens_d, tgt_d)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()               # ... and keep only the rows sampled from here on (timed + instrumented regions, GPU busy)
     launches0 = lib.b200asr_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -288,7 +293,7 @@ def run_b200(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (debug only; the metric uses 32)")

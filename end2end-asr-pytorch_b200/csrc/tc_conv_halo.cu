@@ -48,7 +48,10 @@ template <int BN> struct HaloCfg {
   // ~87% of the tf32 rate, whatever the rest of the kernel does), so hi*hi and hi*lo are ONE N = 128 MMA against the
   // weight tile [B_hi ; B_lo] (adjacent in the stage, 128 K-major rows) into a 128-column accumulator, lo*hi is an N = 64
   // MMA into its first half, and the epilogue adds the two halves.
-  static constexpr bool kCat = BN == 64;
+#ifndef HALO_CAT
+#define HALO_CAT 1
+#endif
+  static constexpr bool kCat = BN == 64 && HALO_CAT;
   static constexpr int kAccW = kCat ? 128 : BN;                                  // accumulator columns per buffer
   static constexpr int kMaxByTmem = (512 - 2 * kAccW) / 64;                      // 64 TMEM columns of A (hi | lo) per stage
   static constexpr int kBySmem = (200 * 1024 - HPATCH_SLOTS * HPATCH_STAGE) / kStageBytes;
@@ -276,7 +279,9 @@ tc_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
               hi[j * 4 + 3] = tf32_rn(v.w); lo[j * 4 + 3] = v.w - hi[j * 4 + 3];
             }
             tmem_st16(acol + half * 16, hi);
+#ifndef HALO_DBG_NO_LO       // timing experiment only (wrong results): skip half of the TMEM stores
             tmem_st16(acol + 32 + half * 16, lo);
+#endif
           }
           if (tap + G < 9) load_tap(patch, tap + G, x);
           tmem_wait_st();
