@@ -6,6 +6,7 @@ needs the built library and a B200.
 """
 from . import _lib
 from .config import ASRConfig, BASELINE_CONFIGS
+from .features import spectrogram_batch
 from .install import install, uninstall
 from .metrics import calculate_loss, calculate_metrics, loss_and_stats
 from .modules import (Decoder, DecoderLayer, Encoder, EncoderLayer, MultiHeadAttention, PositionalEncoding,
@@ -17,4 +18,4 @@ from .parallel import DataParallelStep, shard_batch
 __all__ = ["ASRConfig", "BASELINE_CONFIGS", "install", "uninstall", "calculate_loss", "calculate_metrics",
            "loss_and_stats", "Transformer", "Encoder", "Decoder", "EncoderLayer", "DecoderLayer", "MultiHeadAttention",
            "ScaledDotProductAttention", "PositionwiseFeedForwardWithConv", "PositionalEncoding", "build_model",
-           "precision", "manual_seed", "FlatParams", "FusedAdam", "NoamOpt", "DataParallelStep", "shard_batch"]
+           "precision", "manual_seed", "spectrogram_batch", "FlatParams", "FusedAdam", "NoamOpt", "DataParallelStep", "shard_batch"]

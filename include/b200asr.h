@@ -248,6 +248,19 @@ int b200asr_sumsq(const float* g, long long n, float* out, b200asr_stream_t stre
 int b200asr_permute_cols_cf(const float* src, float* dst, int rows, int C, int F, int inverse,
                             b200asr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Feature front end ("next" row 4 of SURVEY.md §8f): SpectrogramParser.parse_audio (utils/data_loader.py:60-91)
+ * + the padded batch layout of _collate_fn (:182-214).  wave [B,Lmax] fp32 zero padded, lens [B] samples.
+ * STFT with n_fft-sample periodic-Hamming frames every hop samples, centred (n_fft/2 padding on both sides,
+ * reflected when pad_reflect != 0, zeros otherwise), magnitude, log1p, optional per-utterance mean / unbiased-std
+ * normalisation -> out [B,1,n_fft/2+1,Tmax] zero padded; frames_out[b] = 1 + lens[b]/hop (may be NULL).
+ * The STFT of the whole batch is ONE GEMM over overlapping frame rows (precision as for b200asr_linear_fwd).
+ * ws: b200asr_stft_ws_bytes(B, Lmax, n_fft, hop) bytes.  n_fft % 32 == 0, hop % 4 == 0. */
+size_t b200asr_stft_ws_bytes(int B, int Lmax, int n_fft, int hop);
+int b200asr_stft_features(const float* wave, const int* lens, float* out, int* frames_out, void* ws, int B,
+                          int Lmax, int Tmax, int n_fft, int hop, int pad_reflect, int normalize, int precision,
+                          b200asr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
