@@ -43,13 +43,20 @@ def _mha_core(self, query, key, value, key_pad=None, dense_mask=None, causal=Fal
     B, Tq, _ = query.shape
     Tk = key.shape[1]
     H, dk, dv = self.num_heads, self.dim_key, self.dim_value
-    q = ops.LinearFn.apply(query, self.query_linear.weight, self.query_linear.bias).view(B, Tq, H, dk).permute(0, 2, 1, 3)
-    k = ops.LinearFn.apply(key, self.key_linear.weight, self.key_linear.bias).view(B, Tk, H, dk).permute(0, 2, 1, 3)
-    v = ops.LinearFn.apply(value, self.value_linear.weight, self.value_linear.bias).view(B, Tk, H, dv).permute(0, 2, 1, 3)
     p_attn = _drop_p(self, self.attention.dropout)
     scale = 1.0 / float(self.attention.temperature)
-    o = ops.SdpaFn.apply(q, k, v, key_pad, dense_mask, causal, scale, p_attn)         # (B,H,Tq,dv) view of [B,Tq,H,dv]
-    o = o.permute(0, 2, 1, 3).reshape(B, Tq, H * dv)                                  # free: memory is token-major
+    ql, kl, vl = self.query_linear, self.key_linear, self.value_linear
+    if key is value:
+        # projections + attention as one autograd node: Q/K/V (or K/V) run as ONE GEMM when their weights lie back to back
+        # in memory (optim.FlatParams), and the attention kernels address the packed output through strides
+        o = ops.AttnProjFn.apply(query, key, ql.weight, ql.bias, kl.weight, kl.bias, vl.weight, vl.bias, H, dk, dv,
+                                 key_pad, dense_mask, causal, scale, p_attn)                # [B,Tq,H*dv], token-major
+    else:
+        q = ops.LinearFn.apply(query, ql.weight, ql.bias).view(B, Tq, H, dk).permute(0, 2, 1, 3)
+        k = ops.LinearFn.apply(key, kl.weight, kl.bias).view(B, Tk, H, dk).permute(0, 2, 1, 3)
+        v = ops.LinearFn.apply(value, vl.weight, vl.bias).view(B, Tk, H, dv).permute(0, 2, 1, 3)
+        o = ops.SdpaFn.apply(q, k, v, key_pad, dense_mask, causal, scale, p_attn)         # (B,H,Tq,dv) view of [B,Tq,H,dv]
+        o = o.permute(0, 2, 1, 3).reshape(B, Tq, H * dv)                                  # free: memory is token-major
     o = ops.LinearFn.apply(o, self.output_linear.weight, self.output_linear.bias)
     ln = self.layer_norm
     return ops.AddLNFn.apply(o, query, ln.weight, ln.bias, None, row_scale, ln.eps, _drop_p(self, self.dropout))

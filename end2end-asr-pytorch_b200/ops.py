@@ -316,82 +316,229 @@ def _bhtd_strides(t):
     return t.stride(0), t.stride(1), t.stride(2)
 
 
-class SdpaFn(torch.autograd.Function):
-    """Fused softmax(q k^T * scale, masks) v over (B,H,T,d) *views* (any batch/head/row strides).
+def _sdpa_forward_impl(q, k, v, key_pad, dense_mask, causal, scale, p_drop, head_major_out=False):
+    """Attention forward over (B,H,T,d) views (any batch/head/row strides).  Returns (out, state); `state` is what
+    _sdpa_backward_impl needs.  Output memory is token-major [B,Tq,H,dv] (returned as the (B,H,Tq,dv) view), so the head
+    merge of models/common_layers.py:194-195 is free."""
+    _need_cuda(q, k, v)
+    B, H, Tq, dk = q.shape
+    Tk, dv = k.shape[2], v.shape[3]
+    if head_major_out:      # (H,B,Tq,dv) memory: the reference's (H*B) x Tq x dv layout (common_layers.py:185)
+        out = torch.empty((H, B, Tq, dv), device=q.device, dtype=torch.float32).permute(1, 0, 2, 3)
+    else:                   # token-major memory [B,Tq,H,dv]: the head merge of common_layers.py:194-195 is a view
+        out = torch.empty((B, Tq, H, dv), device=q.device, dtype=torch.float32).permute(0, 2, 1, 3)
+    seed, off = rng.next() if p_drop > 0.0 else (0, 0)
+    qs, ks, vs, os_ = _bhtd_strides(q), _bhtd_strides(k), _bhtd_strides(v), _bhtd_strides(out)
+    # shape rules (not fallbacks; DESIGN.md section 4): the materialised 3xTF32 path needs head dims that are whole
+    # 32-float k-blocks and rows of at most 2048 keys; the TF32 flash kernel keeps the score row in TMEM
+    # (Tk <= 448, d in {32,64}); everything else runs on the fp32 CUDA-core kernel
+    prec = config.attn
+    if prec == L.PREC_TF32X3 and not (dk % 32 == 0 and dv % 32 == 0 and Tk <= 2048):
+        prec = L.PREC_FP32
+    if prec == L.PREC_TF32 and not (Tk <= 448 and dk in (32, 64) and dv in (32, 64)):
+        prec = L.PREC_FP32
+    if prec == L.PREC_TF32X3:
+        n = _lib().b200asr_sdpa_mat_ws_bytes(B, H, Tq, Tk) // 4
+        probs = torch.empty(n, device=q.device, dtype=torch.float32)
+        probs_drop = torch.empty(n, device=q.device, dtype=torch.float32) if p_drop > 0.0 else None
+        L.check(_lib().b200asr_sdpa_mat_fwd(L.ptr(q), L.ptr(k), L.ptr(v), *qs, *ks, *vs, L.ptr(key_pad), L.ptr(dense_mask),
+                                            int(causal), L.ptr(out), *os_, L.ptr(probs), L.ptr(probs_drop), B, H, Tq, Tk,
+                                            dk, dv, float(scale), float(p_drop), seed, off, prec, _stream()), "sdpa_mat_fwd")
+        return out, dict(mat=True, tensors=(q, k, v, out, probs, probs_drop),
+                         meta=(int(causal), float(scale), float(p_drop), seed, off, prec))
+    lse = torch.empty((B, H, Tq), device=q.device, dtype=torch.float32)
+    L.check(_lib().b200asr_sdpa_fwd(L.ptr(q), L.ptr(k), L.ptr(v), *qs, *ks, *vs, L.ptr(key_pad), L.ptr(dense_mask),
+                                    int(causal), L.ptr(out), *os_, L.ptr(lse), B, H, Tq, Tk, dk, dv, float(scale),
+                                    float(p_drop), seed, off, prec, _stream()), "sdpa_fwd")
+    bwd_prec = config.attn_bwd if (dk in (32, 64) and dv in (32, 64)) else L.PREC_FP32
+    if bwd_prec == L.PREC_TF32X3:
+        bwd_prec = L.PREC_FP32       # the flash-style backward exists as fp32 (CUDA cores) and TF32 (tcgen05) only
+    return out, dict(mat=False, tensors=(q, k, v, out, lse, key_pad, dense_mask),
+                     meta=(int(causal), float(scale), float(p_drop), seed, off, bwd_prec))
 
-    Output is allocated token-major [B,Tq,H,dv] and returned as the (B,H,Tq,dv) view, so the head merge of
-    models/common_layers.py:194-195 is free."""
 
-    @staticmethod
-    def forward(ctx, q, k, v, key_pad, dense_mask, causal, scale, p_drop, head_major_out=False):
-        _need_cuda(q, k, v)
-        B, H, Tq, dk = q.shape
-        Tk, dv = k.shape[2], v.shape[3]
-        if head_major_out:      # (H,B,Tq,dv) memory: the reference's (H*B) x Tq x dv layout (common_layers.py:185)
-            out = torch.empty((H, B, Tq, dv), device=q.device, dtype=torch.float32).permute(1, 0, 2, 3)
-        else:                   # token-major memory [B,Tq,H,dv]: the head merge of common_layers.py:194-195 is a view
-            out = torch.empty((B, Tq, H, dv), device=q.device, dtype=torch.float32).permute(0, 2, 1, 3)
-        seed, off = rng.next() if p_drop > 0.0 else (0, 0)
-        qs, ks, vs, os_ = _bhtd_strides(q), _bhtd_strides(k), _bhtd_strides(v), _bhtd_strides(out)
-        # shape rules (not fallbacks; DESIGN.md section 4): the materialised 3xTF32 path needs head dims that are whole
-        # 32-float k-blocks and rows of at most 2048 keys; the TF32 flash kernel keeps the score row in TMEM
-        # (Tk <= 448, d in {32,64}); everything else runs on the fp32 CUDA-core kernel
-        prec = config.attn
-        if prec == L.PREC_TF32X3 and not (dk % 32 == 0 and dv % 32 == 0 and Tk <= 2048):
-            prec = L.PREC_FP32
-        if prec == L.PREC_TF32 and not (Tk <= 448 and dk in (32, 64) and dv in (32, 64)):
-            prec = L.PREC_FP32
-        if prec == L.PREC_TF32X3:
-            n = _lib().b200asr_sdpa_mat_ws_bytes(B, H, Tq, Tk) // 4
-            probs = torch.empty(n, device=q.device, dtype=torch.float32)
-            probs_drop = torch.empty(n, device=q.device, dtype=torch.float32) if p_drop > 0.0 else None
-            L.check(_lib().b200asr_sdpa_mat_fwd(L.ptr(q), L.ptr(k), L.ptr(v), *qs, *ks, *vs, L.ptr(key_pad), L.ptr(dense_mask),
-                                                int(causal), L.ptr(out), *os_, L.ptr(probs), L.ptr(probs_drop), B, H, Tq, Tk,
-                                                dk, dv, float(scale), float(p_drop), seed, off, prec, _stream()), "sdpa_mat_fwd")
-            ctx.save_for_backward(q, k, v, out, probs, probs_drop)
-            ctx.meta = (int(causal), float(scale), float(p_drop), seed, off, prec)
-            ctx.mat = True
-            return out
-        lse = torch.empty((B, H, Tq), device=q.device, dtype=torch.float32)
-        L.check(_lib().b200asr_sdpa_fwd(L.ptr(q), L.ptr(k), L.ptr(v), *qs, *ks, *vs, L.ptr(key_pad), L.ptr(dense_mask),
-                                        int(causal), L.ptr(out), *os_, L.ptr(lse), B, H, Tq, Tk, dk, dv, float(scale),
-                                        float(p_drop), seed, off, prec, _stream()), "sdpa_fwd")
-        ctx.save_for_backward(q, k, v, out, lse, key_pad, dense_mask)
-        bwd_prec = config.attn_bwd if (dk in (32, 64) and dv in (32, 64)) else L.PREC_FP32
-        if bwd_prec == L.PREC_TF32X3:
-            bwd_prec = L.PREC_FP32       # the flash-style backward exists as fp32 (CUDA cores) and TF32 (tcgen05) only
-        ctx.meta = (int(causal), float(scale), float(p_drop), seed, off, bwd_prec)
-        ctx.mat = False
-        return out
-
-    @staticmethod
-    def backward(ctx, dout):
-        causal, scale, p_drop, seed, off, prec = ctx.meta
-        q, k, v, out = ctx.saved_tensors[:4]
-        B, H, Tq, dk = q.shape
-        Tk, dv = k.shape[2], v.shape[3]
-        if dout.stride() != out.stride():
-            dout = torch.empty_strided(out.shape, out.stride(), device=out.device, dtype=out.dtype).copy_(dout)
+def _sdpa_backward_impl(state, dout, dq=None, dkk=None, dvv=None):
+    """Attention backward.  dq/dk/dv may be given as preallocated (B,H,T,d) views (they must have the strides of q/k/v;
+    the fused projection path passes column slices of one [tokens, 3*H*d] buffer); otherwise they are allocated."""
+    causal, scale, p_drop, seed, off, prec = state["meta"]
+    q, k, v, out = state["tensors"][:4]
+    B, H, Tq, dk = q.shape
+    Tk, dv = k.shape[2], v.shape[3]
+    if dout.stride() != out.stride():
+        dout = torch.empty_strided(out.shape, out.stride(), device=out.device, dtype=out.dtype).copy_(dout)
+    if dq is None:
         dq = torch.empty_strided(q.shape, q.stride(), device=q.device, dtype=torch.float32) if _dense_like(q) else None
         dkk = torch.empty_strided(k.shape, k.stride(), device=q.device, dtype=torch.float32) if _dense_like(k) else None
         dvv = torch.empty_strided(v.shape, v.stride(), device=q.device, dtype=torch.float32) if _dense_like(v) else None
         if dq is None or dkk is None or dvv is None:
             raise RuntimeError("sdpa backward: q/k/v views must be dense permutations of a contiguous tensor")
-        qs, ks, vs, os_ = _bhtd_strides(q), _bhtd_strides(k), _bhtd_strides(v), _bhtd_strides(out)
-        if ctx.mat:
-            probs, probs_drop = ctx.saved_tensors[4:6]
-            dp = torch.empty_like(probs)
-            L.check(_lib().b200asr_sdpa_mat_bwd(L.ptr(dout), L.ptr(q), L.ptr(k), L.ptr(v), *qs, *ks, *vs, *os_, L.ptr(probs),
-                                                L.ptr(probs_drop), L.ptr(dq), L.ptr(dkk), L.ptr(dvv), L.ptr(dp), B, H, Tq, Tk,
-                                                dk, dv, scale, p_drop, seed, off, prec, _stream()), "sdpa_mat_bwd")
-            return dq, dkk, dvv, None, None, None, None, None, None
-        lse, key_pad, dense_mask = ctx.saved_tensors[4:7]
-        delta = torch.empty((B, H, Tq), device=q.device, dtype=torch.float32)
-        L.check(_lib().b200asr_sdpa_bwd(L.ptr(dout), L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(out), L.ptr(lse), *qs, *ks, *vs, *os_,
-                                        L.ptr(key_pad), L.ptr(dense_mask), causal, L.ptr(dq), L.ptr(dkk), L.ptr(dvv),
-                                        L.ptr(delta), B, H, Tq, Tk, dk, dv, scale, p_drop, seed, off, prec, _stream()),
-                "sdpa_bwd")
+    elif dq.stride() != q.stride() or dkk.stride() != k.stride() or dvv.stride() != v.stride():
+        raise RuntimeError("sdpa backward: preallocated gradients must have the strides of q/k/v")
+    qs, ks, vs, os_ = _bhtd_strides(q), _bhtd_strides(k), _bhtd_strides(v), _bhtd_strides(out)
+    if state["mat"]:
+        probs, probs_drop = state["tensors"][4:6]
+        dp = torch.empty_like(probs)
+        L.check(_lib().b200asr_sdpa_mat_bwd(L.ptr(dout), L.ptr(q), L.ptr(k), L.ptr(v), *qs, *ks, *vs, *os_, L.ptr(probs),
+                                            L.ptr(probs_drop), L.ptr(dq), L.ptr(dkk), L.ptr(dvv), L.ptr(dp), B, H, Tq, Tk,
+                                            dk, dv, scale, p_drop, seed, off, prec, _stream()), "sdpa_mat_bwd")
+        return dq, dkk, dvv
+    lse, key_pad, dense_mask = state["tensors"][4:7]
+    delta = torch.empty((B, H, Tq), device=q.device, dtype=torch.float32)
+    L.check(_lib().b200asr_sdpa_bwd(L.ptr(dout), L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(out), L.ptr(lse), *qs, *ks, *vs, *os_,
+                                    L.ptr(key_pad), L.ptr(dense_mask), causal, L.ptr(dq), L.ptr(dkk), L.ptr(dvv),
+                                    L.ptr(delta), B, H, Tq, Tk, dk, dv, scale, p_drop, seed, off, prec, _stream()),
+            "sdpa_bwd")
+    return dq, dkk, dvv
+
+
+class SdpaFn(torch.autograd.Function):
+    """Fused softmax(q k^T * scale, masks) v over (B,H,T,d) *views* (any batch/head/row strides)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, key_pad, dense_mask, causal, scale, p_drop, head_major_out=False):
+        out, state = _sdpa_forward_impl(q, k, v, key_pad, dense_mask, causal, scale, p_drop, head_major_out)
+        ctx.state = state        # tensors are kept alive by the dict (no in-place ops touch them afterwards)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dq, dkk, dvv = _sdpa_backward_impl(ctx.state, dout)
+        ctx.state = None
         return dq, dkk, dvv, None, None, None, None, None, None
+
+
+def _adjacent(*ts):
+    """True if the tensors are contiguous, same-width row blocks lying back to back in memory (FlatParams lays the
+    q/k/v projection weights -- and their gradients -- out like that), i.e. they can be used as ONE stacked matrix."""
+    for a, b in zip(ts[:-1], ts[1:]):
+        if a is None or b is None or not (a.is_contiguous() and b.is_contiguous()):
+            return False
+        if a.shape[1:] != b.shape[1:] or a.data_ptr() + a.numel() * 4 != b.data_ptr():
+            return False
+        if a.untyped_storage().data_ptr() != b.untyped_storage().data_ptr():
+            return False        # neighbours by accident of the allocator: a view cannot span two storages
+    return True
+
+
+def _stacked(*ts):
+    """The tensors of _adjacent() as one view [sum rows, ...]."""
+    rows = sum(t.shape[0] for t in ts)
+    shape = (rows,) + tuple(ts[0].shape[1:])
+    stride = ts[0].stride() if ts[0].dim() > 1 else (1,)
+    return ts[0].as_strided(shape, stride, ts[0].storage_offset())
+
+
+class AttnProjFn(torch.autograd.Function):
+    """Q/K/V projections + attention as ONE autograd node (MultiHeadAttention.forward up to the head merge,
+    models/common_layers.py:176-195).
+
+    When the three projection weights (and biases, and their .grad) lie back to back in memory -- optim.FlatParams
+    arranges that -- the projections of a common input run as one GEMM with N = 3*H*d (self-attention) or N = 2*H*d (K and
+    V of encoder-decoder attention): 200-tile problems on 148 SMs become 600-tile ones, the three data gradients become one
+    GEMM with K = 3*H*d (no gradient-accumulation adds), the three weight gradients one split-K GEMM.  The attention kernels
+    read Q/K/V as column slices of the packed projection output and write dQ/dK/dV into column slices of one packed
+    buffer, all through strides.  Any other memory arrangement runs the same arithmetic as three GEMMs."""
+
+    @staticmethod
+    def forward(ctx, xq, xkv, wq, bq, wk, bk, wv, bv, H, dk, dv, key_pad, dense_mask, causal, scale, p_drop):
+        _need_cuda(xq, xkv, wq, wk, wv)
+        same = xq is xkv
+        B, Tq, D = xq.shape
+        Tk = xkv.shape[1]
+        xq2 = _f32c(xq).reshape(-1, D)
+        xkv2 = xq2 if same else _f32c(xkv).reshape(-1, xkv.shape[2])
+        ws_list = [_f32c(w.reshape(w.shape[0], -1)) for w in (wq, wk, wv)]
+        prec = _linear_prec(ws_list[0].shape[0], D)
+        has_bias = bq is not None and bk is not None and bv is not None
+        n_q, n_k, n_v = (w.shape[0] for w in ws_list)
+        fuse3 = same and _adjacent(*ws_list) and (not has_bias or _adjacent(bq, bk, bv))
+        fuse2 = (not fuse3) and _adjacent(ws_list[1], ws_list[2]) and (not has_bias or _adjacent(bk, bv))
+        if fuse3:
+            groups = [((0, 1, 2), xq2)]
+        elif fuse2:
+            groups = [((0,), xq2), ((1, 2), xkv2)]
+        else:
+            groups = [((0,), xq2), ((1,), xkv2), ((2,), xkv2)]
+        bs_list = [bq, bk, bv]
+        packed, saved = [], []
+        for idx, x2 in groups:
+            W = _stacked(*[ws_list[i] for i in idx])
+            b = _stacked(*[bs_list[i] for i in idx]) if has_bias else None
+            wsplit = split_weight(W, prec)
+            y = linear_fwd(x2, W, b, False, prec, wsplit)
+            packed.append(y)
+            saved.append((idx, x2, W, wsplit))
+        # column slices of the packed outputs as (B,H,T,d) views
+        def head_view(y, col0, T, d):
+            return y.view(B, T, y.shape[1])[:, :, col0:col0 + H * d].unflatten(2, (H, d)).permute(0, 2, 1, 3)
+        if fuse3:
+            q = head_view(packed[0], 0, Tq, dk); k = head_view(packed[0], n_q, Tk, dk); v = head_view(packed[0], n_q + n_k, Tk, dv)
+        elif fuse2:
+            q = head_view(packed[0], 0, Tq, dk); k = head_view(packed[1], 0, Tk, dk); v = head_view(packed[1], n_k, Tk, dv)
+        else:
+            q = head_view(packed[0], 0, Tq, dk); k = head_view(packed[1], 0, Tk, dk); v = head_view(packed[2], 0, Tk, dv)
+        out, state = _sdpa_forward_impl(q, k, v, key_pad, dense_mask, causal, scale, p_drop)
+        ctx.state, ctx.saved, ctx.prec, ctx.has_bias = state, saved, prec, has_bias
+        ctx.params = (wq, bq, wk, bk, wv, bv)
+        ctx.shapes = (xq.shape, xkv.shape, same, fuse3, fuse2, (n_q, n_k, n_v), H, dk, dv)
+        return out.permute(0, 2, 1, 3).reshape(B, Tq, H * dv)          # free: memory is token-major
+
+    @staticmethod
+    def backward(ctx, dout):
+        xq_shape, xkv_shape, same, fuse3, fuse2, (n_q, n_k, n_v), H, dk, dv = ctx.shapes
+        q, k, v = ctx.state["tensors"][:3]
+        B, Tq, Tk = q.shape[0], q.shape[2], k.shape[2]
+        dev = q.device
+        new = lambda m, n: torch.empty((m, n), device=dev, dtype=torch.float32)
+        def head_view(y, col0, T, d):
+            return y.view(B, T, y.shape[1])[:, :, col0:col0 + H * d].unflatten(2, (H, d)).permute(0, 2, 1, 3)
+        if fuse3:
+            dys = [new(B * Tq, n_q + n_k + n_v)]
+            dq, dkk, dvv = head_view(dys[0], 0, Tq, dk), head_view(dys[0], n_q, Tk, dk), head_view(dys[0], n_q + n_k, Tk, dv)
+        elif fuse2:
+            dys = [new(B * Tq, n_q), new(B * Tk, n_k + n_v)]
+            dq, dkk, dvv = head_view(dys[0], 0, Tq, dk), head_view(dys[1], 0, Tk, dk), head_view(dys[1], n_k, Tk, dv)
+        else:
+            dys = [new(B * Tq, n_q), new(B * Tk, n_k), new(B * Tk, n_v)]
+            dq, dkk, dvv = head_view(dys[0], 0, Tq, dk), head_view(dys[1], 0, Tk, dk), head_view(dys[2], 0, Tk, dv)
+        dout4 = dout.reshape(B, Tq, H, dv).permute(0, 2, 1, 3)
+        _sdpa_backward_impl(ctx.state, dout4, dq, dkk, dvv)
+        ctx.state = None
+        params = ctx.params
+        grads_w, grads_b = [None] * 3, [None] * 3
+        dxq = dxkv = None
+        need_xq, need_xkv = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        for (idx, x2, W, wsplit), dy in zip(ctx.saved, dys):
+            feeds_q = 0 in idx
+            if (feeds_q and need_xq) or (not feeds_q and (need_xkv or (same and need_xq))):
+                dx = linear_bwd_data(dy, W, None, ctx.prec, wsplit)
+                if feeds_q:
+                    dxq = dx if dxq is None else dxq + dx
+                elif same:
+                    dxq = dx if dxq is None else dxq + dx
+                else:
+                    dxkv = dx if dxkv is None else dxkv + dx
+            ws_ = [params[2 * i] for i in idx]
+            bs_ = [params[2 * i + 1] for i in idx]
+            sinks_w = [_grad_sink(w) for w in ws_]
+            sinks_b = [_grad_sink(b) for b in bs_] if ctx.has_bias else []
+            w_sink = b_sink = None
+            if all(g is not None for g in sinks_w) and _adjacent(*[g.reshape(g.shape[0], -1) for g in sinks_w]):
+                w_sink = _stacked(*[g.reshape(g.shape[0], -1) for g in sinks_w])
+            if ctx.has_bias and all(g is not None for g in sinks_b) and _adjacent(*sinks_b):
+                b_sink = _stacked(*sinks_b)
+            dw, db = linear_bwd_weight(dy, x2, ctx.has_bias, ctx.prec, w_sink, b_sink)
+            if dw is not None:          # no direct accumulation: hand the slices to autograd
+                r0 = 0
+                for i in idx:
+                    n_i = (n_q, n_k, n_v)[i]
+                    grads_w[i] = dw[r0:r0 + n_i].view(params[2 * i].shape)
+                    grads_b[i] = db[r0:r0 + n_i] if db is not None else None
+                    r0 += n_i
+        dxq = dxq.view(xq_shape) if dxq is not None else None
+        dxkv = dxkv.view(xkv_shape) if dxkv is not None else None
+        return (dxq, dxkv, grads_w[0], grads_b[0], grads_w[1], grads_b[1], grads_w[2], grads_b[2],
+                None, None, None, None, None, None, None, None)
 
 
 def _dense_like(t):

@@ -21,10 +21,23 @@ class FlatParams:
 
     def __init__(self, module: torch.nn.Module, extra: int = 2):
         seen, params = set(), []
-        for p in module.parameters():
-            if p.requires_grad and id(p) not in seen:
+
+        def take(p):
+            if p is not None and p.requires_grad and id(p) not in seen:
                 seen.add(id(p))
                 params.append(p)
+
+        # Q/K/V projection weights (then their biases) of every attention block go back to back, so that the block can run
+        # them -- and their gradients -- as one stacked GEMM operand (ops.AttnProjFn); everything else in module order
+        for m in module.modules():
+            lin = [getattr(m, n, None) for n in ("query_linear", "key_linear", "value_linear")]
+            if all(isinstance(l, torch.nn.Linear) for l in lin):
+                for l in lin:
+                    take(l.weight)
+                for l in lin:
+                    take(l.bias)
+        for p in module.parameters():
+            take(p)
         self.params = params
         dev = params[0].device
         sizes = [p.numel() for p in params]

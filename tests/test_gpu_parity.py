@@ -171,6 +171,43 @@ def test_add_layernorm_fwd_bwd(b200, rows, T, d, with_res, with_pe, with_scale):
     assert rel_err(bc.grad, beta.grad) < 1e-4
 
 
+@pytest.mark.parametrize("feat,L,H,d,dk,dv,di,B,T,Tt,V,freq", [
+    ("vgg_cnn", 2, 4, 128, 32, 32, 256, 2, 20, 9, 77, 41),
+    ("", 2, 2, 64, 32, 64, 128, 3, 50, 11, 33, 161),                  # dk != dv: the stacked Q|K|V rows differ in width
+])
+def test_flat_params_stack_qkv_projections(b200, feat, L, H, d, dk, dv, di, B, T, Tt, V, freq):
+    """optim.FlatParams lays W_q|W_k|W_v (and biases, and their gradients) back to back, which makes ops.AttnProjFn run
+    the projections as one stacked GEMM with the weight / bias gradients accumulated straight into the flat buffer
+    (self-attention: Q|K|V, encoder-decoder attention: K|V).  Same oracle, same tolerance as the separate-GEMM path."""
+    from tests.gpu_util import TOL, cuda_model, cuda_step
+    ops = _ops(b200)
+    cfg = O.OracleConfig(num_layers=L, num_heads=H, dim_model=d, dim_key=dk, dim_value=dv, dim_inner=di, vocab=V,
+                         feat_extractor=feat, tgt_max_len=Tt, freq=freq)
+    P = O.init_params(cfg, seed=5)
+    for seed in range(1, 200):
+        src, lens, tgt = O.synthetic_batch(cfg, B, T, seed=seed, ragged=True)
+        if feat != "vgg_cnn" or vgg_pools_well_separated(P, src):
+            break
+    pred_o, gold_o, hyp_o, loss_o, n_word, grads_o = O.forward_backward({k: v.double() for k, v in P.items()}, cfg, src.double(),
+                                                                        lens, tgt, 0.1)
+    model = cuda_model(cfg, P)
+    flat = b200.FlatParams(model)
+    att = model.encoder.layers[0].self_attn
+    ws = [att.query_linear.weight, att.key_linear.weight, att.value_linear.weight]
+    assert ops._adjacent(*ws) and ops._adjacent(*[w.grad for w in ws])          # the layout the fused path keys on
+    cross = model.decoder.layers[0].encoder_attn
+    assert ops._adjacent(cross.key_linear.weight, cross.value_linear.weight)
+    flat.zero_grad()
+    pred, gold, hyp, _ = model(src.cuda(), lens, tgt.cuda())
+    loss, stats = b200.loss_and_stats(pred, gold, 0.1)
+    loss.backward()
+    flat.ensure_grad_views()
+    grads = {n: p.grad.detach().cpu() for n, p in model.named_parameters()}
+    assert rel_err(pred.cpu(), pred_o.float()) < TOL
+    assert abs(loss.item() - loss_o.item()) < TOL * abs(loss_o.item())
+    assert_grads_close(grads, {k: v.float() for k, v in grads_o.items()}, TOL, exact_kernels=b200.k == 1.0)
+
+
 def _attention_case(ops, B, H, Tq, Tk, dk, dv, mode, seed=0):
     g = torch.Generator().manual_seed(seed)
     q = torch.randn(B, Tq, H * dk, generator=g, requires_grad=True)
