@@ -132,8 +132,8 @@ def cpu_oracle_throughput(batch, steps, warmup, threads=None):
     """Oracle port (oracle/asr_oracle.py: the reference's algorithm restated on torch CPU kernels) fwd+bwd utt/s."""
     from oracle import asr_oracle as O
     import b200asr
-    if threads:
-        torch.set_num_threads(threads)
+    # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would time a single-threaded baseline)
+    torch.set_num_threads(threads or len(os.sched_getaffinity(0)))
     c = b200asr.BASELINE_CONFIGS[WORKLOAD]["cfg"]
     ocfg = O.OracleConfig(num_layers=c.num_layers, num_heads=c.num_heads, dim_model=c.dim_model, dim_key=c.dim_key,
                           dim_value=c.dim_value, dim_inner=c.dim_inner, vocab=c.vocab, feat_extractor=c.feat_extractor,
@@ -154,7 +154,7 @@ def cpu_oracle_throughput(batch, steps, warmup, threads=None):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    b = 2
+    b = 8            # bounded sample: a quarter of the cfg2 batch per step (~3 s of CPU work), enough rows to keep all cores busy
     ups, mean, threads = cpu_oracle_throughput(b, args.steps, args.warmup)
     out = {"impl": "reference", "metric": METRIC, "value": ups, "unit": "utt/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
