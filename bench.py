@@ -266,7 +266,11 @@ def run_b200(args, rank, local_rank, world):
     roof = {"bound": "tensor", "kernel": top["kernel"], "achieved": top["tflops"], "peak": tf32_peak, "unit": "TFLOP/s",
             "frac": top["tflops"] / tf32_peak, "traffic": None,
             "peak_source": f"{peaks['source']} bf16_tflops_sustained/2 (TF32 = half the bf16 tensor rate)",
-            "share_of_step": top["share"]}
+            "share_of_step": top["share"],
+            # 3xTF32 issues three tf32 MMAs per algorithmic product, so `frac` tops out at 1/3 for precision-3 kernels;
+            # the tensor-pipe occupancy is frac * mma_per_product (ncu: sm__pipe_tensor_cycles_active, profiles/)
+            "mma_per_product": 3 if ops.config.conv_wgrad == 3 else 1,
+            "tensor_pipe_frac": top["tflops"] / tf32_peak * (3 if ops.config.conv_wgrad == 3 else 1)}
     out = {"metric": METRIC, "value": world * B / (ms_dev / 1e3), "unit": "utt/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32" if not args.precision else "f32(" + args.precision + ")", "data": "synthetic",
@@ -277,8 +281,8 @@ def run_b200(args, rank, local_rank, world):
                                     "legend": "0 = fp32 CUDA cores, 1 = tcgen05 TF32 (RN), 3 = tcgen05 3xTF32 (fp32-grade)"},
                       "step": "zero_grad+fwd+CE+bwd+allreduce+adam", "parallelism": f"dp{world}",
                       "l2": "per-step working set (GBs of activations) >> 126 MB L2; no explicit flush"},
-           "e2e": {"value": world * B / (ms_e2e / 1e3), "unit": "utt/s", "h2d_bytes_per_step": src_h.numel() * 4 + tgt_h.numel() * 8,
-                   "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e, "wall_ms_per_step": wall_ms},
+           "e2e": {"value": world * B / (ms_e2e / 1e3), "unit": "utt/s", "h2d_bytes_per_step": world * (src_h.numel() * 4 + tgt_h.numel() * 8),
+                   "d2h_bytes_per_step": world * 4, "ms_per_step": ms_e2e, "wall_ms_per_step": wall_ms},
            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": groups[:24], "profiled_ms_per_step": ms_prof,
            "final_loss": final_loss}
     if world == 1 and not args.no_cpu:
