@@ -1,9 +1,10 @@
 // 3x3 convolution (forward / data gradient), 3xTF32, "halo" variant of the persistent tcgen05 kernel.
 //
-// Why: every tcgen05 kernel of this library runs into the same wall first -- L2 -> SM bandwidth.  ncu on the tap-shifted
-// implicit GEMM (tc_conv.cu) shows l1tex__m_xbar2l1tex_read_bytes (TMA) at 12.3 TB/s = the chip-wide L2 throughput cap
-// (~6300 B/clk, B300_MICROARCH.md), and issuing one MMA instead of three barely shortens the kernel.  That kernel fetches
-// the activation tile nine times per 32-channel slice (once per tap, 16 KB each).  Here the 16 x 8 output tile's input
+// Why: ncu on the tap-shifted implicit GEMM (tc_conv.cu) shows l1tex__m_xbar2l1tex_read_bytes (TMA) at 12.3 TB/s = the
+// chip-wide L2 throughput cap (~6300 B/clk, B300_MICROARCH.md): that kernel fetches the activation tile nine times per
+// 32-channel slice (once per tap, 16 KB each).  (Measured effect of removing that traffic alone: small -- the kernel is
+// not bound by one resource; what moved it was requesting the first-touch patch a slice ahead and the N = 128 MMA for
+// Cout = 64)  Here the 16 x 8 output tile's input
 // patch INCLUDING its one-pixel halo -- 18 x 10 pixels x 32 channels = 22.5 KB -- is fetched ONCE per slice, and the nine
 // taps are nine shifted row mappings of that patch: 6.4x less activation traffic (weights are unchanged).
 //
@@ -12,8 +13,8 @@
 // the MMAs are TS-form (A from TMEM, B = pre-split weights from smem).  So the patch needs no UMMA-legal layout -- a
 // thread simply reads patch row (tt + dt) * 10 + (ff + df) for its output pixel (tt, ff) and tap (dt, df).
 //
-// Roles (448 threads, 1 CTA / SM, persistent over tiles): warp 0 TMA (patch ring of 3, one slice ahead; weight ring of S), warp 1 MMA issue
-// + TMEM owner, warps 2-5 epilogue (double-buffered accumulators), warps 6-13 split (two groups on alternating taps).
+// Roles (448 threads, 1 CTA / SM, persistent over tiles): warp 0 TMA (patch ring of 3, one slice ahead; weight ring of S),
+// warp 1 MMA issue + TMEM owner, warps 2-5 epilogue (double-buffered accumulators), warps 6-13 split (two groups on alternating taps).
 #include <stdlib.h>
 
 #include "../../include/b200asr.h"
@@ -279,9 +280,7 @@ tc_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
               hi[j * 4 + 3] = tf32_rn(v.w); lo[j * 4 + 3] = v.w - hi[j * 4 + 3];
             }
             tmem_st16(acol + half * 16, hi);
-#ifndef HALO_DBG_NO_LO       // timing experiment only (wrong results): skip half of the TMEM stores
             tmem_st16(acol + 32 + half * 16, lo);
-#endif
           }
           if (tap + G < 9) load_tap(patch, tap + G, x);
           tmem_wait_st();

@@ -157,13 +157,9 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             } else {
               const uint64_t b_lo = mk(bd_hi, b_lo32 + kLoStep + ks * b_ks);
               const uint32_t a_hi = a_t + ks * 8, a_lo = a_hi + 32;
-#ifdef ENG_DBG_ONE_MMA      // timing experiment only (wrong results): one of the three products
-              umma_tf32_ts(d_tmem, a_hi, b_hi, idesc_ts, acc0);
-#else
               umma_tf32_ts(d_tmem, a_lo, b_hi, idesc_ts, acc0);
               umma_tf32_ts(d_tmem, a_hi, b_lo, idesc_ts, 1u);
               umma_tf32_ts(d_tmem, a_hi, b_hi, idesc_ts, 1u);
-#endif
             }
           }
           umma_commit(empty_bar(s));
