@@ -63,6 +63,31 @@ def test_flat_params_views_alias_one_buffer():
     assert all(p.grad.data_ptr() >= flat.flat_grad.data_ptr() for p in lin.parameters())
 
 
+def test_flat_params_lay_qkv_projections_back_to_back():
+    """The layout ops.AttnProjFn keys on: W_q|W_k|W_v, their biases and all their gradients adjacent in ONE storage, while
+    names / shapes / values (state_dict) are untouched."""
+    import importlib
+    ops = importlib.import_module(b200asr.__name__ + ".ops")
+    m = b200asr.build_model(b200asr.ASRConfig(num_layers=2, num_heads=2, dim_model=32, dim_key=16, dim_value=8, dim_inner=64,
+                                              vocab=40, feat_extractor="", tgt_max_len=6))
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    flat = b200asr.FlatParams(m)
+    blocks = [l.self_attn for l in m.encoder.layers] + [a for l in m.decoder.layers for a in (l.self_attn, l.encoder_attn)]
+    for att in blocks:
+        ws = [att.query_linear.weight, att.key_linear.weight, att.value_linear.weight]
+        bs = [att.query_linear.bias, att.key_linear.bias, att.value_linear.bias]
+        assert ops._adjacent(*ws) and ops._adjacent(*bs)                       # dk != dv: rows differ, widths equal
+        assert ops._adjacent(*[w.grad for w in ws]) and ops._adjacent(*[b.grad for b in bs])
+        stacked = ops._stacked(*ws)
+        assert stacked.shape == (2 * 16 + 2 * 16 + 2 * 8, 32) and torch.equal(stacked[:32], ws[0]) and torch.equal(stacked[64:], ws[2])
+    after = m.state_dict()
+    assert list(after) == list(before) and all(torch.equal(after[k], before[k]) for k in before)
+    assert len({id(p) for p in flat.params}) == len(list(m.parameters()))      # every parameter exactly once
+    # separately allocated neighbours must not be stacked (a view cannot span two storages)
+    a, b = torch.zeros(4, 8), torch.zeros(4, 8)
+    assert not ops._adjacent(a, b)
+
+
 def test_cpu_tensors_are_rejected_not_computed():
     m = b200asr.build_model(b200asr.ASRConfig(num_layers=1, vocab=40, feat_extractor="", tgt_max_len=6))
     with pytest.raises(RuntimeError, match="CUDA"):
