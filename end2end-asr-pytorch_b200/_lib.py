@@ -31,7 +31,7 @@ SIGNATURES = {
     "b200asr_split_tf32": (_i, [_vp, _vp, _ll, _vp]),
     "b200asr_linear_bwd_weight": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200asr_add_ln_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _u64, _u64, _vp]),
-    "b200asr_add_ln_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _u64, _u64, _vp]),
+    "b200asr_add_ln_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _u64, _u64, _i, _vp]),
     "b200asr_add_ln_bwd_ws_bytes": (_sz, [_i, _i]),
     "b200asr_sdpa_fwd": (_i, [_vp, _vp, _vp] + [_ll] * 9 + [_vp, _vp, _i, _vp, _ll, _ll, _ll, _vp] + [_i] * 6 +
                          [_f, _f, _u64, _u64, _i, _vp]),

@@ -220,14 +220,17 @@ int b200asr_add_ln_fwd(const float* x, const float* residual, const float* gamma
 
 int b200asr_add_ln_bwd(const float* dy, const float* z, const float* gamma, const float* mean, const float* rstd,
                        const float* row_scale, float* dz, float* dx, float* dgamma, float* dbeta, void* partial_ws,
-                       int rows, int d, float p_drop, uint64_t seed, uint64_t offset, b200asr_stream_t stream) {
+                       int rows, int d, float p_drop, uint64_t seed, uint64_t offset, int accumulate,
+                       b200asr_stream_t stream) {
   B200_REQUIRE(dy && z && gamma && mean && rstd && dgamma && dbeta && partial_ws && (dz || dx), B200ASR_BAD_ARG, "add_ln_bwd: null pointer");
   B200_REQUIRE(d > 0 && d % 4 == 0 && d <= LN_MAXV * 128, B200ASR_BAD_SHAPE, "add_ln_bwd: d=%d unsupported", d);
   B200_REQUIRE(aligned16(dy) && aligned16(z) && aligned16(gamma) && (!dz || aligned16(dz)) && (!dx || aligned16(dx)), B200ASR_BAD_ALIGN, "add_ln_bwd: alignment");
   cudaStream_t st = (cudaStream_t)stream;
   if (rows <= 0) {
-    cudaMemsetAsync(dgamma, 0, sizeof(float) * d, st);
-    cudaMemsetAsync(dbeta, 0, sizeof(float) * d, st);
+    if (!accumulate) {
+      cudaMemsetAsync(dgamma, 0, sizeof(float) * d, st);
+      cudaMemsetAsync(dbeta, 0, sizeof(float) * d, st);
+    }
     return B200ASR_OK;
   }
   uint32_t th = p_drop > 0.f ? dropout_thresh16(p_drop) : 0u;
@@ -239,8 +242,10 @@ int b200asr_add_ln_bwd(const float* dy, const float* z, const float* gamma, cons
 #undef LN_BWD
   int rc = check_launch("add_ln_bwd");
   if (rc) return rc;
-  cudaMemsetAsync(dgamma, 0, sizeof(float) * d, st);
-  cudaMemsetAsync(dbeta, 0, sizeof(float) * d, st);
+  if (!accumulate) {          // the finalize kernel adds its slices atomically: into zeros, or into the existing gradients
+    cudaMemsetAsync(dgamma, 0, sizeof(float) * d, st);
+    cudaMemsetAsync(dbeta, 0, sizeof(float) * d, st);
+  }
   ln_bwd_finalize_kernel<<<dim3(ceil_div(d, 32), LN_FIN_SLICES), 256, 0, st>>>((const float*)partial_ws, nblk, d, dgamma, dbeta);
   return check_launch("ln_bwd_finalize");
 }

@@ -289,6 +289,7 @@ class AddLNFn(torch.autograd.Function):
                                           float(p_drop), seed, off, _stream()), "add_ln_fwd")
         ctx.save_for_backward(z if need_z else x2, gamma, mean, rstd, rs)
         ctx.meta = (x.shape, residual is not None, float(p_drop), seed, off, rows, d)
+        ctx.params = (gamma, beta)
         return y.view(x.shape)
 
     @staticmethod
@@ -299,13 +300,18 @@ class AddLNFn(torch.autograd.Function):
         lib = _lib()
         dz = torch.empty_like(dy2)
         dx = torch.empty_like(dy2) if p_drop > 0.0 else dz
-        dgamma = torch.empty(d, device=dy.device, dtype=torch.float32)
-        dbeta = torch.empty(d, device=dy.device, dtype=torch.float32)
+        # gamma / beta gradients go straight into the parameters' .grad (flat gradient buffer) when that exists: no
+        # zero-fill, no AccumulateGrad add -- four tiny launches less per LayerNorm
+        g_sink, b_sink = _grad_sink(ctx.params[0]), _grad_sink(ctx.params[1])
+        direct = g_sink is not None and b_sink is not None
+        dgamma = g_sink if direct else torch.empty(d, device=dy.device, dtype=torch.float32)
+        dbeta = b_sink if direct else torch.empty(d, device=dy.device, dtype=torch.float32)
         ws = torch.empty(lib.b200asr_add_ln_bwd_ws_bytes(rows, d) // 4, device=dy.device, dtype=torch.float32)
         L.check(lib.b200asr_add_ln_bwd(L.ptr(dy2), L.ptr(z), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), L.ptr(rs), L.ptr(dz),
                                        L.ptr(dx), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), rows, d, p_drop, seed, off,
-                                       _stream()), "add_ln_bwd")
-        return dx.view(xshape), (dz.view(xshape) if has_res else None), dgamma, dbeta, None, None, None, None
+                                       int(direct), _stream()), "add_ln_bwd")
+        return (dx.view(xshape), (dz.view(xshape) if has_res else None), None if direct else dgamma, None if direct else dbeta,
+                None, None, None, None)
 
 
 # ----------------------------------------------------------------------------------------------- attention

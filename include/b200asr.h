@@ -84,11 +84,12 @@ int b200asr_add_ln_fwd(const float* x, const float* residual, const float* gamma
                        float* mean, float* rstd, int rows, int d, float eps, float p_drop, uint64_t seed,
                        uint64_t offset, b200asr_stream_t stream);
 /* dz = grad wrt LN input (== grad wrt residual); dx = grad wrt x (dz through the dropout mask; pass
- * dx == dz when p_drop == 0).  dgamma/dbeta are overwritten.  partial_ws: b200asr_add_ln_bwd_ws_bytes. */
+ * dx == dz when p_drop == 0).  dgamma/dbeta are overwritten, or added to when accumulate != 0 (the host passes the
+ * parameters' existing .grad views of the flat gradient buffer).  partial_ws: b200asr_add_ln_bwd_ws_bytes. */
 int b200asr_add_ln_bwd(const float* dy, const float* z, const float* gamma, const float* mean,
                        const float* rstd, const float* row_scale, float* dz, float* dx, float* dgamma,
                        float* dbeta, void* partial_ws, int rows, int d, float p_drop, uint64_t seed,
-                       uint64_t offset, b200asr_stream_t stream);
+                       uint64_t offset, int accumulate, b200asr_stream_t stream);
 size_t b200asr_add_ln_bwd_ws_bytes(int rows, int d);
 
 /* ------------------------------------------------------------------------------------------------
