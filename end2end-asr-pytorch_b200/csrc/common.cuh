@@ -18,6 +18,10 @@ void set_error(const char* fmt, ...);
 int check_launch(const char* what);   // cudaGetLastError -> error code (+message); counts one kernel launch
 void note_launch(int n);              // additional kernel launches not followed by their own check_launch
 int device_sm_count();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device): function attributes are per device, and the
+// reference's nn.DataParallel drives several devices from one process.  `done` is the caller's per-kernel flag array.
+constexpr int kMaxDevices = 64;
+int ensure_dynamic_smem(const void* kernel, int bytes, bool (&done)[kMaxDevices], const char* what);
 int ensure_sm100();                   // B200ASR_OK iff current device is compute capability 10.x
 
 #define B200_REQUIRE(cond, code, ...)            \

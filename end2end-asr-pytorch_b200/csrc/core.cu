@@ -28,6 +28,16 @@ int check_launch(const char* what) {
   return B200ASR_OK;
 }
 
+int ensure_dynamic_smem(const void* kernel, int bytes, bool (&done)[kMaxDevices], const char* what) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) { set_error("%s: cannot query the current device", what); return B200ASR_CUDA_ERROR; }
+  if (done[dev]) return B200ASR_OK;
+  cudaError_t r = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (r != cudaSuccess) { set_error("%s: cannot reserve %d bytes of shared memory: %s", what, bytes, cudaGetErrorString(r)); return B200ASR_CUDA_ERROR; }
+  done[dev] = true;
+  return B200ASR_OK;
+}
+
 int device_sm_count() {
   static thread_local int cached_dev = -1, cached = 0;
   int dev = 0;

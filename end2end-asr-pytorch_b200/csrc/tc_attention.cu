@@ -241,12 +241,8 @@ static int launch_att(const AttnP& p, cudaStream_t st) {
   rc = make_bhtd_map(&mv, p.v, DV, p.Tk, p.H, p.B, p.v_rs, p.v_hs, p.v_bs, 64, true);
   if (rc) return rc;
   auto* kern = tc_sdpa_fwd_kernel<DK, DV>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t r = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (r != cudaSuccess) { set_error("tc_sdpa_fwd: cannot reserve %d bytes of shared memory: %s", Cfg::kSmemBytes, cudaGetErrorString(r)); return B200ASR_CUDA_ERROR; }
-    attr_set = true;
-  }
+  static bool attr_set[kMaxDevices] = {};
+  if ((rc = ensure_dynamic_smem((const void*)kern, Cfg::kSmemBytes, attr_set, "tc_sdpa_fwd"))) return rc;
   dim3 grid(ceil_div(p.Tq, 128), p.H, p.B);
   kern<<<grid, ATT_THREADS, Cfg::kSmemBytes, st>>>(mq, mk, mv, p);
   return check_launch("tc_sdpa_fwd");

@@ -369,15 +369,9 @@ static int launch_bwd(const AttnP& p, const float* dout, float* dq, float* dk, f
   if ((rc = bhtd_map(&mOm, dout, DV, p.Tq, p.H, p.B, p.o_rs, p.o_hs, p.o_bs, true))) return rc;
   auto* ka = tc_sdpa_bwd_dkdv_kernel<DK, DV>;
   auto* kb = tc_sdpa_bwd_dq_kernel<DK, DV>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kA_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kB_smem) != cudaSuccess) {
-      set_error("tc_sdpa_bwd: cannot reserve %d / %d bytes of shared memory", Cfg::kA_smem, Cfg::kB_smem);
-      return B200ASR_CUDA_ERROR;
-    }
-    attr_set = true;
-  }
+  static bool attr_a[kMaxDevices] = {}, attr_b[kMaxDevices] = {};
+  if ((rc = ensure_dynamic_smem((const void*)ka, Cfg::kA_smem, attr_a, "tc_sdpa_bwd_dkdv"))) return rc;
+  if ((rc = ensure_dynamic_smem((const void*)kb, Cfg::kB_smem, attr_b, "tc_sdpa_bwd_dq"))) return rc;
   ka<<<dim3(ceil_div(p.Tk, 128), p.H, p.B), AB_THREADS, Cfg::kA_smem, st>>>(mQk, mQm, mKk, mV, mOk, mOm, p, delta, dk, dv);
   rc = check_launch("tc_sdpa_bwd_dkdv");
   if (rc) return rc;

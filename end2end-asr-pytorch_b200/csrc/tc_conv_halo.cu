@@ -306,12 +306,8 @@ template <int BN>
 static int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const HaloP& p, cudaStream_t st) {
   using Cfg = HaloCfg<BN>;
   auto* kern = tc_conv3x3_halo_kernel<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t r = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (r != cudaSuccess) { set_error("tc_conv3x3_halo: cannot reserve %d bytes of shared memory: %s", Cfg::kSmemBytes, cudaGetErrorString(r)); return B200ASR_CUDA_ERROR; }
-    attr_set = true;
-  }
+  static bool attr_set[kMaxDevices] = {};
+  if (int rc = ensure_dynamic_smem((const void*)kern, Cfg::kSmemBytes, attr_set, "tc_conv3x3_halo")) return rc;
   const long long tiles = (long long)p.nft * p.ntt * p.B;
   if (tiles <= 0) return B200ASR_OK;
   if (tiles >= (1LL << 31)) { set_error("tc_conv3x3_halo: too many tiles"); return B200ASR_BAD_SHAPE; }

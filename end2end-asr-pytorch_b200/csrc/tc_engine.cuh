@@ -316,12 +316,8 @@ int launch_engine(const CUtensorMap& ma, const CUtensorMap& mb, const typename P
                   const char* what) {
   using Cfg = EngineCfg<Policy, NSPLIT>;
   auto* kern = tc_engine_kernel<Policy, NSPLIT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t r = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-    if (r != cudaSuccess) { set_error("%s: cannot reserve %d bytes of shared memory: %s", what, Cfg::kSmemBytes, cudaGetErrorString(r)); return B200ASR_CUDA_ERROR; }
-    attr_set = true;
-  }
+  static bool attr_set[kMaxDevices] = {};
+  if (int rc = ensure_dynamic_smem((const void*)kern, Cfg::kSmemBytes, attr_set, what)) return rc;
   if (ntiles <= 0) return B200ASR_OK;
   const int grid = min(ntiles, device_sm_count());
   kern<<<grid, NSPLIT == 1 ? ENG_THREADS_X1 : ENG_THREADS_X3, Cfg::kSmemBytes, st>>>(ma, mb, p);
