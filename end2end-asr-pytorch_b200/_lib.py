@@ -43,6 +43,9 @@ SIGNATURES = {
     "b200asr_sdpa_mat_bwd": (_i, [_vp] * 4 + [_ll] * 12 + [_vp] * 6 + [_i] * 6 + [_f, _f, _u64, _u64, _i, _vp]),
     "b200asr_stft_ws_bytes": (_sz, [_i, _i, _i, _i]),
     "b200asr_stft_features": (_i, [_vp] * 5 + [_i] * 8 + [_vp]),
+    "b200asr_im2col": (_i, [_vp, _vp] + [_i] * 11 + [_vp]),
+    "b200asr_col2im": (_i, [_vp, _vp] + [_i] * 11 + [_vp]),
+    "b200asr_transpose_cp": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "b200asr_conv3x3_c1_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200asr_conv3x3_c1_bwd_weight": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "b200asr_conv3x3_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -659,9 +659,69 @@ class PermuteColsFn(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------------------------- emb_cnn front end
+def _conv_geom(x, w, geom):
+    B, Ci, H, W = x.shape
+    KH, KW, SH, SW, PH, PW = geom
+    OH, OW = (H + 2 * PH - KH) // SH + 1, (W + 2 * PW - KW) // SW + 1
+    K = Ci * KH * KW
+    return B, Ci, H, W, w.shape[0], OH, OW, K, (K + 3) // 4 * 4
+
+
+def _im2col(x, geom, Kp):
+    B, Ci, H, W = x.shape
+    KH, KW, SH, SW, PH, PW = geom
+    OH, OW = (H + 2 * PH - KH) // SH + 1, (W + 2 * PW - KW) // SW + 1
+    col = torch.empty((B * OH * OW, Kp), device=x.device, dtype=torch.float32)
+    L.check(_lib().b200asr_im2col(L.ptr(x), L.ptr(col), B, Ci, H, W, KH, KW, SH, SW, PH, PW, Kp, _stream()), "im2col")
+    return col
+
+
+def _padded_weight(w, K, Kp):
+    w2 = _f32c(w).reshape(w.shape[0], K)
+    if Kp == K:
+        return w2
+    wp = torch.zeros((w.shape[0], Kp), device=w.device, dtype=torch.float32)
+    wp[:, :K] = w2
+    return wp
+
+
+def _conv_gemm_fwd(x, w, b, geom, prec):
+    """NCHW convolution as im2col + the tensor-core GEMM of the linear layers (+ bias in its epilogue); returns NCHW."""
+    B, Ci, H, W, Co, OH, OW, K, Kp = _conv_geom(x, w, geom)
+    col = _im2col(x, geom, Kp)
+    wp = _padded_weight(w, K, Kp)
+    y_pc = linear_fwd(col, wp, b, False, prec, split_weight(wp, prec))           # [B*OH*OW, Co]
+    y = torch.empty((B, Co, OH, OW), device=x.device, dtype=torch.float32)
+    L.check(_lib().b200asr_transpose_cp(L.ptr(y_pc), L.ptr(y), B, Co, OH * OW, 0, _stream()), "transpose_cp")
+    return y, col          # the column matrix is kept for the weight gradient (9 GB at cfg3 -- small change on 180 GB)
+
+
+def _conv_gemm_bwd(dy, x, w, col, geom, prec, prec_w, need_dx):
+    """(dx or None, dw, db) of _conv_gemm_fwd: weight gradient = GEMM over the saved im2col matrix (bias gradient fused),
+    data gradient = GEMM into the column space followed by col2im."""
+    B, Ci, H, W, Co, OH, OW, K, Kp = _conv_geom(x, w, geom)
+    lib, st = _lib(), _stream()
+    dy_pc = torch.empty((B * OH * OW, Co), device=x.device, dtype=torch.float32)
+    L.check(lib.b200asr_transpose_cp(L.ptr(_f32c(dy)), L.ptr(dy_pc), B, Co, OH * OW, 1, st), "transpose_cp")
+    dwp, db = linear_bwd_weight(dy_pc, col, True, prec_w)
+    dw = dwp[:, :K].reshape(w.shape).contiguous() if Kp != K else dwp.view(w.shape)
+    dx = None
+    if need_dx:
+        wp = _padded_weight(w, K, Kp)
+        dcol = linear_bwd_data(dy_pc, wp, None, prec, split_weight(wp, prec))
+        dx = torch.empty((B, Ci, H, W), device=x.device, dtype=torch.float32)
+        KH, KW, SH, SW, PH, PW = geom
+        L.check(lib.b200asr_col2im(L.ptr(dcol), L.ptr(dx), B, Ci, H, W, KH, KW, SH, SW, PH, PW, Kp, st), "col2im")
+    return dx, dw, db
+
+
 class EmbFrontendFn(torch.autograd.Function):
     """models/asr/transformer.py:33-40 (+ flatten :74-76): conv(41x11,s2x2,p0x10)+BN+clamp, conv(21x11,s2x1)+BN+clamp.
-    BatchNorm uses batch statistics (training mode); running statistics are not updated by this path."""
+    BatchNorm uses batch statistics (training mode); running statistics are not updated by this path.
+    The convolutions run as im2col + tensor-core GEMM (config.conv / config.conv_wgrad) or, for precision "fp32", as
+    direct CUDA-core kernels."""
+
+    G1, G2 = (41, 11, 2, 2, 0, 10), (21, 11, 2, 1, 0, 0)
 
     @staticmethod
     def forward(ctx, x, w0, b0, g1, be1, w3, b3, g4, be4, eps):
@@ -672,24 +732,34 @@ class EmbFrontendFn(torch.autograd.Function):
         dev = x.device
         new = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
         C = w0.shape[0]
+        gemm = config.conv != L.PREC_FP32 and C % 4 == 0
         H1, W1 = (H - 41) // 2 + 1, (W + 20 - 11) // 2 + 1
-        c1 = new(B, C, H1, W1)
-        L.check(lib.b200asr_conv2d_fwd(L.ptr(x), L.ptr(_f32c(w0)), L.ptr(b0), L.ptr(c1), B, 1, H, W, C, 41, 11, 2, 2, 0, 10, st), "emb_conv1")
+        if gemm:
+            c1, col1 = _conv_gemm_fwd(x, w0, b0, EmbFrontendFn.G1, config.conv)
+        else:
+            c1 = new(B, C, H1, W1)
+            L.check(lib.b200asr_conv2d_fwd(L.ptr(x), L.ptr(_f32c(w0)), L.ptr(b0), L.ptr(c1), B, 1, H, W, C, 41, 11, 2, 2, 0, 10, st), "emb_conv1")
         a1, m1, s1 = new(B, C, H1, W1), new(C), new(C)
         L.check(lib.b200asr_bn_clamp_fwd(L.ptr(c1), L.ptr(g1), L.ptr(be1), L.ptr(a1), L.ptr(m1), L.ptr(s1), B, C, H1 * W1, eps, 0.0, 20.0, st), "emb_bn1")
         H2, W2 = (H1 - 21) // 2 + 1, (W1 - 11) // 1 + 1
-        c2 = new(B, C, H2, W2)
-        L.check(lib.b200asr_conv2d_fwd(L.ptr(a1), L.ptr(_f32c(w3)), L.ptr(b3), L.ptr(c2), B, C, H1, W1, C, 21, 11, 2, 1, 0, 0, st), "emb_conv2")
+        if gemm:
+            c2, col2 = _conv_gemm_fwd(a1, w3, b3, EmbFrontendFn.G2, config.conv)
+        else:
+            c2 = new(B, C, H2, W2)
+            L.check(lib.b200asr_conv2d_fwd(L.ptr(a1), L.ptr(_f32c(w3)), L.ptr(b3), L.ptr(c2), B, C, H1, W1, C, 21, 11, 2, 1, 0, 0, st), "emb_conv2")
         a2, m2, s2 = new(B, C, H2, W2), new(C), new(C)
         L.check(lib.b200asr_bn_clamp_fwd(L.ptr(c2), L.ptr(g4), L.ptr(be4), L.ptr(a2), L.ptr(m2), L.ptr(s2), B, C, H2 * W2, eps, 0.0, 20.0, st), "emb_bn2")
         out = new(B, W2, C * H2)
         L.check(lib.b200asr_flatten_bcft_fwd(L.ptr(a2), L.ptr(out), B, C, H2, W2, st), "emb_flatten")
         ctx.save_for_backward(x, c1, a1, m1, s1, c2, a2, m2, s2, w0, g1, w3, g4)
+        ctx.gemm = (gemm, config.conv, config.conv_wgrad)
+        ctx.cols = (col1, col2) if gemm else None
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, c1, a1, m1, s1, c2, a2, m2, s2, w0, g1, w3, g4 = ctx.saved_tensors
+        gemm, prec, prec_w = ctx.gemm
         lib, st = _lib(), _stream()
         B, _, H, W = x.shape
         C = w0.shape[0]
@@ -702,14 +772,21 @@ class EmbFrontendFn(torch.autograd.Function):
         L.check(lib.b200asr_flatten_bcft_bwd(L.ptr(dout), L.ptr(da2), B, C, H2, W2, st), "emb_flatten_bwd")
         dc2, dg4, dbe4 = new(B, C, H2, W2), new(C), new(C)
         L.check(lib.b200asr_bn_clamp_bwd(L.ptr(da2), L.ptr(c2), L.ptr(a2), L.ptr(g4), L.ptr(m2), L.ptr(s2), L.ptr(dc2), L.ptr(dg4), L.ptr(dbe4), B, C, H2 * W2, 0.0, 20.0, st), "emb_bn2_bwd")
-        dw3, db3 = torch.empty_like(w3), new(C)
-        L.check(lib.b200asr_conv2d_bwd_weight(L.ptr(dc2), L.ptr(a1), L.ptr(dw3), L.ptr(db3), B, C, H1, W1, C, 21, 11, 2, 1, 0, 0, st), "emb_conv2_wgrad")
-        da1 = new(B, C, H1, W1)
-        L.check(lib.b200asr_conv2d_bwd_data(L.ptr(dc2), L.ptr(_f32c(w3)), L.ptr(da1), B, C, H1, W1, C, 21, 11, 2, 1, 0, 0, st), "emb_conv2_dgrad")
+        if gemm:
+            da1, dw3, db3 = _conv_gemm_bwd(dc2, a1, w3, ctx.cols[1], EmbFrontendFn.G2, prec, prec_w, True)
+        else:
+            dw3, db3 = torch.empty_like(w3), new(C)
+            L.check(lib.b200asr_conv2d_bwd_weight(L.ptr(dc2), L.ptr(a1), L.ptr(dw3), L.ptr(db3), B, C, H1, W1, C, 21, 11, 2, 1, 0, 0, st), "emb_conv2_wgrad")
+            da1 = new(B, C, H1, W1)
+            L.check(lib.b200asr_conv2d_bwd_data(L.ptr(dc2), L.ptr(_f32c(w3)), L.ptr(da1), B, C, H1, W1, C, 21, 11, 2, 1, 0, 0, st), "emb_conv2_dgrad")
         dc1, dg1, dbe1 = new(B, C, H1, W1), new(C), new(C)
         L.check(lib.b200asr_bn_clamp_bwd(L.ptr(da1), L.ptr(c1), L.ptr(a1), L.ptr(g1), L.ptr(m1), L.ptr(s1), L.ptr(dc1), L.ptr(dg1), L.ptr(dbe1), B, C, H1 * W1, 0.0, 20.0, st), "emb_bn1_bwd")
-        dw0, db0 = torch.empty_like(w0), new(C)
-        L.check(lib.b200asr_conv2d_bwd_weight(L.ptr(dc1), L.ptr(x), L.ptr(dw0), L.ptr(db0), B, 1, H, W, C, 41, 11, 2, 2, 0, 10, st), "emb_conv1_wgrad")
+        if gemm:
+            _, dw0, db0 = _conv_gemm_bwd(dc1, x, w0, ctx.cols[0], EmbFrontendFn.G1, prec, prec_w, False)
+            ctx.cols = None
+        else:
+            dw0, db0 = torch.empty_like(w0), new(C)
+            L.check(lib.b200asr_conv2d_bwd_weight(L.ptr(dc1), L.ptr(x), L.ptr(dw0), L.ptr(db0), B, 1, H, W, C, 41, 11, 2, 2, 0, 10, st), "emb_conv1_wgrad")
         return None, dw0, db0, dg1, dbe1, dw3, db3, dg4, dbe4, None
 
 
