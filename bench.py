@@ -283,8 +283,12 @@ def run_b200(args, rank, local_rank, world):
     groups = summarize_profile(report, prof_steps, peaks)
     top = next((g for g in groups if g["gflop_per_step"] > 0), groups[0])
     tf32_peak = peaks["bf16_tflops_sustained"] / 2.0       # kind::tf32 runs at half the bf16 rate
+    # DRAM bytes per launch (dram__bytes_read + dram__bytes_write) from the ncu --set full captures of this code under
+    # profiles/ (engine_WgradPolicy_r1b.md, conv_halo_r1.md), averaged over the launches of the group at cfg2
+    ncu_traffic = {"conv3x3_bwd_weight": (1.0891e9 + 0.8074e9 + 2.4947e9) / 3.0}
     roof = {"bound": "tensor", "kernel": top["kernel"], "achieved": top["tflops"], "peak": tf32_peak, "unit": "TFLOP/s",
-            "frac": top["tflops"] / tf32_peak, "traffic": None,
+            "frac": top["tflops"] / tf32_peak, "traffic": ncu_traffic.get(top["kernel"]),
+            "traffic_note": "bytes per launch from profiles/ (ncu); algorithmic x + dy bytes of the three layers average 1.25e9",
             "peak_source": f"{peaks['source']} bf16_tflops_sustained/2 (TF32 = half the bf16 tensor rate)",
             "share_of_step": top["share"],
             # 3xTF32 issues three tf32 MMAs per algorithmic product, so `frac` tops out at 1/3 for precision-3 kernels;
