@@ -21,7 +21,7 @@ class _Config:
 
     Default = the fp32-grade mix, everything on tcgen05 with the 3xTF32 split: GEMMs, convolutions and the attention
     contractions (materialised path: batched GEMMs around exact fp32 softmax kernels, attention_mat.cu).  Measured at
-    the cfg2 architecture against an fp64 oracle (tools/parity_cfg2.py): logits ~1e-5, median gradient error ~1e-4.
+    the cfg2 architecture against an fp64 oracle (tests/parity_cfg2.py): logits ~1e-5, median gradient error ~1e-4.
     Alternatives per family: "fp32" = CUDA-core kernels (exact fp32; attention = the flash-style kernel, which is also
     what shapes outside the tensor-core shape rules run on), "tf32" = single-pass TF32 (convolutions: logits 3e-4 but
     gradients ~6e-3; attention = the single-kernel flash forward/backward with S/P resident in TMEM, gradients ~3e-3
