@@ -135,3 +135,24 @@ print("OK")
 ''' % (REF, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     out = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-2000:]
+
+
+def test_bench_flop_accounting_reads_integer_dimensions_of_the_abi():
+    """bench.algorithmic_flops picks problem sizes out of the raw C-ABI argument tuples by position: every position it reads
+    must be a C int of that entry point's prototype (guards the indices against ABI edits)."""
+    import ctypes
+    import importlib
+    import bench
+    L = importlib.import_module(b200asr.__name__ + "._lib")
+    for name in ("linear_fwd", "linear_bwd_data", "linear_bwd_weight", "conv3x3_fwd", "conv3x3_bwd_data", "conv3x3_bwd_weight",
+                 "conv3x3_c1_fwd", "conv3x3_c1_bwd_weight", "sdpa_fwd", "sdpa_bwd", "sdpa_mat_fwd", "sdpa_mat_bwd"):
+        argtypes = L.SIGNATURES["b200asr_" + name][1]
+
+        class Probe(tuple):
+            def __getitem__(self, i):
+                idx = range(len(self))[i] if isinstance(i, slice) else [i]
+                for j in idx:
+                    assert argtypes[j] is ctypes.c_int, (name, j, argtypes[j])
+                return [3] * len(idx) if isinstance(i, slice) else 3
+
+        assert bench.algorithmic_flops(name, Probe(range(len(argtypes)))) > 0
