@@ -57,8 +57,8 @@ SIGNATURES = {
     "b200asr_conv2d_fwd": (_i, [_vp, _vp, _vp, _vp] + [_i] * 11 + [_vp]),
     "b200asr_conv2d_bwd_data": (_i, [_vp, _vp, _vp] + [_i] * 11 + [_vp]),
     "b200asr_conv2d_bwd_weight": (_i, [_vp, _vp, _vp, _vp] + [_i] * 11 + [_vp]),
-    "b200asr_bn_clamp_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _vp]),
-    "b200asr_bn_clamp_bwd": (_i, [_vp] * 9 + [_i, _i, _i, _f, _f, _vp]),
+    "b200asr_bn_clamp_fwd": (_i, [_vp] * 9 + [_i, _i, _i, _f, _f, _i, _f, _f, _vp]),
+    "b200asr_bn_clamp_bwd": (_i, [_vp] * 9 + [_i, _i, _i, _i, _f, _f, _vp]),
     "b200asr_flatten_bcft_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "b200asr_flatten_bcft_bwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "b200asr_preprocess_targets": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
@@ -66,6 +66,7 @@ SIGNATURES = {
     "b200asr_embed_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _u64, _u64, _i, _vp]),
     "b200asr_length_masks": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "b200asr_argmax_rows": (_i, [_vp, _vp, _i, _i, _vp]),
+    "b200asr_greedy_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "b200asr_ce_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "b200asr_ce_finalize": (_i, [_vp, _vp, _i, _vp]),
     "b200asr_ce_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp, _vp]),

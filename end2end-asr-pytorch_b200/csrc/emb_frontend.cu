@@ -125,20 +125,38 @@ __device__ __forceinline__ float block_sum256(float v, float* red) {
   return t;
 }
 
+// BatchNorm2d + Hardtanh (models/asr/transformer.py:34-35,38-39).  training != 0: batch statistics (biased variance for the
+// normalisation, as ATen), and -- when the running buffers are given -- the nn.BatchNorm2d state update
+//   running_mean <- (1-m) running_mean + m mean,   running_var <- (1-m) running_var + m var * n/(n-1),   num_batches_tracked += 1.
+// training == 0 (model.eval(), the reference's validation loop trainer.py:123): normalise with the running statistics.
 __global__ void __launch_bounds__(256) bn_clamp_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float* __restrict__ y,
-                                                           float* __restrict__ mean_out, float* __restrict__ invstd_out, int B,
-                                                           int C, int HW, float eps, float lo, float hi) {
+                                                           float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                                           float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                           long long* __restrict__ num_batches, int B, int C, int HW, float eps,
+                                                           float momentum, int training, float lo, float hi) {
   __shared__ float red[8];
   const int c = blockIdx.x;
   const long long n = (long long)B * HW;
-  float s = 0.f;
-  for (long long j = threadIdx.x; j < n; j += 256) s += x[((size_t)(j / HW) * C + c) * HW + (j % HW)];
-  const float mean = block_sum256(s, red) / (float)n;
-  float q = 0.f;
-  for (long long j = threadIdx.x; j < n; j += 256) { float d = x[((size_t)(j / HW) * C + c) * HW + (j % HW)] - mean; q += d * d; }
-  const float var = block_sum256(q, red) / (float)n;
-  const float invstd = rsqrtf(var + eps);
+  float mean, invstd;
+  if (training) {
+    float s = 0.f;
+    for (long long j = threadIdx.x; j < n; j += 256) s += x[((size_t)(j / HW) * C + c) * HW + (j % HW)];
+    mean = block_sum256(s, red) / (float)n;
+    float q = 0.f;
+    for (long long j = threadIdx.x; j < n; j += 256) { float d = x[((size_t)(j / HW) * C + c) * HW + (j % HW)] - mean; q += d * d; }
+    const float var = block_sum256(q, red) / (float)n;
+    invstd = rsqrtf(var + eps);
+    if (threadIdx.x == 0 && running_mean && running_var) {
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      const float unbiased = n > 1 ? var * ((float)n / (float)(n - 1)) : var;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+      if (c == 0 && num_batches) *num_batches += 1;
+    }
+  } else {
+    mean = running_mean[c];
+    invstd = rsqrtf(running_var[c] + eps);
+  }
   if (threadIdx.x == 0) { mean_out[c] = mean; invstd_out[c] = invstd; }
   const float ga = gamma[c], be = beta[c];
   for (long long j = threadIdx.x; j < n; j += 256) {
@@ -152,7 +170,7 @@ __global__ void __launch_bounds__(256) bn_clamp_bwd_kernel(const float* __restri
                                                            const float* __restrict__ y, const float* __restrict__ gamma,
                                                            const float* __restrict__ mean_in, const float* __restrict__ invstd_in,
                                                            float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                           int B, int C, int HW, float lo, float hi) {
+                                                           int B, int C, int HW, int training, float lo, float hi) {
   __shared__ float red[8];
   const int c = blockIdx.x;
   const long long n = (long long)B * HW;
@@ -168,7 +186,7 @@ __global__ void __launch_bounds__(256) bn_clamp_bwd_kernel(const float* __restri
   s1 = block_sum256(s1, red);
   s2 = block_sum256(s2, red);
   if (threadIdx.x == 0) { dbeta[c] = s1; dgamma[c] = s2; }
-  const float inv_n = 1.f / (float)n;
+  const float inv_n = training ? 1.f / (float)n : 0.f;      // eval mode: the statistics are constants of the graph
   for (long long j = threadIdx.x; j < n; j += 256) {
     size_t o = ((size_t)(j / HW) * C + c) * HW + (j % HW);
     float yv = y[o];
@@ -342,18 +360,21 @@ int b200asr_transpose_cp(const float* src, float* dst, int B, int C, int P, int 
   return check_launch("transpose_cp");
 }
 
-int b200asr_bn_clamp_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* invstd, int B,
-                         int C, int HW, float eps, float lo, float hi, b200asr_stream_t stream) {
+int b200asr_bn_clamp_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* invstd,
+                         float* running_mean, float* running_var, long long* num_batches_tracked, int B, int C, int HW, float eps,
+                         float momentum, int training, float lo, float hi, b200asr_stream_t stream) {
   B200_REQUIRE(x && gamma && beta && y && mean && invstd && B > 0 && C > 0 && HW > 0, B200ASR_BAD_ARG, "bn_clamp_fwd: bad arguments");
-  bn_clamp_fwd_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, y, mean, invstd, B, C, HW, eps, lo, hi);
+  B200_REQUIRE(training || (running_mean && running_var), B200ASR_BAD_ARG, "bn_clamp_fwd: eval mode needs the running statistics");
+  bn_clamp_fwd_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, y, mean, invstd, running_mean, running_var,
+                                                           num_batches_tracked, B, C, HW, eps, momentum, training, lo, hi);
   return check_launch("bn_clamp_fwd");
 }
 
 int b200asr_bn_clamp_bwd(const float* dy, const float* x, const float* y, const float* gamma, const float* mean,
-                         const float* invstd, float* dx, float* dgamma, float* dbeta, int B, int C, int HW, float lo, float hi,
-                         b200asr_stream_t stream) {
+                         const float* invstd, float* dx, float* dgamma, float* dbeta, int B, int C, int HW, int training, float lo,
+                         float hi, b200asr_stream_t stream) {
   B200_REQUIRE(dy && x && y && gamma && mean && invstd && dx && dgamma && dbeta, B200ASR_BAD_ARG, "bn_clamp_bwd: null pointer");
-  bn_clamp_bwd_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(dy, x, y, gamma, mean, invstd, dx, dgamma, dbeta, B, C, HW, lo, hi);
+  bn_clamp_bwd_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(dy, x, y, gamma, mean, invstd, dx, dgamma, dbeta, B, C, HW, training, lo, hi);
   return check_launch("bn_clamp_bwd");
 }
 

@@ -115,6 +115,32 @@ __global__ void argmax_rows_kernel(const float* __restrict__ x, int64_t* __restr
   if (lane == 0) out[row] = bi;
 }
 
+// One greedy-decoding step (models/asr/transformer.py:375-382 + the EOS cut of :385-393) on the device: argmax of every
+// utterance's last-position logits (first max, as torch.max), next input token, the emitted id (-1 once the utterance has
+// produced EOS: the reference drops everything from the first EOS on when it builds the strings) and the EOS bookkeeping
+// that lets the host stop the loop without reading the ids back (finished[b], *n_finished).
+__global__ void greedy_step_kernel(const float* __restrict__ logits, int64_t* __restrict__ next_tok, int64_t* __restrict__ ys,
+                                   int* __restrict__ finished, int* __restrict__ n_finished, int B, int V, int t, int steps) {
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const float* r = logits + (size_t)row * V;
+  float bv = -INFINITY; int bi = 0x7fffffff;
+  for (int c = lane; c < V; c += 32) { float v = r[c]; if (v > bv) { bv = v; bi = c; } }
+  if (bi == 0x7fffffff) bi = lane < V ? lane : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    argmax_combine(bv, bi, ov, oi);
+  }
+  if (lane == 0) {
+    next_tok[row] = bi;
+    const int fin = finished[row];
+    ys[(size_t)row * steps + t] = (fin || bi == TOK_EOS) ? -1 : bi;
+    if (!fin && bi == TOK_EOS) { finished[row] = 1; atomicAdd(n_finished, 1); }
+  }
+}
+
 constexpr int CE_THREADS = 256;
 
 __global__ void __launch_bounds__(CE_THREADS) ce_fwd_kernel(const float* __restrict__ logits,
@@ -298,6 +324,14 @@ int b200asr_embed_bwd(const int64_t* tokens, const float* dout, float* dtable, i
                                                                         p_drop > 0.f ? dropout_thresh16(p_drop) : 0u,
                                                                         dropout_inv_keep(p_drop), dropout_key(seed, offset), pad_idx);
   return check_launch("embed_bwd");
+}
+
+int b200asr_greedy_step(const float* logits, int64_t* next_tok, int64_t* ys, int* finished, int* n_finished, int B, int V, int t,
+                        int steps, b200asr_stream_t stream) {
+  B200_REQUIRE(logits && next_tok && ys && finished && n_finished && B > 0 && V > 0 && t >= 0 && t < steps, B200ASR_BAD_ARG,
+               "greedy_step: bad arguments");
+  greedy_step_kernel<<<ceil_div(B * 32, 128), 128, 0, (cudaStream_t)stream>>>(logits, next_tok, ys, finished, n_finished, B, V, t, steps);
+  return check_launch("greedy_step");
 }
 
 int b200asr_argmax_rows(const float* logits, int64_t* out, int rows, int V, b200asr_stream_t stream) {

@@ -189,11 +189,16 @@ def greedy_decode_ids(self, encoder_padded_outputs, steps=300):
     return ys[:, 1:]
 
 
-def greedy_decode_cached(self, encoder_padded_outputs, steps=300):
+def greedy_decode_cached(self, encoder_padded_outputs, steps=300, stop_at_eos=False, check_every=8):
     """Incremental greedy decode with self- and cross-attention K/V caches: the same token ids as
     greedy_decode_ids / the reference's greedy_search, at O(T) instead of O(T^2) work -- per step only the new position is
     projected, its K/V rows are appended to per-layer caches, and single-query attention runs over the cache (self) and
-    over the once-projected encoder K/V (cross, no mask as in transformer.py:347)."""
+    over the once-projected encoder K/V (cross, no mask as in transformer.py:347).
+
+    stop_at_eos: the EOS cut of transformer.py:385-393 stays on the device -- ids from an utterance's first EOS on are -1
+    (the reference drops them when it builds the strings), a device counter tracks finished utterances and the loop ends
+    as soon as every utterance has emitted EOS (checked every `check_every` steps: one 4-byte read, no id traffic)
+    instead of always running the reference's 300 fixed steps."""
     B, Te, _ = encoder_padded_outputs.shape
     dev = encoder_padded_outputs.device
     was_training = self.training
@@ -210,8 +215,9 @@ def greedy_decode_cached(self, encoder_padded_outputs, steps=300):
                 cross.append((k, v))
                 kc.append(torch.empty((B, steps, H * dk), device=dev, dtype=torch.float32))
                 vc.append(torch.empty((B, steps, H * dv), device=dev, dtype=torch.float32))
-            ys = torch.empty((B, steps), dtype=torch.long, device=dev)
+            ys = torch.full((B, steps), -1, dtype=torch.long, device=dev) if stop_at_eos else torch.empty((B, steps), dtype=torch.long, device=dev)
             tok = torch.full((B, 1), SOS_TOKEN, dtype=torch.long, device=dev)
+            finished = torch.zeros(B + 1, dtype=torch.int32, device=dev) if stop_at_eos else None      # [B] flags + [1] counter
 
             def attend(mod, x, k4, v4):
                 q = ops.LinearFn.apply(x, mod.query_linear.weight, mod.query_linear.bias).view(B, 1, H, dk).permute(0, 2, 1, 3)
@@ -232,8 +238,13 @@ def greedy_decode_cached(self, encoder_padded_outputs, steps=300):
                     x = attend(layer.encoder_attn, x, cross[li][0], cross[li][1])
                     x = _ffn_core(layer.pos_ffn, x)
                 logits = ops.LinearFn.apply(x.view(B, -1), self.output_linear.weight, None)
-                tok = ops.argmax_rows(logits).view(B, 1)
-                ys[:, t:t + 1] = tok
+                if stop_at_eos:
+                    tok = ops.greedy_step(logits, ys, finished, t)
+                    if (t + 1) % check_every == 0 and int(finished[B].item()) == B:
+                        break
+                else:
+                    tok = ops.argmax_rows(logits).view(B, 1)
+                    ys[:, t:t + 1] = tok
     finally:
         self.train(was_training)
     return ys
@@ -250,8 +261,15 @@ def _front_end(self, padded_input):
         return h.view(B, T4, F4 * C), (C, F4)
     if self.feat_extractor == "emb_cnn":
         c = self.conv
+        # nn.BatchNorm2d state (running_mean, running_var, num_batches_tracked, momentum): updated by the kernel in training
+        # mode, used for the normalisation in eval mode -- exactly what the stock module does (transformer.py:34,38)
+        def bn_state(m):
+            if not m.track_running_stats or m.running_mean is None:
+                return None
+            return (m.running_mean, m.running_var, m.num_batches_tracked, m.momentum)
+        training = self.training or bn_state(c[1]) is None or bn_state(c[4]) is None
         h = ops.EmbFrontendFn.apply(padded_input, c[0].weight, c[0].bias, c[1].weight, c[1].bias, c[3].weight, c[3].bias,
-                                    c[4].weight, c[4].bias, float(c[1].eps))
+                                    c[4].weight, c[4].bias, float(c[1].eps), training, bn_state(c[1]), bn_state(c[4]))
         return h, None
     return ops.FlattenFn.apply(padded_input), None
 

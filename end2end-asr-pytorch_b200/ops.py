@@ -717,15 +717,28 @@ def _conv_gemm_bwd(dy, x, w, col, geom, prec, prec_w, need_dx):
 
 class EmbFrontendFn(torch.autograd.Function):
     """models/asr/transformer.py:33-40 (+ flatten :74-76): conv(41x11,s2x2,p0x10)+BN+clamp, conv(21x11,s2x1)+BN+clamp.
-    BatchNorm uses batch statistics (training mode); running statistics are not updated by this path.
+    BatchNorm2d semantics of torch: `training` -> batch statistics, and the module's running_mean / running_var /
+    num_batches_tracked buffers (bn1, bn2 = (running_mean, running_var, num_batches_tracked, momentum) or None) are
+    updated in the kernel; eval -> the running statistics normalise (the reference validates with model.eval(),
+    trainer.py:123, and Transformer.evaluate reads the same buffers through the stock nn.BatchNorm2d).
     The convolutions run as im2col + tensor-core GEMM (config.conv / config.conv_wgrad) or, for precision "fp32", as
     direct CUDA-core kernels."""
 
     G1, G2 = (41, 11, 2, 2, 0, 10), (21, 11, 2, 1, 0, 0)
 
     @staticmethod
-    def forward(ctx, x, w0, b0, g1, be1, w3, b3, g4, be4, eps):
+    def forward(ctx, x, w0, b0, g1, be1, w3, b3, g4, be4, eps, training=True, bn1=None, bn2=None):
         _need_cuda(x, w0)
+        if not training and (bn1 is None or bn2 is None):
+            raise RuntimeError("emb_cnn front end in eval mode needs the BatchNorm running statistics")
+
+        def bn_args(bn):
+            if bn is None:
+                return None, None, None, 0.1
+            rm, rv, nbt, mom = bn
+            if mom is None:
+                raise RuntimeError("BatchNorm2d(momentum=None) (cumulative average) is not used by the reference and not implemented")
+            return rm, rv, nbt, float(mom)
         lib, st = _lib(), _stream()
         x = _f32c(x)
         B, _, H, W = x.shape
@@ -740,7 +753,9 @@ class EmbFrontendFn(torch.autograd.Function):
             c1 = new(B, C, H1, W1)
             L.check(lib.b200asr_conv2d_fwd(L.ptr(x), L.ptr(_f32c(w0)), L.ptr(b0), L.ptr(c1), B, 1, H, W, C, 41, 11, 2, 2, 0, 10, st), "emb_conv1")
         a1, m1, s1 = new(B, C, H1, W1), new(C), new(C)
-        L.check(lib.b200asr_bn_clamp_fwd(L.ptr(c1), L.ptr(g1), L.ptr(be1), L.ptr(a1), L.ptr(m1), L.ptr(s1), B, C, H1 * W1, eps, 0.0, 20.0, st), "emb_bn1")
+        rm, rv, nbt, mom = bn_args(bn1)
+        L.check(lib.b200asr_bn_clamp_fwd(L.ptr(c1), L.ptr(g1), L.ptr(be1), L.ptr(a1), L.ptr(m1), L.ptr(s1), L.ptr(rm), L.ptr(rv),
+                                         L.ptr(nbt), B, C, H1 * W1, eps, mom, int(training), 0.0, 20.0, st), "emb_bn1")
         H2, W2 = (H1 - 21) // 2 + 1, (W1 - 11) // 1 + 1
         if gemm:
             c2, col2 = _conv_gemm_fwd(a1, w3, b3, EmbFrontendFn.G2, config.conv)
@@ -748,11 +763,14 @@ class EmbFrontendFn(torch.autograd.Function):
             c2 = new(B, C, H2, W2)
             L.check(lib.b200asr_conv2d_fwd(L.ptr(a1), L.ptr(_f32c(w3)), L.ptr(b3), L.ptr(c2), B, C, H1, W1, C, 21, 11, 2, 1, 0, 0, st), "emb_conv2")
         a2, m2, s2 = new(B, C, H2, W2), new(C), new(C)
-        L.check(lib.b200asr_bn_clamp_fwd(L.ptr(c2), L.ptr(g4), L.ptr(be4), L.ptr(a2), L.ptr(m2), L.ptr(s2), B, C, H2 * W2, eps, 0.0, 20.0, st), "emb_bn2")
+        rm, rv, nbt, mom = bn_args(bn2)
+        L.check(lib.b200asr_bn_clamp_fwd(L.ptr(c2), L.ptr(g4), L.ptr(be4), L.ptr(a2), L.ptr(m2), L.ptr(s2), L.ptr(rm), L.ptr(rv),
+                                         L.ptr(nbt), B, C, H2 * W2, eps, mom, int(training), 0.0, 20.0, st), "emb_bn2")
         out = new(B, W2, C * H2)
         L.check(lib.b200asr_flatten_bcft_fwd(L.ptr(a2), L.ptr(out), B, C, H2, W2, st), "emb_flatten")
         ctx.save_for_backward(x, c1, a1, m1, s1, c2, a2, m2, s2, w0, g1, w3, g4)
         ctx.gemm = (gemm, config.conv, config.conv_wgrad)
+        ctx.training = bool(training)
         ctx.cols = (col1, col2) if gemm else None
         return out
 
@@ -771,7 +789,7 @@ class EmbFrontendFn(torch.autograd.Function):
         da2 = new(B, C, H2, W2)
         L.check(lib.b200asr_flatten_bcft_bwd(L.ptr(dout), L.ptr(da2), B, C, H2, W2, st), "emb_flatten_bwd")
         dc2, dg4, dbe4 = new(B, C, H2, W2), new(C), new(C)
-        L.check(lib.b200asr_bn_clamp_bwd(L.ptr(da2), L.ptr(c2), L.ptr(a2), L.ptr(g4), L.ptr(m2), L.ptr(s2), L.ptr(dc2), L.ptr(dg4), L.ptr(dbe4), B, C, H2 * W2, 0.0, 20.0, st), "emb_bn2_bwd")
+        L.check(lib.b200asr_bn_clamp_bwd(L.ptr(da2), L.ptr(c2), L.ptr(a2), L.ptr(g4), L.ptr(m2), L.ptr(s2), L.ptr(dc2), L.ptr(dg4), L.ptr(dbe4), B, C, H2 * W2, int(ctx.training), 0.0, 20.0, st), "emb_bn2_bwd")
         if gemm:
             da1, dw3, db3 = _conv_gemm_bwd(dc2, a1, w3, ctx.cols[1], EmbFrontendFn.G2, prec, prec_w, True)
         else:
@@ -780,14 +798,14 @@ class EmbFrontendFn(torch.autograd.Function):
             da1 = new(B, C, H1, W1)
             L.check(lib.b200asr_conv2d_bwd_data(L.ptr(dc2), L.ptr(_f32c(w3)), L.ptr(da1), B, C, H1, W1, C, 21, 11, 2, 1, 0, 0, st), "emb_conv2_dgrad")
         dc1, dg1, dbe1 = new(B, C, H1, W1), new(C), new(C)
-        L.check(lib.b200asr_bn_clamp_bwd(L.ptr(da1), L.ptr(c1), L.ptr(a1), L.ptr(g1), L.ptr(m1), L.ptr(s1), L.ptr(dc1), L.ptr(dg1), L.ptr(dbe1), B, C, H1 * W1, 0.0, 20.0, st), "emb_bn1_bwd")
+        L.check(lib.b200asr_bn_clamp_bwd(L.ptr(da1), L.ptr(c1), L.ptr(a1), L.ptr(g1), L.ptr(m1), L.ptr(s1), L.ptr(dc1), L.ptr(dg1), L.ptr(dbe1), B, C, H1 * W1, int(ctx.training), 0.0, 20.0, st), "emb_bn1_bwd")
         if gemm:
             _, dw0, db0 = _conv_gemm_bwd(dc1, x, w0, ctx.cols[0], EmbFrontendFn.G1, prec, prec_w, False)
             ctx.cols = None
         else:
             dw0, db0 = torch.empty_like(w0), new(C)
             L.check(lib.b200asr_conv2d_bwd_weight(L.ptr(dc1), L.ptr(x), L.ptr(dw0), L.ptr(db0), B, 1, H, W, C, 41, 11, 2, 2, 0, 10, st), "emb_conv1_wgrad")
-        return None, dw0, db0, dg1, dbe1, dw3, db3, dg4, dbe4, None
+        return None, dw0, db0, dg1, dbe1, dw3, db3, dg4, dbe4, None, None, None, None
 
 
 class FlattenFn(torch.autograd.Function):
@@ -877,6 +895,18 @@ def argmax_rows(logits: torch.Tensor) -> torch.Tensor:
     out = torch.empty(x.shape[0], device=x.device, dtype=torch.long)
     L.check(_lib().b200asr_argmax_rows(L.ptr(x), L.ptr(out), x.shape[0], V, _stream()), "argmax_rows")
     return out.view(logits.shape[:-1])
+
+
+def greedy_step(logits: torch.Tensor, ys: torch.Tensor, finished: torch.Tensor, t: int) -> torch.Tensor:
+    """One step of greedy decoding on the device (include/b200asr.h b200asr_greedy_step): returns the next input tokens
+    [B,1]; writes ys[:, t] (-1 from the first EOS on) and updates finished[:B] / the finished-utterance counter finished[B]."""
+    _need_cuda(logits, ys, finished)
+    B, V = logits.shape
+    x = _f32c(logits.detach())
+    tok = torch.empty((B, 1), device=x.device, dtype=torch.long)
+    L.check(_lib().b200asr_greedy_step(L.ptr(x), L.ptr(tok), L.ptr(ys), L.ptr(finished), finished.data_ptr() + 4 * B, B, V, int(t),
+                                       ys.shape[1], _stream()), "greedy_step")
+    return tok
 
 
 class CrossEntropyFn(torch.autograd.Function):

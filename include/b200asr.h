@@ -171,7 +171,7 @@ int b200asr_maxpool2x2_bwd(const float* dy, const float* x, float* dx, int B, in
 
 /* ------------------------------------------------------------------------------------------------
  * emb_cnn front end (models/asr/transformer.py:33-40): generic strided NCHW convolution, BatchNorm2d
- * with batch statistics (training mode) fused with Hardtanh(lo,hi), and the (B,C,F,T)->(B,T,C*F)
+ * (train: batch statistics + running-state update; eval: running statistics) fused with Hardtanh(lo,hi), and the (B,C,F,T)->(B,T,C*F)
  * flatten of :74-76.
  */
 int b200asr_conv2d_fwd(const float* x, const float* w, const float* bias, float* y, int B, int Ci, int H,
@@ -181,13 +181,17 @@ int b200asr_conv2d_bwd_data(const float* dy, const float* w, float* dx, int B, i
 int b200asr_conv2d_bwd_weight(const float* dy, const float* x, float* dw, float* dbias, int B, int Ci, int H,
                               int W, int Co, int KH, int KW, int SH, int SW, int PH, int PW,
                               b200asr_stream_t stream);
-/* y = clamp(BN(x), lo, hi); x,y [B,C,HW]; mean/invstd [C] are outputs (biased variance, as ATen) */
+/* y = clamp(BN(x), lo, hi); x,y [B,C,HW]; mean/invstd [C] are outputs (the statistics used: saved for backward).
+ * training != 0: batch statistics (biased variance, as ATen) and, if the buffers are given, the nn.BatchNorm2d state
+ * update running_mean/var <- (1-momentum) old + momentum new (unbiased variance), num_batches_tracked (int64) += 1.
+ * training == 0 (model.eval(), trainer.py:123): normalise with running_mean / running_var. */
 int b200asr_bn_clamp_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean,
-                         float* invstd, int B, int C, int HW, float eps, float lo, float hi,
+                         float* invstd, float* running_mean, float* running_var, long long* num_batches_tracked,
+                         int B, int C, int HW, float eps, float momentum, int training, float lo, float hi,
                          b200asr_stream_t stream);
 int b200asr_bn_clamp_bwd(const float* dy, const float* x, const float* y, const float* gamma,
                          const float* mean, const float* invstd, float* dx, float* dgamma, float* dbeta,
-                         int B, int C, int HW, float lo, float hi, b200asr_stream_t stream);
+                         int B, int C, int HW, int training, float lo, float hi, b200asr_stream_t stream);
 /* x [B,C,F,T] -> y [B,T,C*F] and its inverse (gradient) */
 int b200asr_flatten_bcft_fwd(const float* x, float* y, int B, int C, int F, int T, b200asr_stream_t stream);
 int b200asr_flatten_bcft_bwd(const float* dy, float* dx, int B, int C, int F, int T, b200asr_stream_t stream);
@@ -223,6 +227,12 @@ int b200asr_length_masks(const int32_t* lengths, uint8_t* key_pad, float* non_pa
  * [2] = number of correct argmax among them.  stats[0..2] are overwritten.  row_lse is [rows].
  */
 int b200asr_argmax_rows(const float* logits, int64_t* out, int rows, int V, b200asr_stream_t stream);
+/* One step of Decoder.greedy_search (models/asr/transformer.py:375-382) with the EOS cut of :385-393 kept on the device:
+ * next_tok[b] = argmax(logits[b,:]) (first max); ys[b*steps+t] = that id, or -1 from the utterance's first EOS on;
+ * finished[b] / *n_finished (int32, zero-initialised by the caller) record which utterances have emitted EOS so the host
+ * loop can stop early (on-device EOS stop). */
+int b200asr_greedy_step(const float* logits, int64_t* next_tok, int64_t* ys, int* finished, int* n_finished, int B, int V,
+                        int t, int steps, b200asr_stream_t stream);
 int b200asr_ce_fwd(const float* logits, const int64_t* gold, float* row_lse, float* stats, int rows, int V,
                    float smoothing, b200asr_stream_t stream);
 /* stats[3] = stats[0] / stats[1] (the reference's mean loss), stats[4] = 1 / stats[1];

@@ -82,15 +82,33 @@ def vgg_frontend(spec: torch.Tensor, P: Dict[str, torch.Tensor]) -> torch.Tensor
     return F.max_pool2d(h, 2, 2)
 
 
-def emb_frontend(spec: torch.Tensor, P: Dict[str, torch.Tensor], eps: float = 1e-5) -> torch.Tensor:
-    """models/asr/transformer.py:33-40 -- strided conv + BatchNorm (batch statistics,
-    training mode) + Hardtanh(0, 20), twice.  Running statistics are not modelled."""
+def emb_frontend(spec: torch.Tensor, P: Dict[str, torch.Tensor], eps: float = 1e-5, training: bool = True,
+                 state: Optional[Dict[str, torch.Tensor]] = None, momentum: float = 0.1) -> torch.Tensor:
+    """models/asr/transformer.py:33-40 -- strided conv + BatchNorm2d + Hardtanh(0, 20), twice.
+    nn.BatchNorm2d semantics: training -> batch statistics, and `state` (conv.{1,4}.running_mean / running_var /
+    num_batches_tracked, the module's buffers) is updated in place with momentum 0.1 and the unbiased variance;
+    eval -> `state` normalises (the reference validates with model.eval(), trainer/asr/trainer.py:123)."""
+    def bn(h, i):
+        rm = state[f"conv.{i}.running_mean"] if state is not None else None
+        rv = state[f"conv.{i}.running_var"] if state is not None else None
+        if training and state is not None:
+            state[f"conv.{i}.num_batches_tracked"] += 1
+        return F.batch_norm(h, rm, rv, P[f"conv.{i}.weight"], P[f"conv.{i}.bias"], training=training, momentum=momentum, eps=eps)
+
     h = F.conv2d(spec, P["conv.0.weight"], P["conv.0.bias"], stride=(2, 2), padding=(0, 10))
-    h = F.batch_norm(h, None, None, P["conv.1.weight"], P["conv.1.bias"], training=True, eps=eps)
-    h = torch.clamp(h, 0.0, 20.0)
+    h = torch.clamp(bn(h, 1), 0.0, 20.0)
     h = F.conv2d(h, P["conv.3.weight"], P["conv.3.bias"], stride=(2, 1))
-    h = F.batch_norm(h, None, None, P["conv.4.weight"], P["conv.4.bias"], training=True, eps=eps)
-    return torch.clamp(h, 0.0, 20.0)
+    return torch.clamp(bn(h, 4), 0.0, 20.0)
+
+
+def bn_initial_state(dtype=torch.float32) -> Dict[str, torch.Tensor]:
+    """Fresh nn.BatchNorm2d(32) buffers of the emb_cnn front end (running_mean 0, running_var 1, num_batches_tracked 0)."""
+    st = {}
+    for i in (1, 4):
+        st[f"conv.{i}.running_mean"] = torch.zeros(32, dtype=dtype)
+        st[f"conv.{i}.running_var"] = torch.ones(32, dtype=dtype)
+        st[f"conv.{i}.num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+    return st
 
 
 def flatten_features(h: torch.Tensor) -> torch.Tensor:
@@ -214,12 +232,12 @@ def decoder_forward(padded_target, enc_out, enc_lengths, P, cfg: OracleConfig):
     return logits, seq_out
 
 
-def transformer_forward(P, cfg: OracleConfig, spec, lengths, padded_target):
-    """models/asr/transformer.py:59-85 -> (pred, gold, hyp_seq)."""
+def transformer_forward(P, cfg: OracleConfig, spec, lengths, padded_target, training: bool = True, bn_state=None):
+    """models/asr/transformer.py:59-85 -> (pred, gold, hyp_seq).  training / bn_state: BatchNorm mode of the emb_cnn front end."""
     if cfg.feat_extractor == "vgg_cnn":
         h = flatten_features(vgg_frontend(spec, P))
     elif cfg.feat_extractor == "emb_cnn":
-        h = flatten_features(emb_frontend(spec, P))
+        h = flatten_features(emb_frontend(spec, P, training=training, state=bn_state))
     else:
         h = flatten_features(spec)
     enc = encoder_forward(h, lengths, P, cfg)

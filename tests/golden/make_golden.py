@@ -107,9 +107,50 @@ def run_case(name):
           "%.1f KB" % (os.path.getsize(path) / 1024))
 
 
+def run_greedy():
+    """Fixture `greedy`: token ids of the reference's Decoder.greedy_search (models/asr/transformer.py:316-394) -- 300 fixed
+    steps of full-prefix re-decode, strings cut at the first EOS (:385-393).  Shims (none edit the
+    reference): get_subsequent_mask(...).bool() (the uint8 mask no longer adds to a bool one on torch >= 1.2) and
+    --tgt-max-len 301 (the positional table must cover 300 positions).  Every id >= 3 maps to its own character, so
+    the returned strings map back to ids.  The EOS row of output_linear is scaled so that utterances end at different,
+    non-trivial steps (a random-init model would otherwise hardly ever emit EOS)."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import ref_shim
+    V, B, Te = 40, 4, 23
+    ns = ref_shim.load(["--num-layers", "2", "--num-heads", "2", "--dim-model", "64", "--dim-emb", "64", "--dim-key", "32",
+                        "--dim-value", "32", "--dim-inner", "128", "--feat_extractor", "", "--tgt-max-len", "301",
+                        "--dropout", "0.0"], q12_shim=True)
+    import torch
+    l2i, i2l = ref_shim.labels(V)
+    torch.manual_seed(123456)
+    model = ns.functions.init_transformer_model(ns.constant.args, l2i, i2l)
+    model.eval()
+    g = torch.Generator().manual_seed(11)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+        model.decoder.output_linear.weight.mul_(4.0)            # spread the logits (fewer near-ties)
+        model.decoder.output_linear.weight[2].mul_(2.2)         # EOS wins now and then
+    enc = torch.randn(B, Te, 64, generator=g)
+    with torch.no_grad():
+        strs = model.decoder.greedy_search(enc)
+    ids = np.full((B, 300), -1, dtype=np.int64)                 # -1 = not produced (after the EOS cut)
+    for b, s in enumerate(strs):
+        ids[b, :len(s)] = [l2i[c] for c in s]
+    out = {"in.enc": enc.numpy(), "out.ids": ids, "out.lengths": np.array([len(s) for s in strs], dtype=np.int64)}
+    for n, p in model.state_dict().items():
+        if n.startswith("decoder.") and not n.endswith("positional_encoding.pe"):
+            out["param." + n] = p.detach().numpy()
+    out["meta.cfg"] = np.array([2, 2, 64, 32, 32, 128, V, 301, 161], dtype=np.int64)
+    path = os.path.join(HERE, "greedy.npz")
+    np.savez_compressed(path, **out)
+    print("greedy: utterance lengths (cut at EOS)", [len(s) for s in strs], "->", path, "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
 if __name__ == "__main__":
     if len(sys.argv) == 3 and sys.argv[1] == "--case":
-        run_case(sys.argv[2])
+        run_greedy() if sys.argv[2] == "greedy" else run_case(sys.argv[2])
     else:
-        for c in CASES:
+        for c in list(CASES) + ["greedy"]:
             subprocess.check_call([sys.executable, "-W", "ignore", os.path.abspath(__file__), "--case", c])

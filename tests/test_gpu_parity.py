@@ -316,6 +316,40 @@ def test_emb_frontend_fwd_bwd(b200):
     assert max(errs.values()) < 1e-3, errs
 
 
+def test_emb_frontend_batchnorm_state_and_eval_mode(b200):
+    """nn.BatchNorm2d state of the emb_cnn front end (models/asr/transformer.py:34,38): three training steps update
+    running_mean / running_var / num_batches_tracked exactly as torch does, and model.eval() normalises with them."""
+    from tests.gpu_util import TOL, cuda_model
+    cfg = O.OracleConfig(num_layers=1, num_heads=2, dim_model=64, dim_key=32, dim_value=32, dim_inner=64, vocab=30,
+                         feat_extractor="emb_cnn", tgt_max_len=8)
+    P = O.init_params(cfg, seed=3)
+    g = torch.Generator().manual_seed(9)
+    for k in ("conv.1.weight", "conv.1.bias", "conv.4.weight", "conv.4.bias"):
+        P[k] = P[k] + 0.2 * torch.randn(P[k].shape, generator=g)
+    state = O.bn_initial_state()
+    model = cuda_model(cfg, P)
+    model.train()
+    with torch.no_grad():
+        for step in range(3):
+            src, lens, tgt = O.synthetic_batch(cfg, 3, 44, seed=20 + step, ragged=False)
+            O.transformer_forward(P, cfg, src, lens, tgt, training=True, bn_state=state)
+            model(src.cuda(), lens, tgt.cuda())
+    sd = model.state_dict()
+    for i in (1, 4):
+        assert int(sd[f"conv.{i}.num_batches_tracked"]) == 3 == int(state[f"conv.{i}.num_batches_tracked"])
+        assert rel_err(sd[f"conv.{i}.running_mean"], state[f"conv.{i}.running_mean"]) < 1e-4
+        assert rel_err(sd[f"conv.{i}.running_var"], state[f"conv.{i}.running_var"]) < 1e-4
+    src, lens, tgt = O.synthetic_batch(cfg, 2, 44, seed=40, ragged=False)
+    pred_o, _, _ = O.transformer_forward(P, cfg, src, lens, tgt, training=False, bn_state=state)
+    model.eval()
+    with torch.no_grad():
+        pred, *_ = model(src.cuda(), lens, tgt.cuda())
+    assert rel_err(pred, pred_o) < TOL
+    assert int(model.state_dict()["conv.1.num_batches_tracked"]) == 3          # eval does not touch the state
+    pred_t, _, _ = O.transformer_forward(P, cfg, src, lens, tgt, training=True, bn_state=None)
+    assert rel_err(pred_t, pred_o) > 10 * TOL                                  # ... and differs from batch statistics
+
+
 def test_preprocess_embedding_and_masks(b200):
     ops = _ops(b200)
     tgt = torch.tensor([[5, 6, 7, 0, 0], [9, 0, 4, 0, 0], [3, 3, 3, 3, 3]])
@@ -435,3 +469,39 @@ def test_greedy_decode_token_ids_match_oracle(b200):
         safe = int((margins[b] > band).long().cumprod(0).sum())      # steps before the first near-tie
         assert safe >= 4, "test input degenerate: near-tie too early"
         assert torch.equal(ids[b, :safe], ids_o[b, :safe]), (b, ids[b].tolist(), ids_o[b].tolist())
+
+
+def test_greedy_decode_matches_reference_greedy_search_fixture(b200):
+    """A18 / f3 pinned by the reference itself: tests/golden/greedy.npz holds the token ids of the reference's
+    Decoder.greedy_search (300 steps, cut at EOS).  Full-prefix decode, KV-cached decode and the KV-cached decode with the
+    on-device EOS stop must reproduce them id for id (up to the first step whose top-2 logit margin is inside the rounding
+    band: a near-tie may resolve either way and then changes the rest of the sequence)."""
+    from tests.gpu_util import cuda_model
+    from tests.helpers import cut_at_eos, load_greedy_golden
+    cfg, P, enc, ref_ids, ref_len = load_greedy_golden()
+    _, margins = O.greedy_decode(P, cfg, enc, steps=300)
+    full = dict(O.init_params(cfg, seed=1))              # encoder / front-end entries are unused by the decode
+    full.update(P)
+    model = cuda_model(cfg, full, train=False)
+    dec = model.decoder
+    ids_cached = dec.greedy_decode_cached(enc.cuda(), steps=300).cpu()
+    ids_stop = dec.greedy_decode_cached(enc.cuda(), steps=300, stop_at_eos=True).cpu()
+    ids_full = dec.greedy_decode_ids(enc.cuda(), steps=64).cpu()
+    band = 1e-3 * float(margins.abs().max())
+    for b in range(enc.shape[0]):
+        n = int(ref_len[b])
+        safe = int((margins[b] > band).long().cumprod(0).sum())          # steps before the first near-tie
+        m = min(n, safe)
+        assert m >= 32, "fixture degenerate: near-tie too early"
+        ref = ref_ids[b, :n].tolist()
+        assert cut_at_eos(ids_cached[b])[:m] == ref[:m], b
+        assert cut_at_eos(ids_full[b])[:min(m, 64)] == ref[:min(m, 64)], b
+        got = ids_stop[b]
+        k = int((got >= 0).sum())
+        assert got[:k].tolist()[:m] == ref[:m] and (got[k:] == -1).all(), b      # ids, then -1 from the first EOS on
+        if safe >= n:
+            assert k == n and cut_at_eos(ids_cached[b]) == ref, b                # whole utterance incl. the cut position
+    # early exit: with every utterance finished the loop stops (utterances 1..3 of the fixture end before step 200)
+    sub = enc[1:].cuda()
+    ids_sub = dec.greedy_decode_cached(sub, steps=300, stop_at_eos=True, check_every=4)
+    assert ids_sub.shape == (3, 300) and int((ids_sub >= 0).sum(1).max()) < 300

@@ -1,0 +1,185 @@
+"""The UNMODIFIED reference on the B200, with and without `b200asr.install()` (the drop-in boundary on hardware).
+
+The reference checkout travels to the GPU box as oracle/_ref (staged by oracle/make_ref.py, git-ignored).  Here
+  * `init_transformer_model` (utils/functions.py:116-152) builds the reference's own `Transformer`;
+  * the SAME weights run (i) on the CPU, uninstalled -- the reference's own PyTorch forward/backward, (ii) on the GPU,
+    uninstalled -- the reference eager on the B200 (fp32 flags), (iii) on the GPU after `install()` -- our kernels bound onto
+    the reference's classes; pred / loss / num_correct / every gradient are compared;
+  * the reference's `Trainer.train` loop (trainer/asr/trainer.py:20-211) is driven unchanged for an epoch (train iterations
+    with `opt.step()` of the reference's NoamOpt + torch Adam, the eval-mode validation loop, the checkpoint save) with
+    synthetic `_collate_fn`-shaped batches, once on the reference eager and once installed: losses, updated parameters and
+    BatchNorm buffers must agree.
+"""
+import copy
+import os
+import tempfile
+
+import pytest
+import torch
+
+from oracle import ref_shim
+from tests.helpers import grads_rel_err, rel_err
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_shim.available(), reason="reference checkout not staged (oracle/make_ref.py)")]
+
+TOL = 1e-3
+
+SMALL_VGG = ["--num-layers", "2", "--num-heads", "2", "--dim-model", "64", "--dim-emb", "64", "--dim-key", "32", "--dim-value", "32",
+             "--dim-inner", "128", "--feat_extractor", "vgg_cnn", "--sample-rate", "4000", "--tgt-max-len", "12"]
+SMALL_EMB = ["--num-layers", "1", "--num-heads", "2", "--dim-model", "64", "--dim-emb", "64", "--dim-key", "32", "--dim-value", "32",
+             "--dim-inner", "128", "--feat_extractor", "emb_cnn", "--tgt-max-len", "10"]
+CFG2_ARCH = ["--num-layers", "4", "--num-heads", "8", "--dim-model", "512", "--dim-emb", "512", "--dim-key", "64", "--dim-value", "64",
+             "--dim-inner", "2048", "--feat_extractor", "vgg_cnn", "--tgt-max-len", "40"]
+
+
+def _fp32_flags():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def _build(flags, vocab, extra=()):
+    ns = ref_shim.load(list(flags) + ["--dropout", "0.0", "--label-smoothing", "0.1"] + list(extra))
+    l2i, i2l = ref_shim.labels(vocab)
+    torch.manual_seed(123456)
+    model = ns.functions.init_transformer_model(ns.constant.args, l2i, i2l)
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+    return ns, model, l2i, i2l
+
+
+def _batch(B, freq, T, vocab, Lt, seed=0, ragged=True):
+    g = torch.Generator().manual_seed(seed)
+    src = torch.randn(B, 1, freq, T, generator=g)
+    lens = (T * (0.5 + 0.5 * torch.rand(B, generator=g))).long().clamp(1, T) if ragged else torch.full((B,), T)
+    lens[0] = T
+    lens = torch.sort(lens, descending=True).values
+    for i in range(B):
+        src[i, :, :, int(lens[i]):] = 0
+    tgt = torch.randint(3, vocab, (B, Lt), generator=g)
+    tl = (Lt * (0.4 + 0.6 * torch.rand(B, generator=g))).long().clamp(1, Lt)
+    tl[0] = Lt
+    for i in range(B):
+        tgt[i, int(tl[i]):] = 0
+    return src, lens.to(torch.int32), tgt, tl.to(torch.int32)
+
+
+def _step(ns, model, src, lens, tgt, dev):
+    model.zero_grad(set_to_none=True)
+    pred, gold, hyp, _ = model(src.to(dev), lens, tgt.to(dev), verbose=False)
+    loss, n_correct = ns.metrics.calculate_metrics(pred, gold, smoothing=0.1, loss_type="ce")
+    loss.backward()
+    grads = {n: p.grad.detach().float().cpu() for n, p in model.named_parameters()}
+    return pred.detach().float().cpu(), gold.cpu(), hyp.cpu(), float(loss.item()), int(n_correct), grads
+
+
+@pytest.mark.parametrize("case", ["small_vgg", "small_emb", "cfg2_arch"])
+def test_install_on_unmodified_reference_matches_reference_forward_backward(case):
+    import b200asr
+    flags, vocab, freq, B, T = {"small_vgg": (SMALL_VGG, 40, 41, 3, 32), "small_emb": (SMALL_EMB, 40, 161, 3, 48),
+                                "cfg2_arch": (CFG2_ARCH, 4364, 161, 2, 200)}[case]
+    ns, model, _, _ = _build(flags, vocab)
+    src, lens, tgt, _ = _batch(B, freq, T, vocab, ns.constant.args.tgt_max_len - 1)
+    keys = list(model.state_dict().keys())
+    model.train()
+    _fp32_flags()
+    cpu = _step(ns, model, src, lens, tgt, "cpu")                       # (i) the reference's own CPU forward/backward
+    model = model.cuda()
+    eager = _step(ns, model, src, lens, tgt, "cuda")                    # (ii) the reference eager on the B200
+    orig_forward = ns.transformer.Transformer.forward
+    b200asr.install()
+    try:
+        assert ns.transformer.Transformer.forward is not orig_forward
+        launches0 = b200asr._lib.load().b200asr_launch_count()
+        ours = _step(ns, model, src, lens, tgt, "cuda")                 # (iii) our kernels behind the reference's classes
+        assert b200asr._lib.load().b200asr_launch_count() > launches0   # ... and they did launch
+    finally:
+        b200asr.uninstall()
+    assert ns.transformer.Transformer.forward is orig_forward
+    assert list(model.state_dict().keys()) == keys                      # module tree / parameter names untouched
+    for name, other in (("cpu", cpu), ("eager-gpu", eager)):
+        assert torch.equal(ours[1], other[1]), name                     # gold
+        e_pred = rel_err(ours[0], other[0])
+        errs = grads_rel_err(ours[5], other[5])
+        worst = max(errs, key=errs.get)
+        real = other[1].ne(0)
+        flips = int((ours[2][real] != other[2][real]).sum())
+        print(f"[{case}] installed vs {name}: pred {e_pred:.2e} loss {abs(ours[3] - other[3]) / abs(other[3]):.2e} "
+              f"grads max {errs[worst]:.2e} ({worst}) argmax flips {flips}/{int(real.sum())} num_correct {ours[4]} vs {other[4]}")
+        assert e_pred < TOL
+        assert abs(ours[3] - other[3]) < TOL * abs(other[3])
+        assert errs[worst] < TOL, (name, worst, errs[worst])
+        assert flips <= max(1, int(real.sum()) // 100)                  # near-ties at random init
+        assert abs(ours[4] - other[4]) <= max(1, int(real.sum()) // 100)
+
+
+def _loaders(freq, T, vocab, Lt, n_train, B):
+    def one(seed):
+        src, lens, tgt, tl = _batch(B, freq, T, vocab, Lt, seed=seed)
+        return (src, tgt, lens.float() / float(T), lens, tl)            # _collate_fn order, utils/data_loader.py:213
+    return [one(s) for s in range(n_train)], [[one(100)]]
+
+
+def _run_trainer(ns, model, l2i, i2l, train, valid, installed, tmp):
+    """Drive the reference's Trainer.train unchanged for one epoch; returns (per-iteration losses, state_dict)."""
+    import b200asr
+    ns.constant.args.save_folder, ns.constant.args.name = tmp, "b200" if installed else "eager"
+    opt = ns.functions.init_optimizer(ns.constant.args, model, "noam")
+    losses = []
+    if installed:
+        b200asr.install()
+    cur = ns.trainer.calculate_metrics
+
+    def recording(*a, **k):
+        out = cur(*a, **k)
+        losses.append(float(out[0].item()))
+        return out
+
+    ns.trainer.calculate_metrics = recording
+    try:
+        tr = copy.deepcopy(train), copy.deepcopy(valid)                 # the loop scales src_percentages in place (trainer.py:82)
+        ns.trainer.Trainer().train(model, tr[0], None, tr[1], opt, "ce", 0, 1, l2i, i2l)
+    finally:
+        ns.trainer.calculate_metrics = cur
+        if installed:
+            b200asr.uninstall()
+    assert os.path.exists(os.path.join(tmp, ns.constant.args.name, "best_model.th"))      # save_model ran (functions.py:10-57)
+    return losses, {k: v.detach().float().cpu().clone() for k, v in model.state_dict().items()}
+
+
+@pytest.mark.parametrize("case", ["small_vgg", "small_emb"])
+def test_reference_trainer_loop_runs_on_installed_kernels(case):
+    """trainer/asr/trainer.py:47-118 (train) and :123-190 (eval-mode validation) -- unchanged code, our kernels underneath.
+    small_emb also checks the BatchNorm buffers (running_mean / running_var / num_batches_tracked) and the eval-mode
+    forward that uses them."""
+    flags, vocab, freq, B, T = {"small_vgg": (SMALL_VGG, 40, 41, 4, 32), "small_emb": (SMALL_EMB, 40, 161, 4, 48)}[case]
+    _fp32_flags()
+    results = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for installed in (False, True):
+            ns, model, l2i, i2l = _build(flags, vocab, extra=["--cuda", "--warmup", "4", "--k-lr", "1", "--min-lr", "1e-4", "--clip", "--max-norm", "400"])
+            init = {k: v.detach().float().clone() for k, v in model.state_dict().items()}
+            model = model.cuda()
+            train, valid = _loaders(freq, T, vocab, ns.constant.args.tgt_max_len - 1, 3, B)
+            results[installed] = _run_trainer(ns, model, l2i, i2l, train, valid, installed, tmp)
+    (l_e, sd_e), (l_b, sd_b) = results[False], results[True]
+    print(f"[{case}] losses eager {l_e}\n[{case}] losses b200  {l_b}")
+    assert len(l_e) == len(l_b) == 4                                    # 3 train iterations + 1 validation batch
+    for a, b in zip(l_e, l_b):
+        assert abs(a - b) < TOL * abs(a), (l_e, l_b)
+    for k in sd_e:
+        if "num_batches_tracked" in k:
+            assert sd_e[k].item() == sd_b[k].item() == 3, k
+            continue
+        if "running_" in k:
+            assert rel_err(sd_b[k], sd_e[k]) < TOL, k
+            continue
+        if k.endswith("positional_encoding.pe"):
+            continue
+        d_e, d_b = sd_e[k] - init[k], sd_b[k] - init[k]
+        if d_e.numel() < 256:
+            continue                                                    # tiny tensors: Adam's sign-like first steps on noise-level gradients
+        # Adam normalises the step, so an element whose gradient is rounding noise moves by +-lr either way: compare in L2
+        assert float((d_e - d_b).norm() / d_e.norm().clamp_min(1e-30)) < 0.05, k

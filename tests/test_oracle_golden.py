@@ -56,3 +56,17 @@ def test_noam_and_adam_reference():
         opt.step()
         q, m, v = O.adam_reference(q, g, m, v, step, 1e-3)
         assert torch.allclose(q, p.detach(), rtol=1e-5, atol=1e-7)
+
+
+def test_greedy_decode_matches_reference_greedy_search():
+    """Pins oracle.greedy_decode: the reference's own Decoder.greedy_search output (300 steps, strings cut at EOS; fixture
+    generated from the live reference with the Q12 shim) is reproduced id for id."""
+    from tests.helpers import cut_at_eos, load_greedy_golden
+    cfg, P, enc, ref_ids, ref_len = load_greedy_golden()
+    ids, margins = O.greedy_decode(P, cfg, enc, steps=300)
+    assert int(ref_len.min()) < 300 <= int(ref_len.max())              # the fixture has both cut and uncut utterances
+    for b in range(enc.shape[0]):
+        mine = cut_at_eos(ids[b])
+        n = int(ref_len[b])
+        assert mine == ref_ids[b, :n].tolist(), b
+        assert (ref_ids[b, n:] == -1).all()
