@@ -42,7 +42,7 @@ SIGNATURES = {
                              [_f, _f, _u64, _u64, _i, _vp]),
     "b200asr_sdpa_mat_bwd": (_i, [_vp] * 4 + [_ll] * 12 + [_vp] * 6 + [_i] * 6 + [_f, _f, _u64, _u64, _i, _vp]),
     "b200asr_stft_ws_bytes": (_sz, [_i, _i, _i, _i]),
-    "b200asr_stft_features": (_i, [_vp] * 5 + [_i] * 8 + [_vp]),
+    "b200asr_stft_features": (_i, [_vp] * 5 + [_i] * 9 + [_vp]),
     "b200asr_im2col": (_i, [_vp, _vp] + [_i] * 11 + [_vp]),
     "b200asr_col2im": (_i, [_vp, _vp] + [_i] * 11 + [_vp]),
     "b200asr_transpose_cp": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
@@ -72,6 +72,7 @@ SIGNATURES = {
     "b200asr_ce_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _f, _vp, _vp, _vp]),
     "b200asr_adam_step": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _i, _f, _vp, _vp]),
     "b200asr_sumsq": (_i, [_vp, _ll, _vp, _vp]),
+    "b200asr_grad_scale": (_i, [_vp, _ll, _vp, _f, _vp, _vp, _vp]),
     "b200asr_permute_cols_cf": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
 }
 

@@ -270,6 +270,21 @@ __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __
   }
 }
 
+// out[0] = (1 / n_tokens) * min(1, max_norm / (||g|| / n_tokens + 1e-6)): the normalisation by the global token count
+// (utils/metrics.py:127-130) times the coefficient of torch.nn.utils.clip_grad_norm_ (trainer/asr/trainer.py:108-109),
+// computed on the device so that the optimizer step needs no host round trip.
+__global__ void grad_scale_kernel(const float* __restrict__ n_tokens, const float* __restrict__ sumsq, float max_norm,
+                                  float* __restrict__ out) {
+  const float inv = 1.f / n_tokens[0];
+  float clip = 1.f;
+  if (sumsq) {
+    const float norm = sqrtf(sumsq[0]) * inv;
+    clip = fminf(1.f, max_norm / (norm + 1e-6f));
+  }
+  out[0] = inv * clip;
+  out[1] = sumsq ? sqrtf(sumsq[0]) * inv : 0.f;      // the gradient norm, for logging
+}
+
 __global__ void permute_cols_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int C, int F, int inverse) {
   long long n = (long long)rows * C * F;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -383,6 +398,18 @@ int b200asr_sumsq(const float* g, long long n, float* out, b200asr_stream_t stre
   int cap = device_sm_count() * 8;
   sumsq_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(g, n, out);
   return check_launch("sumsq");
+}
+
+int b200asr_grad_scale(const float* g, long long n, const float* n_tokens, float max_norm, float* scratch, float* out,
+                       b200asr_stream_t stream) {
+  B200_REQUIRE(n_tokens && out && (max_norm <= 0.f || (g && scratch)), B200ASR_BAD_ARG, "grad_scale: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (max_norm > 0.f) {
+    cudaMemsetAsync(scratch, 0, sizeof(float), st);
+    if (int rc = b200asr_sumsq(g, n, scratch, stream)) return rc;
+  }
+  grad_scale_kernel<<<1, 1, 0, st>>>(n_tokens, max_norm > 0.f ? scratch : nullptr, max_norm, out);
+  return check_launch("grad_scale");
 }
 
 int b200asr_permute_cols_cf(const float* src, float* dst, int rows, int C, int F, int inverse, b200asr_stream_t stream) {

@@ -65,8 +65,10 @@ __global__ void feat_pad_kernel(const float* __restrict__ wave, const int* __res
 }
 
 // basis[r][n]: r < nb: w[n] cos(2 pi r n / N); nb <= r < 2 nb: -w[n] sin(2 pi (r-nb) n / N); zero rows after.
-// w = periodic Hamming (scipy.signal.get_window('hamming', N, fftbins=True), what librosa.stft uses).
-__global__ void feat_basis_kernel(float* __restrict__ basis, int n_fft, int nb, int npad) {
+// w = Hamming window over wden points: wden = N - 1 is the SYMMETRIC window -- what the reference computes: it hands the
+// callable scipy.signal.hamming to librosa.stft (utils/data_loader.py:20,52,77-78) and librosa.filters.get_window calls a
+// callable as window(N), i.e. sym=True --; wden = N is the periodic window of window='hamming' strings.
+__global__ void feat_basis_kernel(float* __restrict__ basis, int n_fft, int nb, int npad, int wden) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npad * n_fft) return;
   const int r = i / n_fft, n = i % n_fft;
@@ -76,7 +78,7 @@ __global__ void feat_basis_kernel(float* __restrict__ basis, int n_fft, int nb, 
     const int m = (int)(((long long)k * n) % n_fft);                 // exact phase reduction
     float s, c;
     sincospif(2.0f * (float)m / (float)n_fft, &s, &c);
-    const float w = 0.54f - 0.46f * cospif(2.0f * (float)n / (float)n_fft);
+    const float w = 0.54f - 0.46f * cospif(2.0f * (float)n / (float)wden);
     v = r < nb ? w * c : -w * s;
   }
   basis[i] = v;
@@ -151,7 +153,7 @@ size_t b200asr_stft_ws_bytes(int B, int Lmax, int n_fft, int hop) {
 }
 
 int b200asr_stft_features(const float* wave, const int* lens, float* out, int* frames_out, void* ws, int B, int Lmax,
-                          int Tmax, int n_fft, int hop, int pad_reflect, int normalize, int precision,
+                          int Tmax, int n_fft, int hop, int pad_reflect, int normalize, int window_periodic, int precision,
                           b200asr_stream_t stream) {
   B200_REQUIRE(wave && lens && out && ws, B200ASR_BAD_ARG, "stft_features: null pointer");
   B200_REQUIRE(B > 0 && Lmax > 0 && Tmax > 0, B200ASR_BAD_SHAPE, "stft_features: empty problem");
@@ -171,7 +173,7 @@ int b200asr_stft_features(const float* wave, const int* lens, float* out, int* f
   feat_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(wave, lens, padded, B, Lmax, w.Lp, n_fft / 2, pad_reflect, total);
   int rc = check_launch("feat_pad");
   if (rc) return rc;
-  feat_basis_kernel<<<ceil_div(w.npad * n_fft, 256), 256, 0, st>>>(basis, n_fft, nb, w.npad);
+  feat_basis_kernel<<<ceil_div(w.npad * n_fft, 256), 256, 0, st>>>(basis, n_fft, nb, w.npad, window_periodic ? n_fft : n_fft - 1);
   rc = check_launch("feat_basis");
   if (rc) return rc;
   const int M = B * w.rows_per_utt;

@@ -1,7 +1,8 @@
 """GPU feature front end: waveforms -> the `(inputs, input_percentages, input_sizes)` triple of the reference's loader.
 
 Mirrors `SpectrogramParser.parse_audio` (utils/data_loader.py:60-91) + the padded batch of `_collate_fn` (:182-214):
-STFT (n_fft = sample_rate * window_size, hop = sample_rate * window_stride, periodic Hamming window, centred frames),
+STFT (n_fft = sample_rate * window_size, hop = sample_rate * window_stride, symmetric Hamming window -- the reference
+passes the callable scipy.signal.hamming, which librosa evaluates as window(n_fft), i.e. sym=True --, centred frames),
 magnitude, log1p, per-utterance mean / unbiased-std normalisation, zero padding to the longest utterance.  One C-ABI call
 (`b200asr_stft_features`): the STFT of the whole batch is a single 3xTF32 tcgen05 GEMM over overlapping frame rows.
 """
@@ -17,7 +18,7 @@ from . import ops
 
 def spectrogram_batch(waves: Sequence[torch.Tensor] | torch.Tensor, lengths: torch.Tensor | None = None, sample_rate: int = 16000,
                       window_size: float = 0.02, window_stride: float = 0.01, normalize: bool = True, reflect: bool = True,
-                      precision: int | None = None):
+                      precision: int | None = None, window_periodic: bool = False):
     """waves: list of 1-D CUDA float tensors, or a zero-padded [B, L_max] CUDA tensor with `lengths` (int32 samples).
     Returns (inputs [B,1,F,T_max] fp32, input_percentages [B] fp32, input_sizes [B] int32), all on the device."""
     n_fft, hop = int(sample_rate * window_size), int(sample_rate * window_stride)
@@ -43,5 +44,5 @@ def spectrogram_batch(waves: Sequence[torch.Tensor] | torch.Tensor, lengths: tor
     frames = torch.empty(B, device=wave.device, dtype=torch.int32)
     prec = ops.config.linear if precision is None else precision
     L.check(lib.b200asr_stft_features(L.ptr(wave), L.ptr(lens), L.ptr(out), L.ptr(frames), L.ptr(ws), B, Lmax, t_max, n_fft, hop,
-                                      int(reflect), int(normalize), prec, ops._stream()), "stft_features")
+                                      int(reflect), int(normalize), int(window_periodic), prec, ops._stream()), "stft_features")
     return out, frames.float() / float(t_max), frames

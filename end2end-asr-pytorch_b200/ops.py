@@ -170,8 +170,10 @@ def linear_bwd_data(dy2, w, relu_out, prec, w_split=None):
 def _grad_sink(param):
     """The parameter's existing .grad if a kernel can accumulate straight into it (the flat gradient buffer of
     optim.FlatParams), else None.  Writing there removes autograd's AccumulateGrad add kernel and a temporary per weight."""
-    if param is None or not param.is_leaf:
-        return None
+    if param is None or not param.is_leaf or not getattr(param, "_b200_flat_grad", False):
+        return None          # opt-in: only parameters re-homed by optim.FlatParams (it owns their .grad views)
+    if getattr(param, "_backward_hooks", None) or getattr(param, "_post_accumulate_grad_hooks", None):
+        return None          # tensor hooks (DDP, clipping hooks ...) must see the gradient: let autograd deliver it
     g = param.grad
     if g is None or not g.is_cuda or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != param.shape:
         return None
@@ -255,10 +257,14 @@ class FFNFn(torch.autograd.Function):
         xs, w1s, w2s = ctx.shapes
         dy2 = _f32c(dy).reshape(-1, w2m.shape[0])
         w1, b1, w2, b2 = ctx.params
-        dw2, db2 = linear_bwd_weight(dy2, h, True, ctx.prec, _grad_sink(w2), _grad_sink(b2))
-        dh = linear_bwd_data(dy2, w2m, h, ctx.prec, ws2)     # masked by relu'(h)
-        dw1, db1 = linear_bwd_weight(dh, x2, True, ctx.prec, _grad_sink(w1), _grad_sink(b1))
-        dx = linear_bwd_data(dh, w1m, None, ctx.prec, ws1) if ctx.needs_input_grad[0] else None
+        need = ctx.needs_input_grad                          # (x, w1, b1, w2, b2): frozen weights get no wgrad GEMM
+        dw1 = db1 = dw2 = db2 = None
+        if need[3] or need[4]:
+            dw2, db2 = linear_bwd_weight(dy2, h, True, ctx.prec, _grad_sink(w2), _grad_sink(b2))
+        dh = linear_bwd_data(dy2, w2m, h, ctx.prec, ws2) if (need[0] or need[1] or need[2]) else None     # masked by relu'(h)
+        if need[1] or need[2]:
+            dw1, db1 = linear_bwd_weight(dh, x2, True, ctx.prec, _grad_sink(w1), _grad_sink(b1))
+        dx = linear_bwd_data(dh, w1m, None, ctx.prec, ws1) if need[0] else None
         return ((dx.view(xs) if dx is not None else None), (dw1.view(w1s) if dw1 is not None else None), db1,
                 (dw2.view(w2s) if dw2 is not None else None), db2)
 
@@ -339,10 +345,13 @@ def _sdpa_forward_impl(q, k, v, key_pad, dense_mask, causal, scale, p_drop, head
     # 32-float k-blocks and rows of at most 2048 keys; the TF32 flash kernel keeps the score row in TMEM
     # (Tk <= 448, d in {32,64}); everything else runs on the fp32 CUDA-core kernel
     prec = config.attn
-    if prec == L.PREC_TF32X3 and not (dk % 32 == 0 and dv % 32 == 0 and Tk <= 2048):
+    if prec == L.PREC_TF32X3 and not (dk % 32 == 0 and dv % 32 == 0 and dk <= 256 and dv <= 256 and Tk <= 2048):
         prec = L.PREC_FP32
     if prec == L.PREC_TF32 and not (Tk <= 448 and dk in (32, 64) and dv in (32, 64)):
         prec = L.PREC_FP32
+    if prec == L.PREC_FP32 and not (dk in (16, 32, 64, 128) and dv in (16, 32, 64, 128)):
+        raise RuntimeError(f"b200asr attention: head dims (dk={dk}, dv={dv}) are supported for multiples of 32 up to 256 with "
+                           f"Tk <= 2048 (tensor-core path) or for 16/32/64/128 (fp32 path); no kernel covers this shape")
     if prec == L.PREC_TF32X3:
         n = _lib().b200asr_sdpa_mat_ws_bytes(B, H, Tq, Tk) // 4
         probs = torch.empty(n, device=q.device, dtype=torch.float32)
@@ -454,7 +463,6 @@ class AttnProjFn(torch.autograd.Function):
         xq2 = _f32c(xq).reshape(-1, D)
         xkv2 = xq2 if same else _f32c(xkv).reshape(-1, xkv.shape[2])
         ws_list = [_f32c(w.reshape(w.shape[0], -1)) for w in (wq, wk, wv)]
-        prec = _linear_prec(ws_list[0].shape[0], D)
         has_bias = bq is not None and bk is not None and bv is not None
         n_q, n_k, n_v = (w.shape[0] for w in ws_list)
         fuse3 = same and _adjacent(*ws_list) and (not has_bias or _adjacent(bq, bk, bv))
@@ -470,10 +478,11 @@ class AttnProjFn(torch.autograd.Function):
         for idx, x2 in groups:
             W = _stacked(*[ws_list[i] for i in idx])
             b = _stacked(*[bs_list[i] for i in idx]) if has_bias else None
+            prec = _linear_prec(W.shape[0], W.shape[1])       # shape rule per stacked group (N = H*dk, H*dv or their sums)
             wsplit = split_weight(W, prec)
             y = linear_fwd(x2, W, b, False, prec, wsplit)
             packed.append(y)
-            saved.append((idx, x2, W, wsplit))
+            saved.append((idx, x2, W, wsplit, prec))
         # column slices of the packed outputs as (B,H,T,d) views
         def head_view(y, col0, T, d):
             return y.view(B, T, y.shape[1])[:, :, col0:col0 + H * d].unflatten(2, (H, d)).permute(0, 2, 1, 3)
@@ -484,7 +493,7 @@ class AttnProjFn(torch.autograd.Function):
         else:
             q = head_view(packed[0], 0, Tq, dk); k = head_view(packed[1], 0, Tk, dk); v = head_view(packed[2], 0, Tk, dv)
         out, state = _sdpa_forward_impl(q, k, v, key_pad, dense_mask, causal, scale, p_drop)
-        ctx.state, ctx.saved, ctx.prec, ctx.has_bias = state, saved, prec, has_bias
+        ctx.state, ctx.saved, ctx.has_bias = state, saved, has_bias
         ctx.params = (wq, bq, wk, bk, wv, bv)
         ctx.shapes = (xq.shape, xkv.shape, same, fuse3, fuse2, (n_q, n_k, n_v), H, dk, dv)
         return out.permute(0, 2, 1, 3).reshape(B, Tq, H * dv)          # free: memory is token-major
@@ -514,10 +523,10 @@ class AttnProjFn(torch.autograd.Function):
         grads_w, grads_b = [None] * 3, [None] * 3
         dxq = dxkv = None
         need_xq, need_xkv = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        for (idx, x2, W, wsplit), dy in zip(ctx.saved, dys):
+        for (idx, x2, W, wsplit, prec), dy in zip(ctx.saved, dys):
             feeds_q = 0 in idx
             if (feeds_q and need_xq) or (not feeds_q and (need_xkv or (same and need_xq))):
-                dx = linear_bwd_data(dy, W, None, ctx.prec, wsplit)
+                dx = linear_bwd_data(dy, W, None, prec, wsplit)
                 if feeds_q:
                     dxq = dx if dxq is None else dxq + dx
                 elif same:
@@ -533,7 +542,7 @@ class AttnProjFn(torch.autograd.Function):
                 w_sink = _stacked(*[g.reshape(g.shape[0], -1) for g in sinks_w])
             if ctx.has_bias and all(g is not None for g in sinks_b) and _adjacent(*sinks_b):
                 b_sink = _stacked(*sinks_b)
-            dw, db = linear_bwd_weight(dy, x2, ctx.has_bias, ctx.prec, w_sink, b_sink)
+            dw, db = linear_bwd_weight(dy, x2, ctx.has_bias, prec, w_sink, b_sink)
             if dw is not None:          # no direct accumulation: hand the slices to autograd
                 r0 = 0
                 for i in idx:

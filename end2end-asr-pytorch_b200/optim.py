@@ -55,6 +55,7 @@ class FlatParams:
                 self.flat[o:o + n].copy_(p.detach().reshape(-1))
                 p.data = self.flat[o:o + n].view(p.shape)
                 p.grad = self.flat_grad[o:o + n].view(p.shape)
+                p._b200_flat_grad = True      # opt-in for ops._grad_sink: backward kernels may accumulate straight into .grad
 
     @property
     def extras(self) -> torch.Tensor:

@@ -11,7 +11,8 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-from . import metrics
+from . import _lib as L
+from . import metrics, ops
 from .optim import FlatParams, FusedAdam, NoamOpt
 
 
@@ -41,7 +42,15 @@ class DataParallelStep:
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.clip = clip_max_norm
-        self._inv_tokens = torch.zeros(1, device=self.flat.flat.device, dtype=torch.float32)
+        self._scale = torch.zeros(4, device=self.flat.flat.device, dtype=torch.float32)    # [scale, grad norm, scratch, -]
+        self._host_tail = loss_fn is not None or adam_factory is not None                  # CPU stand-ins (gloo tests)
+        if self.world > 1:
+            # replicas start identical (nn.DataParallel re-replicates from device 0 every step, utils/functions.py:158-160;
+            # here once is enough because every rank applies the identical update) ...
+            dist.broadcast(self.flat.flat, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0,
+                           group=process_group)
+            # ... but draw DIFFERENT dropout masks for their shards (the kernels' counter-based generator is seeded per process)
+            ops.rng.seed = (ops.rng.seed ^ (0x9E3779B97F4A7C15 * (dist.get_rank(process_group) + 1))) & 0xFFFFFFFFFFFFFFFF
 
     def forward_backward(self, src, lengths, tgt):
         """Local shard fwd+bwd with the un-normalised loss; gradients land in the flat buffer."""
@@ -58,12 +67,25 @@ class DataParallelStep:
             dist.all_reduce(self.flat.flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
 
     def optimizer_step(self):
-        torch.reciprocal(self.flat.extras[1:2], out=self._inv_tokens)     # 1 / global n_tokens (device scalar)
-        scale = 1.0
-        if self.clip is not None:                                          # trainer.py:108-109 (needs the norm on the host)
-            norm = float(self.adam.grad_sumsq().sqrt().item()) * float(self._inv_tokens.item())
-            scale = min(1.0, self.clip / (norm + 1e-6))
-        self.opt.step(grad_scale=scale, grad_scale_dev=self._inv_tokens)
+        """Adam with the gradient read as g * (1 / global n_tokens) * clip coefficient -- both computed on the device
+        (b200asr_grad_scale): no host round trip between the all-reduce and the update (trainer.py:108-111)."""
+        if self._host_tail:                                                # protocol tests on CPU / gloo
+            inv = 1.0 / float(self.flat.extras[1])
+            scale = 1.0
+            if self.clip is not None:
+                norm = float(self.flat.flat_grad[:self.flat.numel].norm()) * inv
+                scale = min(1.0, self.clip / (norm + 1e-6))
+            self._scale[0] = inv * scale
+        else:
+            f = self.flat
+            L.check(L.load().b200asr_grad_scale(L.ptr(f.flat_grad), f.numel, f.extras[1:2].data_ptr(),
+                                                float(self.clip) if self.clip is not None else 0.0, self._scale[2:3].data_ptr(),
+                                                L.ptr(self._scale), torch.cuda.current_stream().cuda_stream), "grad_scale")
+        self.opt.step(grad_scale=1.0, grad_scale_dev=self._scale[0:1])
+
+    def grad_norm(self) -> torch.Tensor:
+        """Norm of the token-normalised global gradient of the last step (device scalar; 0 when clipping is off)."""
+        return self._scale[1]
 
     def step(self, src, lengths, tgt):
         pred, hyp, stats = self.forward_backward(src, lengths, tgt)

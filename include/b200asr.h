@@ -264,6 +264,11 @@ int b200asr_adam_step(float* p, const float* g, float* m, float* v, long long n,
                       b200asr_stream_t stream);
 /* out[0] += sum(g^2) (caller zeroes out) */
 int b200asr_sumsq(const float* g, long long n, float* out, b200asr_stream_t stream);
+/* Device-side gradient scale of the step tail: out[0] = (1 / *n_tokens) * clip, where clip = 1 if max_norm <= 0, else
+ * min(1, max_norm / (||g||_2 / *n_tokens + 1e-6)) -- torch.nn.utils.clip_grad_norm_ (trainer/asr/trainer.py:108-109) on the
+ * token-normalised gradient; out[1] = that norm (0 without clipping).  scratch: 1 float.  No host synchronisation. */
+int b200asr_grad_scale(const float* g, long long n, const float* n_tokens, float max_norm, float* scratch, float* out,
+                       b200asr_stream_t stream);
 /* dst = src permuted: dst[r, f*C + c] = src[r, c*F + f] (input_linear column order, see VGG note);
  * inverse != 0 applies the inverse permutation. */
 int b200asr_permute_cols_cf(const float* src, float* dst, int rows, int C, int F, int inverse,
@@ -272,15 +277,16 @@ int b200asr_permute_cols_cf(const float* src, float* dst, int rows, int C, int F
 /* ------------------------------------------------------------------------------------------------
  * Feature front end ("next" row 4 of SURVEY.md §8f): SpectrogramParser.parse_audio (utils/data_loader.py:60-91)
  * + the padded batch layout of _collate_fn (:182-214).  wave [B,Lmax] fp32 zero padded, lens [B] samples.
- * STFT with n_fft-sample periodic-Hamming frames every hop samples, centred (n_fft/2 padding on both sides,
+ * STFT with n_fft-sample Hamming frames (symmetric window, as the reference's callable scipy.signal.hamming gives
+ * through librosa; window_periodic != 0 selects the periodic variant) every hop samples, centred (n_fft/2 padding on both sides,
  * reflected when pad_reflect != 0, zeros otherwise), magnitude, log1p, optional per-utterance mean / unbiased-std
  * normalisation -> out [B,1,n_fft/2+1,Tmax] zero padded; frames_out[b] = 1 + lens[b]/hop (may be NULL).
  * The STFT of the whole batch is ONE GEMM over overlapping frame rows (precision as for b200asr_linear_fwd).
  * ws: b200asr_stft_ws_bytes(B, Lmax, n_fft, hop) bytes.  n_fft % 32 == 0, hop % 4 == 0. */
 size_t b200asr_stft_ws_bytes(int B, int Lmax, int n_fft, int hop);
 int b200asr_stft_features(const float* wave, const int* lens, float* out, int* frames_out, void* ws, int B,
-                          int Lmax, int Tmax, int n_fft, int hop, int pad_reflect, int normalize, int precision,
-                          b200asr_stream_t stream);
+                          int Lmax, int Tmax, int n_fft, int hop, int pad_reflect, int normalize, int window_periodic,
+                          int precision, b200asr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -73,7 +73,7 @@ def run_steps(model, world_group, rank, world, steps=3):
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    torch.manual_seed(0)
+    torch.manual_seed(rank)          # ranks build DIFFERENT replicas: DataParallelStep broadcasts rank 0's (seed 0) parameters
     model = TinyModel()
     losses, flat = run_steps(model, None, rank, world)
     q.put((rank, losses, flat))
