@@ -171,17 +171,124 @@ def cpu_oracle_throughput(batch, steps, warmup, threads=None):
     return batch / mean, mean, torch.get_num_threads()
 
 
+def reference_flags(cfg, cuda=False):
+    """The reference's own command-line flags (utils/constant.py) for an ASRConfig."""
+    f = ["--num-layers", cfg.num_layers, "--num-heads", cfg.num_heads, "--dim-model", cfg.dim_model, "--dim-emb", cfg.dim_model,
+         "--dim-key", cfg.dim_key, "--dim-value", cfg.dim_value, "--dim-inner", cfg.dim_inner, "--feat_extractor", cfg.feat_extractor,
+         "--tgt-max-len", cfg.tgt_max_len, "--src-max-len", cfg.src_max_len, "--dropout", cfg.dropout,
+         "--label-smoothing", cfg.label_smoothing, "--warmup", 4000, "--min-lr", 1e-6, "--k-lr", 1]
+    return [str(x) for x in f] + (["--cuda"] if cuda else [])
+
+
+def build_reference(cfg, cuda=False):
+    """The UNMODIFIED reference model + its own optimizer (utils/functions.py:101-152), imported from /root/reference or the
+    staged oracle/_ref (oracle/make_ref.py).  Returns (namespace, model, opt) or None when the checkout is absent."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        return None
+    ns = ref_shim.load(reference_flags(cfg, cuda))
+    l2i, i2l = ref_shim.labels(cfg.vocab)
+    torch.manual_seed(123456)
+    model = ns.functions.init_transformer_model(ns.constant.args, l2i, i2l)
+    if cuda:
+        model = model.cuda()
+    model.train()
+    opt = ns.functions.init_optimizer(ns.constant.args, model, "noam")
+    return ns, model, opt
+
+
+def reference_step(ns, model, opt, src, lens, tgt, smoothing):
+    """One iteration of the reference's training loop, trainer/asr/trainer.py:56-111 minus the string metrics:
+    zero_grad -> model(...) -> calculate_metrics -> loss.backward() -> opt.step()."""
+    opt.zero_grad()
+    pred, gold, hyp, _ = model(src, lens, tgt, verbose=False)
+    loss, _ = ns.metrics.calculate_metrics(pred, gold, smoothing=smoothing, loss_type="ce")
+    loss.backward()
+    opt.step()
+    return loss
+
+
+def cpu_reference_throughput(batch, steps, warmup, threads=None):
+    """The reference's own PyTorch CPU path (kind "reference") on a `batch`-utterance sample of the workload; falls back to
+    the oracle port (kind "port") only if the reference checkout is not staged."""
+    import b200asr
+    spec = b200asr.BASELINE_CONFIGS[WORKLOAD]
+    cfg = spec["cfg"]
+    torch.set_num_threads(threads or host_threads())
+    built = build_reference(cfg, cuda=False)
+    if built is None:
+        ups, mean, thr = cpu_oracle_throughput(batch, steps, warmup, threads)
+        return ups, mean, thr, "port"
+    ns, model, opt = built
+    g = torch.Generator().manual_seed(0)
+    src = torch.randn(batch, 1, cfg.freq, spec["t_src"], generator=g)
+    tgt = torch.randint(3, cfg.vocab, (batch, cfg.tgt_max_len - 1), generator=g)
+    lens = torch.full((batch,), spec["t_src"], dtype=torch.int32)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        reference_step(ns, model, opt, src, lens, tgt, cfg.label_smoothing)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    mean = sum(times) / len(times)
+    return batch / mean, mean, torch.get_num_threads(), "reference"
+
+
+def gpu_reference_throughput(dev, batch, steps=5, warmup=3):
+    """The unmodified reference, eager, ON THE SAME B200 ("the kernel-for-kernel bar"): same step as
+    reference_step, inputs resident on the device, CUDA-event timed; once with PyTorch's default flags (cuDNN convolutions
+    may use TF32, matmuls are fp32) and once with allow_tf32 everywhere.  None when the checkout is not staged."""
+    import b200asr
+    spec = b200asr.BASELINE_CONFIGS[WORKLOAD]
+    cfg = spec["cfg"]
+    out = {}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for name, conv_tf32, mm_tf32 in (("fp32_strict", False, False), ("torch_default", True, False), ("allow_tf32", True, True)):
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = conv_tf32, mm_tf32
+            built = build_reference(cfg, cuda=True)
+            if built is None:
+                return None
+            ns, model, opt = built
+            g = torch.Generator().manual_seed(0)
+            src = torch.randn(batch, 1, cfg.freq, spec["t_src"], generator=g).to(dev)
+            tgt = torch.randint(3, cfg.vocab, (batch, cfg.tgt_max_len - 1), generator=g).to(dev)
+            lens = torch.full((batch,), spec["t_src"], dtype=torch.int32)
+            for _ in range(warmup):
+                reference_step(ns, model, opt, src, lens, tgt, cfg.label_smoothing)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                loss = reference_step(ns, model, opt, src, lens, tgt, cfg.label_smoothing)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"ms_per_step": ms, "value": batch / (ms / 1e3), "unit": "utt/s", "cudnn_allow_tf32": conv_tf32,
+                         "matmul_allow_tf32": mm_tf32, "loss": float(loss.item())}
+            del model, opt, src, tgt
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    out["note"] = (f"unmodified reference (oracle/_ref) eager on this GPU, batch {batch}, zero_grad+fwd+calculate_metrics+bwd+"
+                   f"NoamOpt/Adam step, {steps} timed steps after {warmup} warm-up; torch {torch.__version__}")
+    return out
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     b = 8            # bounded sample: a quarter of the cfg2 batch per step (~3 s of CPU work), enough rows to keep all cores busy
-    ups, mean, threads = cpu_oracle_throughput(b, args.steps, args.warmup)
+    ups, mean, threads, kind = cpu_reference_throughput(b, args.steps, args.warmup)
+    what = "the unmodified reference (oracle/_ref)" if kind == "reference" else "oracle port"
     out = {"impl": "reference", "metric": METRIC, "value": ups, "unit": "utt/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": WORKLOAD, "sample": f"{b} utterances per step of the cfg2 shape (T_src=800, T_tgt=100)"},
-           "cpu_baseline": {"value": ups, "unit": "utt/s", "cores": threads, "kind": "port",
-                            "sample": f"oracle fwd+bwd on {b} utterances/step, {args.steps} steps"},
+           "config": {"workload": WORKLOAD, "sample": f"{b} utterances per step of the cfg2 shape (T_src=800, T_tgt=100)",
+                      "step": "zero_grad+fwd+CE+bwd+adam", "dropout": 0.1, "label_smoothing": 0.1},
+           "cpu_baseline": {"value": ups, "unit": "utt/s", "cores": threads, "kind": kind,
+                            "sample": f"{what}: training step on {b} utterances/step, {args.steps} steps"},
            "e2e": {"value": ups, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
@@ -277,18 +384,44 @@ def run_b200(args, rank, local_rank, world):
     ms_e2e = max(max_over_ranks(e0.elapsed_time(e1)) / args.steps, 0.0)
     final_loss = float(loss_h.item())
 
+    # ---- the gradient all-reduce alone (N > 1): CUDA events around dp.all_reduce(), max over ranks
+    allreduce = None
+    if world > 1:
+        for _ in range(3):
+            dp.all_reduce()
+        barrier()
+        e0.record()
+        for _ in range(10):
+            dp.all_reduce()
+        e1.record()
+        barrier()
+        ar_ms = max_over_ranks(e0.elapsed_time(e1)) / 10
+        nbytes = dp.flat.flat_grad.numel() * 4
+        allreduce = {"ms": ar_ms, "bytes": nbytes, "algbw_gbs": nbytes / ar_ms / 1e6, "busbw_gbs": nbytes / ar_ms / 1e6 * 2 * (world - 1) / world,
+                     "note": "one all-reduce(SUM) of the flat fp32 gradient buffer + [sum-loss, n_tokens], timed back to back"}
+
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     peaks = load_peaks()
     groups = summarize_profile(report, prof_steps, peaks)
     top = next((g for g in groups if g["gflop_per_step"] > 0), groups[0])
     tf32_peak = peaks["bf16_tflops_sustained"] / 2.0       # kind::tf32 runs at half the bf16 rate
-    # DRAM bytes per launch (dram__bytes_read + dram__bytes_write) from the ncu --set full captures of this code under
-    # profiles/ (engine_WgradPolicy_r1b.md, conv_halo_r1.md), averaged over the launches of the group at cfg2
-    ncu_traffic = {"conv3x3_bwd_weight": (1.0891e9 + 0.8074e9 + 2.4947e9) / 3.0}
+    # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant group come from the tracked ncu
+    # summary profiles/ncu_traffic.json (written by tools/ncu_traffic.py from an `ncu --set full` capture of this very
+    # command; it records the git revision it was taken at) -- null when that file has no entry for the group
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tj = json.load(f)
+        ent = tj.get("groups", {}).get(top["kernel"])
+        if ent:
+            traffic, traffic_src = ent["dram_bytes_per_launch"], f"profiles/ncu_traffic.json (git {tj.get('git', '?')}, {ent.get('launches', '?')} launches)"
+    except Exception:
+        pass
     roof = {"bound": "tensor", "kernel": top["kernel"], "achieved": top["tflops"], "peak": tf32_peak, "unit": "TFLOP/s",
-            "frac": top["tflops"] / tf32_peak, "traffic": ncu_traffic.get(top["kernel"]),
-            "traffic_note": "bytes per launch from profiles/ (ncu); algorithmic x + dy bytes of the three layers average 1.25e9",
+            "frac": top["tflops"] / tf32_peak, "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": f"{peaks['source']} bf16_tflops_sustained/2 (TF32 = half the bf16 tensor rate)",
             "share_of_step": top["share"],
             # 3xTF32 issues three tf32 MMAs per algorithmic product, so `frac` tops out at 1/3 for precision-3 kernels;
@@ -318,10 +451,18 @@ def run_b200(args, rank, local_rank, world):
                    "d2h_bytes_per_step": world * 4, "ms_per_step": ms_e2e, "wall_ms_per_step": wall_ms},
            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "attention_roofline": attention, "kernels": groups[:24], "profiled_ms_per_step": ms_prof,
            "final_loss": final_loss}
+    if world == 1 and not args.no_ref_gpu:
+        try:
+            out["reference_gpu"] = gpu_reference_throughput(dev, B)
+        except Exception as e:                      # the reference eager run must never take the product line down
+            out["reference_gpu"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    if allreduce is not None:
+        out["allreduce"] = allreduce
     if world == 1 and not args.no_cpu:
-        ups, mean, threads = cpu_oracle_throughput(2, 2, 1)
-        out["cpu_baseline"] = {"value": ups, "unit": "utt/s", "cores": threads, "kind": "port",
-                               "sample": "oracle fwd+bwd, 2 utterances of the cfg2 shape per step, 2 timed steps"}
+        ups, mean, threads, kind = cpu_reference_throughput(4, 3, 1)
+        out["cpu_baseline"] = {"value": ups, "unit": "utt/s", "cores": threads, "kind": kind,
+                               "sample": ("the unmodified reference (oracle/_ref)" if kind == "reference" else "oracle port") +
+                                         ": training step, 4 utterances of the cfg2 shape per step, 3 timed steps after 1 warm-up"}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -336,6 +477,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (debug only; the metric uses 32)")
     ap.add_argument("--precision", default="", help="linear,conv,attn[,conv_wgrad[,attn_bwd]] in {fp32,tf32,tf32x3} (default: package default)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip timing the unmodified reference eager on this GPU")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

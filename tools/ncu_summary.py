@@ -57,5 +57,47 @@ def full(src, dst):
     print("wrote", dst)
 
 
+# C-ABI kernel group (bench.py's roofline.kernel) -> substrings of the kernel names that implement it
+GROUPS = {"conv3x3_bwd_weight": ["WgradPolicy"], "conv3x3_fwd": ["tc_conv3x3_halo"], "conv3x3_bwd_data": ["tc_conv3x3_halo"],
+          "linear_fwd": ["GemmPolicy<false, false"], "linear_bwd_data": ["GemmPolicy<false, true"], "linear_bwd_weight": ["GemmPolicy<true, true"],
+          "sdpa_mat_fwd": ["BGemmPolicy", "softmax_fwd"], "sdpa_mat_bwd": ["BGemmPolicy", "softmax_bwd"],
+          "sdpa_fused_fwd": ["sdpa_fused_fwd"], "sdpa_fused_bwd": ["sdpa_fused_bwd"]}
+
+
+def traffic(src, dst):
+    """profiles/ncu_traffic.json: DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of every kernel in an
+    `ncu --set full` (or --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum) capture of bench.py,
+    per kernel and per C-ABI group; bench.py reads `roofline.traffic` from it."""
+    import json
+    import os
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    ti = hdr.index("gpu__time_duration.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tscale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
+    kern = OrderedDict()
+    for r in rows[2:]:
+        name = r[ki].split("(")[0].replace("void ", "").replace("b200asr::", "").replace("tc::", "")
+        b = float(r[ri].replace(",", "")) * scale[units[ri]] + float(r[wi].replace(",", "")) * scale[units[wi]]
+        t = float(r[ti].replace(",", "")) * tscale[units[ti]]
+        n, sb, st = kern.get(name, (0, 0.0, 0.0))
+        kern[name] = (n + 1, sb + b, st + t)
+    groups = {}
+    for g, subs in GROUPS.items():
+        sel = [(n, sb, st) for name, (n, sb, st) in kern.items() if any(x in name for x in subs)]
+        if sel:
+            n = sum(x[0] for x in sel)
+            groups[g] = {"launches": n, "dram_bytes_per_launch": sum(x[1] for x in sel) / n, "us_per_launch_under_ncu": sum(x[2] for x in sel) / n}
+    git = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True, cwd=os.path.dirname(os.path.abspath(__file__))).stdout.strip()
+    doc = {"git": git, "source": os.path.basename(src), "how": "ncu --clock-control none, dram__bytes_read.sum + dram__bytes_write.sum per launch",
+           "groups": groups,
+           "kernels": {k: {"launches": n, "dram_bytes_per_launch": sb / n, "us_per_launch_under_ncu": st / n} for k, (n, sb, st) in kern.items()}}
+    with open(dst, "w") as f:
+        json.dump(doc, f, indent=1)
+    print("wrote", dst, "groups:", {g: "%.3g B" % v["dram_bytes_per_launch"] for g, v in groups.items()})
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
