@@ -17,6 +17,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "b200asr.h")
 _lib = None
 
 PREC_FP32, PREC_TF32, PREC_TF32X3 = 0, 1, 3
+PREC_BF16, PREC_BF16X3 = 2, 6          # kind::f16 modes (include/b200asr.h)
 
 _vp, _i, _f, _u64, _ll, _sz = C.c_void_p, C.c_int, C.c_float, C.c_uint64, C.c_longlong, C.c_size_t
 
@@ -29,6 +30,7 @@ SIGNATURES = {
     "b200asr_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "b200asr_linear_bwd_data": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "b200asr_split_tf32": (_i, [_vp, _vp, _ll, _vp]),
+    "b200asr_split_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "b200asr_linear_bwd_weight": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200asr_add_ln_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _u64, _u64, _vp]),
     "b200asr_add_ln_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _u64, _u64, _i, _vp]),

@@ -14,7 +14,9 @@ int launch_colsum(const float* X, float* out, int M, int N, int accumulate, cuda
 // shape/alignment cannot be expressed as TMA tiles (callers turn that into an error, never a fallback).
 int gemm_tc(const float* A, bool a_kmaj, int lda, const float* B, bool b_kmaj, int ldb, float* C, int ldc, int M,
             int N, int K, const float* bias, int relu, const float* relu_mask, int accumulate, int nsplit,
-            cudaStream_t st, const float* b_split = nullptr, int b_rows = 0, float* rowsum = nullptr);
+            cudaStream_t st, const void* b_split = nullptr, int b_rows = 0, float* rowsum = nullptr);
+// nsplit = 2 (bf16) / 6 (bf16x3): A must be K-major fp32; B is ignored and b_split is REQUIRED: the K-major bf16 operand
+// [1 or 2][b_rows][ldb] (ldb % 8 == 0) written by b200asr_split_bf16.
 // rowsum: optional [M] += sum_k A(m,k), fused into the kernel when both operands are MN-major and nsplit == 3 (the
 // bias gradient of the weight-gradient GEMM); gemm_tc_fuses_rowsum() tells the caller whether it will be.
 bool gemm_tc_fuses_rowsum(bool a_kmaj, bool b_kmaj, int nsplit);

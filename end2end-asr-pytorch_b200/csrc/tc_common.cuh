@@ -185,6 +185,55 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
       : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------- bf16 operands (kind::f16)
+// 2-term bf16 split ("bf16x3"): x ~ hi + lo with hi = bf16(x), lo = bf16(x - hi) -- 16 significant bits, |x - hi - lo| <=
+// 2^-18 |x| -- and hi*hi + hi*lo + lo*hi per product: three kind::f16 MMAs at TWICE the tf32 rate with half the operand
+// bytes in shared memory.  Error per product ~2^-17 (dropped lo*lo and the representation error), i.e. ~100x below
+// single-pass TF32 and ~30x above 3xTF32.  Rounding is done with integer adds on the ALU pipe (round to nearest, ties away),
+// like the tf32 split: bf16(x) = top 16 bits of (bits(x) + 0x8000).
+// pack2(a, b): 32-bit word with bf16(a) in the low half (element k) and bf16(b) in the high half (element k + 1) -- the
+// order in which a TMEM column holds two consecutive-k elements of a 16-bit A operand.
+__device__ __forceinline__ void split_bf16_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const uint32_t r0 = __float_as_uint(x0) + 0x8000u, r1 = __float_as_uint(x1) + 0x8000u;
+  hi = __byte_perm(r0, r1, 0x7632);
+  const float l0 = x0 - __uint_as_float(r0 & 0xFFFF0000u), l1 = x1 - __uint_as_float(r1 & 0xFFFF0000u);
+  lo = __byte_perm(__float_as_uint(l0) + 0x8000u, __float_as_uint(l1) + 0x8000u, 0x7632);
+}
+__device__ __forceinline__ uint32_t pack_bf16_pair(float x0, float x1) {
+  return __byte_perm(__float_as_uint(x0) + 0x8000u, __float_as_uint(x1) + 0x8000u, 0x7632);
+}
+// 32 lanes x 16 columns store of raw 32-bit words (registers -> TMEM)
+__device__ __forceinline__ void tmem_st16u(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem], bf16 operands (A: lane = row, one 32-bit column per TWO k elements), fp32 accumulate
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 operands
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor, SWIZZLE_128B.  Fields (bits): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
 // version=1 [46,48), base_offset [49,52) = 0 (tiles are 1024-byte aligned), layout [61,64) = 2 (128B swizzle).
@@ -192,7 +241,9 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
 //   MN-major fp32/tf32 tile: the only legal layout is "128B swizzle, 32-byte atoms" (layout type 1; TMA mode
 //   CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 128 B (32 fp32) contiguous along MN per k-line, swizzle period 4 k-lines
 //   (512 B).  Chunks of 32 MN-elements are LBO apart, groups of 4 k-lines SBO = 512 B apart.
-constexpr uint32_t kLayoutSW128 = 2, kLayoutSW128Base32B = 1;
+//   K-major bf16 tile with 64-byte rows (32 bf16; the 32-deep k-block of the bf16 modes): SWIZZLE_64B (layout type 4), 8-row
+//   groups 512 B apart -> SBO = 512; a k-step (16 bf16 = 32 B) advances the start address by 32 B, as in the tf32 tiles.
+constexpr uint32_t kLayoutSW128 = 2, kLayoutSW128Base32B = 1, kLayoutSW64 = 4;
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                                    uint32_t layout_type = 2, uint32_t base_offset = 0) {
   uint64_t d = 0;
@@ -212,6 +263,12 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool a_mn_m
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Instruction descriptor for kind::f16 with BF16 operands (a_format = b_format = 1) and fp32 accumulation; K = 16 per MMA.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // ---------------------------------------------------------------------------------------------- host: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -222,6 +279,10 @@ EncodeTiledFn get_encode_tiled();
 // fp32 -> tf32 in flight) instead of FLOAT32.  Returns 0 on success.
 int make_tensor_map_f32(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
                         const uint32_t* box, bool atom32b = false, bool tf32_dtype = false);
+
+// bf16 tensor (2 bytes / element), `rank` dims, strides in ELEMENTS; box[0] * 2 bytes = 64 -> SWIZZLE_64B, = 128 -> SWIZZLE_128B.
+int make_tensor_map_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                         const uint32_t* box);
 
 }  // namespace tc
 }  // namespace b200asr

@@ -31,6 +31,13 @@
 namespace b200asr {
 namespace tc {
 
+// NSPLIT selects the arithmetic: 1 = TF32 (SS-MMA), 3 = 3xTF32 (A split into TMEM, TS-MMA), and the kind::f16 modes
+// 2 = bf16 (A converted to bf16 into TMEM, one TS-MMA) and 6 = bf16x3 (2-term bf16 split, three TS-MMAs at twice the tf32
+// rate).  The bf16 modes need a K-major A tile (fp32, converted by the split warps) and a PRE-CONVERTED K-major bf16 B
+// operand ([hi] or [hi | lo], 64-byte rows, SWIZZLE_64B): Policy::load16 / Policy::b_desc16.
+constexpr bool eng_is_bf16(int nsplit) { return nsplit == 2 || nsplit == 6; }
+constexpr bool eng_has_split_warps(int nsplit) { return nsplit != 1; }
+
 constexpr int ENG_THREADS_X1 = 192;     // TMA, MMA, 4 epilogue warps
 constexpr int ENG_THREADS_X3 = 448;     // + 8 split warps
 constexpr int ENG_SPLIT_THREADS = 256;
@@ -44,8 +51,12 @@ constexpr int ENG_SPLIT_THREADS = 256;
 // tensor core no longer competes with the split for smem bandwidth on the A side (an SS 128x128x8 MMA reads 8 KB of smem
 // per 64 cycles = the full 128 B/clk of the SM).
 template <class Policy, int NSPLIT> struct EngineCfg {
-  static constexpr int kStageBytes = NSPLIT == 1 ? (Policy::kABytes + Policy::kBBytes) : (Policy::kABytes + 2 * Policy::kBBytes);
-  static constexpr int kMaxByTmem = NSPLIT == 1 ? 8 : (512 - 2 * Policy::BN) / 64;          // 64 TMEM columns of A per stage
+  static constexpr bool kBf16 = eng_is_bf16(NSPLIT);
+  static constexpr int kBHalves = (NSPLIT == 3 || NSPLIT == 6) ? 2 : 1;                     // B tiles per stage (hi | lo)
+  static constexpr int kBTile = kBf16 ? Policy::BN * 64 : Policy::kBBytes;                   // bf16: 32 k x 2 B = 64-byte rows
+  static constexpr int kACols = NSPLIT == 3 ? 64 : (NSPLIT == 6 ? 32 : (NSPLIT == 2 ? 16 : 0));   // TMEM columns of A per stage
+  static constexpr int kStageBytes = Policy::kABytes + kBHalves * kBTile;
+  static constexpr int kMaxByTmem = NSPLIT == 1 ? 8 : (512 - 2 * Policy::BN) / kACols;
   static constexpr int kBySmem = (200 * 1024) / kStageBytes;
 #ifndef ENG_MAX_STAGES
 #define ENG_MAX_STAGES 8
@@ -54,13 +65,16 @@ template <class Policy, int NSPLIT> struct EngineCfg {
   static constexpr int kStagesCap = kStagesRaw > ENG_MAX_STAGES ? ENG_MAX_STAGES : kStagesRaw;
   static constexpr int kStages = NSPLIT == 1 ? kStagesCap : kStagesCap - kStagesCap % ENG_SPLIT_GROUPS;
   static constexpr int kOffBhi = Policy::kABytes;
-  static constexpr int kOffBlo = kOffBhi + Policy::kBBytes;
+  static constexpr int kOffBlo = kOffBhi + kBTile;
   static constexpr int kBarOff = kStages * kStageBytes;
   static constexpr int kSmemBytes = kBarOff + 512 + 1024;
   static constexpr int kAccCols = 2 * Policy::BN;
-  static constexpr int kTmemCols = NSPLIT == 3 ? 512 : (kAccCols <= 32 ? 32 : (kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : 256)));
-  static constexpr int kTxBytes = Policy::kABytes + Policy::kBBytes +
-                                  (NSPLIT == 3 && !Policy::kSplitB ? Policy::kBBytes : 0);   // pre-split B arrives as hi+lo
+  static constexpr int kTmemCols = NSPLIT != 1 ? 512 : (kAccCols <= 32 ? 32 : (kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : 256)));
+  static constexpr int kTxBytes = kBf16 ? Policy::kABytes + kBHalves * kBTile
+                                        : Policy::kABytes + Policy::kBBytes +
+                                          (NSPLIT == 3 && !Policy::kSplitB ? Policy::kBBytes : 0);   // pre-split B arrives as hi+lo
+  static_assert(!kBf16 || (!Policy::kAMN && !Policy::kBMN && !Policy::kSplitB),
+                "bf16 modes: K-major fp32 A (converted in the kernel) and a pre-converted K-major bf16 B");
   static_assert(kStages >= 2, "stage too large");
   // Each split group must see EVERY phase of the full barriers it waits on: mbarrier parity waits only distinguish the
   // current phase from the one before, so a group that skipped a phase of a stage could take a stale completion for the
@@ -69,7 +83,7 @@ template <class Policy, int NSPLIT> struct EngineCfg {
 };
 
 template <class Policy, int NSPLIT>
-__global__ void __launch_bounds__(NSPLIT == 1 ? ENG_THREADS_X1 : ENG_THREADS_X3, 1)
+__global__ void __launch_bounds__(eng_has_split_warps(NSPLIT) ? ENG_THREADS_X3 : ENG_THREADS_X1, 1)
 tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                  const typename Policy::Params p) {
   using Cfg = EngineCfg<Policy, NSPLIT>;
@@ -114,7 +128,8 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         mbar_wait(empty_bar(s), ((kbg / S) & 1) ^ 1);
         const uint32_t sa = smem_base + s * Cfg::kStageBytes;
         if (leader) mbar_expect_tx(full_bar(s), Cfg::kTxBytes);
-        Policy::load(p, tc, &mapA, &mapB, sa, sa + Cfg::kOffBhi, sa + Cfg::kOffBlo, full_bar(s), leader);
+        if constexpr (Cfg::kBf16) Policy::load16(p, tc, &mapA, &mapB, sa, sa + Cfg::kOffBhi, sa + Cfg::kOffBlo, full_bar(s), leader, Cfg::kBHalves);
+        else Policy::load(p, tc, &mapA, &mapB, sa, sa + Cfg::kOffBhi, sa + Cfg::kOffBlo, full_bar(s), leader);
         __syncwarp();
       }
     }
@@ -128,11 +143,19 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const bool leader = elect_one();
     constexpr uint32_t idesc = make_idesc_tf32(128, BN, Policy::kAMN, Policy::kBMN);
     constexpr uint32_t idesc_ts = make_idesc_tf32(128, BN, false, Policy::kBMN);
-    constexpr bool kNeedXfm = NSPLIT == 3;
-    constexpr uint32_t kStageStep = Cfg::kStageBytes >> 4, kLoStep = Policy::kBBytes >> 4;
-    const uint64_t bd0 = Policy::b_desc(smem_base + Cfg::kOffBhi, 0), ad0 = Policy::a_desc(smem_base, 0);
-    const uint32_t b_ks = (uint32_t)(Policy::b_desc(0, 1) - Policy::b_desc(0, 0));     // address-field step per 8-deep k-step
-    const uint32_t a_ks = (uint32_t)(Policy::a_desc(0, 1) - Policy::a_desc(0, 0));
+    constexpr bool kNeedXfm = NSPLIT != 1;
+    constexpr uint32_t idesc_bf = make_idesc_bf16(128, BN, false, false);
+    constexpr uint32_t kStageStep = Cfg::kStageBytes >> 4, kLoStep = Cfg::kBTile >> 4;
+    uint64_t bd0, ad0;
+    uint32_t b_ks, a_ks;
+    if constexpr (Cfg::kBf16) {
+      bd0 = Policy::b_desc16(smem_base + Cfg::kOffBhi, 0); ad0 = 0;
+      b_ks = (uint32_t)(Policy::b_desc16(0, 1) - Policy::b_desc16(0, 0)); a_ks = 0;   // address-field step per 16-deep k-step
+    } else {
+      bd0 = Policy::b_desc(smem_base + Cfg::kOffBhi, 0); ad0 = Policy::a_desc(smem_base, 0);
+      b_ks = (uint32_t)(Policy::b_desc(0, 1) - Policy::b_desc(0, 0));     // address-field step per 8-deep k-step
+      a_ks = (uint32_t)(Policy::a_desc(0, 1) - Policy::a_desc(0, 0));
+    }
     const uint32_t bd_hi = (uint32_t)(bd0 >> 32), ad_hi = (uint32_t)(ad0 >> 32);
     auto mk = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; };
     uint32_t s = 0, ph = 0, tcount = 0;
@@ -147,13 +170,21 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         tc_fence_after();
         if (leader) {
           const uint32_t b_lo32 = (uint32_t)bd0 + s * kStageStep, a_lo32 = (uint32_t)ad0 + s * kStageStep;
-          const uint32_t a_t = tmem_base + Cfg::kAccCols + s * 64;
+          const uint32_t a_t = tmem_base + Cfg::kAccCols + s * Cfg::kACols;
 #pragma unroll
-          for (int ks = 0; ks < 4; ks++) {
+          for (int ks = 0; ks < (Cfg::kBf16 ? 2 : 4); ks++) {
             const uint64_t b_hi = mk(bd_hi, b_lo32 + ks * b_ks);
             const uint32_t acc0 = (kb | ks) != 0 ? 1u : 0u;
-            if (NSPLIT == 1) {
+            if constexpr (NSPLIT == 1) {
               umma_tf32(d_tmem, mk(ad_hi, a_lo32 + ks * a_ks), b_hi, idesc, acc0);
+            } else if constexpr (NSPLIT == 2) {
+              umma_bf16_ts(d_tmem, a_t + ks * 8, b_hi, idesc_bf, acc0);          // 16 k = 8 packed columns per step
+            } else if constexpr (NSPLIT == 6) {
+              const uint64_t b_lo = mk(bd_hi, b_lo32 + kLoStep + ks * b_ks);
+              const uint32_t a_hi = a_t + ks * 8, a_lo = a_hi + 16;
+              umma_bf16_ts(d_tmem, a_lo, b_hi, idesc_bf, acc0);
+              umma_bf16_ts(d_tmem, a_hi, b_lo, idesc_bf, 1u);
+              umma_bf16_ts(d_tmem, a_hi, b_hi, idesc_bf, 1u);
             } else {
               const uint64_t b_lo = mk(bd_hi, b_lo32 + kLoStep + ks * b_ks);
               const uint32_t a_hi = a_t + ks * 8, a_lo = a_hi + 32;
@@ -197,7 +228,43 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
   } else {
     // ------------------------------------------------------------------ operand split warps (3xTF32 only)
-    if (NSPLIT == 3) {
+    if constexpr (Cfg::kBf16) {
+      // bf16 modes: the thread that owns A-tile row r reads its 32 fp32 k-values (128B-swizzled row), converts them to bf16
+      // (NSPLIT == 6: hi and lo of the 2-term split) and stores them PACKED, two k per 32-bit column, into TMEM.
+      constexpr int G = ENG_SPLIT_GROUPS, WPG = 8 / G;
+      static_assert(WPG == 4, "bf16 split: one thread per A row and group");
+      const int group = (warp - 6) / WPG;
+      const int quarter = warp & 3;
+      const int row = quarter * 32 + lane;
+      uint32_t kbg = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int nkb = Policy::num_kb(p, tile);
+        for (int kb = 0; kb < nkb; kb++, kbg++) {
+          if ((int)(kbg % G) != group) continue;
+          const int s = kbg % S;
+          mbar_wait(full_bar(s), (kbg / S) & 1);
+          const uint8_t* araw = gen_base + s * Cfg::kStageBytes;
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const float4 x = *reinterpret_cast<const float4*>(araw + row * 128 + ((j ^ (row & 7)) << 4));
+            if constexpr (NSPLIT == 6) {
+              split_bf16_pair(x.x, x.y, hi[2 * j], lo[2 * j]);
+              split_bf16_pair(x.z, x.w, hi[2 * j + 1], lo[2 * j + 1]);
+            } else {
+              hi[2 * j] = pack_bf16_pair(x.x, x.y);
+              hi[2 * j + 1] = pack_bf16_pair(x.z, x.w);
+            }
+          }
+          const uint32_t acol = tmem_base + ((uint32_t)(quarter * 32) << 16) + Cfg::kAccCols + s * Cfg::kACols;
+          tmem_st16u(acol, hi);
+          if constexpr (NSPLIT == 6) tmem_st16u(acol + 16, lo);
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(xfm_bar(s));
+        }
+      }
+    } else if (NSPLIT == 3) {
       // The smem -> registers -> TMEM chain of one k-block is a serial latency (LDS, tcgen05.st, wait::st, arrive), so the
       // warps are divided into groups that take alternating k-blocks: each thread handles a wider slice less often and the
       // chains of consecutive k-blocks overlap.
@@ -320,7 +387,7 @@ int launch_engine(const CUtensorMap& ma, const CUtensorMap& mb, const typename P
   if (int rc = ensure_dynamic_smem((const void*)kern, Cfg::kSmemBytes, attr_set, what)) return rc;
   if (ntiles <= 0) return B200ASR_OK;
   const int grid = min(ntiles, device_sm_count());
-  kern<<<grid, NSPLIT == 1 ? ENG_THREADS_X1 : ENG_THREADS_X3, Cfg::kSmemBytes, st>>>(ma, mb, p);
+  kern<<<grid, eng_has_split_warps(NSPLIT) ? ENG_THREADS_X3 : ENG_THREADS_X1, Cfg::kSmemBytes, st>>>(ma, mb, p);
   return check_launch(what);
 }
 

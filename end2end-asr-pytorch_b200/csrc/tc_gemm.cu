@@ -56,6 +56,23 @@ int make_tensor_map_f32(CUtensorMap* map, const void* base, int rank, const uint
   return B200ASR_OK;
 }
 
+int make_tensor_map_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                         const uint32_t* box) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return B200ASR_CUDA_ERROR; }
+  cuuint64_t gdim[5], gstride[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; i++) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
+  for (int i = 1; i < rank; i++) gstride[i - 1] = strides_elems[i - 1] * 2;
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
+  const CUtensorMapSwizzle sw = box[0] * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstride, bdim, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (bf16) failed with CUresult %d", (int)r); return B200ASR_CUDA_ERROR; }
+  return B200ASR_OK;
+}
+
 constexpr int GBM = 128, GBN = 128, GBK = 32;            // tile; k-block in fp32 elements (= 128 bytes)
 constexpr int TILE_BYTES = GBM * GBK * 4;                // 16 KB per operand per stage
 
@@ -111,6 +128,17 @@ struct GemmPolicy {
         for (int c = 0; c < 4; c++) tma_load_2d(dst + c * 4096, mapB, bar, n0 + 32 * c, k0 + roff);
     }
   }
+  // bf16 modes (engine NSPLIT 2 / 6): fp32 K-major A tile + pre-converted K-major bf16 B tile(s), 64-byte rows (SWIZZLE_64B)
+  static __device__ __forceinline__ void load16(const Params& p, Tile& t, const CUtensorMap* mapA, const CUtensorMap* mapB,
+                                                uint32_t sa, uint32_t sb, uint32_t sb_lo, uint32_t bar, bool leader, int halves) {
+    const int k0 = t.k0, m0 = t.m0, n0 = t.n0;
+    t.k0 += GBK;
+    if (!leader) return;
+    tma_load_2d(sa, mapA, bar, k0, m0);
+    tma_load_2d(sb, mapB, bar, k0, n0);
+    if (halves == 2) tma_load_2d(sb_lo, mapB, bar, k0, n0 + p.b_rows);
+  }
+  static __device__ __forceinline__ uint64_t b_desc16(uint32_t s, int ks) { return make_smem_desc(s + ks * 32, 16, 512, kLayoutSW64); }
   // every (row, k) of A is staged once by the n-tile-0 tiles (over all k-splits)
   static __device__ __forceinline__ bool want_sums(const Params& p, const Tile& t) { return p.e.rowsum != nullptr && t.n0 == 0; }
   static __device__ __forceinline__ void sum_a_store(const Params& p, const Tile& t, int r, float v) {
@@ -205,12 +233,33 @@ bool gemm_tc_fuses_rowsum(bool a_kmaj, bool b_kmaj, int nsplit) { return !a_kmaj
 
 int gemm_tc(const float* A, bool a_kmaj, int lda, const float* B, bool b_kmaj, int ldb, float* C, int ldc, int M, int N,
             int K, const float* bias, int relu, const float* relu_mask, int accumulate, int nsplit, cudaStream_t st,
-            const float* b_split, int b_rows, float* rowsum) {
+            const void* b_split, int b_rows, float* rowsum) {
   using namespace tc;
-  const bool presplit = b_split != nullptr && nsplit == 3 && a_kmaj;   // fwd (B K-major) and dgrad (B MN-major)
-  if (presplit) B = b_split;
   if (M <= 0 || N <= 0) return B200ASR_OK;
-  B200_REQUIRE(nsplit == 1 || nsplit == 3, B200ASR_BAD_ARG, "gemm_tc: nsplit must be 1 or 3");
+  if (eng_is_bf16(nsplit)) {
+    // kind::f16 modes: fp32 K-major A converted in the kernel, pre-converted K-major bf16 B
+    B200_REQUIRE(a_kmaj && b_split && b_rows >= N, B200ASR_BAD_ARG, "gemm_tc (bf16): needs a K-major A and the bf16 operand from b200asr_split_bf16");
+    B200_REQUIRE(aligned16(A) && aligned16(b_split) && lda % 4 == 0 && ldb % 8 == 0, B200ASR_BAD_SHAPE,
+                 "gemm_tc (bf16): TMA needs 16-byte row pitches (lda=%d must be a multiple of 4, ldb=%d of 8)", lda, ldb);
+    B200_REQUIRE(!rowsum, B200ASR_BAD_ARG, "gemm_tc (bf16): no fused row sums");
+    CUtensorMap ma, mb;
+    {
+      uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}, strides[1] = {(uint64_t)lda};
+      uint32_t box[2] = {GBK, GBM};
+      if (int rc = make_tensor_map_f32(&ma, A, 2, dims, strides, box, false, false)) return rc;
+    }
+    {
+      uint64_t dims[2] = {(uint64_t)K, (uint64_t)(nsplit == 6 ? 2 : 1) * b_rows}, strides[1] = {(uint64_t)ldb};
+      uint32_t box[2] = {GBK, GBN};
+      if (int rc = make_tensor_map_bf16(&mb, b_split, 2, dims, strides, box)) return rc;
+    }
+    EpiP e{C, ldc, M, N, K, bias, relu_mask, relu, accumulate, 1, ceil_div(K, GBK) * GBK, nullptr};
+    if (nsplit == 6) return launch_persistent<false, false, 6, true>(ma, mb, e, st, b_rows);
+    return launch_persistent<false, false, 2, true>(ma, mb, e, st, b_rows);
+  }
+  const bool presplit = b_split != nullptr && nsplit == 3 && a_kmaj;   // fwd (B K-major) and dgrad (B MN-major)
+  if (presplit) B = (const float*)b_split;
+  B200_REQUIRE(nsplit == 1 || nsplit == 3, B200ASR_BAD_ARG, "gemm_tc: nsplit must be 1, 3 (tf32) or 2, 6 (bf16)");
   B200_REQUIRE(aligned16(A) && aligned16(B) && lda % 4 == 0 && ldb % 4 == 0, B200ASR_BAD_SHAPE,
                "gemm_tc: TMA needs 16-byte aligned operands and leading dimensions that are multiples of 4 (lda=%d ldb=%d); "
                "use precision 0 for this shape", lda, ldb);

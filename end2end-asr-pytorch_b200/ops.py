@@ -13,7 +13,8 @@ import torch
 from . import _lib as L
 
 # ----------------------------------------------------------------------------------------------- configuration
-_PREC_NAMES = {"fp32": L.PREC_FP32, "tf32": L.PREC_TF32, "tf32x3": L.PREC_TF32X3}
+_PREC_NAMES = {"fp32": L.PREC_FP32, "tf32": L.PREC_TF32, "tf32x3": L.PREC_TF32X3, "bf16": L.PREC_BF16, "bf16x3": L.PREC_BF16X3}
+_BF16_PRECS = (L.PREC_BF16, L.PREC_BF16X3)
 
 
 class _Config:
@@ -28,7 +29,7 @@ class _Config:
     because dP - delta cancels in TF32) -- neither meets the 1e-3 gradient bar, so they are opt-in only."""
 
     def __init__(self):
-        self.linear = _PREC_NAMES[os.environ.get("B200ASR_LINEAR", "tf32x3")]
+        self.linear = _PREC_NAMES[os.environ.get("B200ASR_LINEAR", "tf32x3")]      # + "bf16x3" / "bf16" (kind::f16 modes)
         self.conv = _PREC_NAMES[os.environ.get("B200ASR_CONV", "tf32x3")]
         self.conv_wgrad = _PREC_NAMES[os.environ.get("B200ASR_CONV_WGRAD", "tf32x3")]
         self.attn = _PREC_NAMES[os.environ.get("B200ASR_ATTN", "tf32x3")]
@@ -140,21 +141,37 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------------------------- dense layers
-def split_weight(w2, prec):
-    """[2,N,K] = (rn_tf32(w), w - hi) for the 3xTF32 GEMM (done once per step and weight; the backward reuses it)."""
-    if prec != L.PREC_TF32X3:
-        return None
-    ws = torch.empty((2,) + tuple(w2.shape), device=w2.device, dtype=torch.float32)
-    L.check(_lib().b200asr_split_tf32(L.ptr(w2), L.ptr(ws), w2.numel(), _stream()), "split_tf32")
-    return ws
+class WSplit:
+    """Tensor-core operand copies of one weight matrix, made once per step and shared by forward and backward:
+    `fwd` feeds y = x w^T, `bwd` feeds dx = dy w.  3xTF32: one fp32 [2,N,K] = (rn_tf32(w), w - hi) for both.  bf16 modes:
+    bf16 [terms,N,K] and the transposed [terms,K,N8] (so that both GEMMs see a K-major B operand)."""
+    __slots__ = ("fwd", "bwd")
+
+    def __init__(self, fwd, bwd):
+        self.fwd, self.bwd = fwd, bwd
+
+
+def split_weight(w2, prec, need_bwd=True):
+    if prec == L.PREC_TF32X3:
+        ws = torch.empty((2,) + tuple(w2.shape), device=w2.device, dtype=torch.float32)
+        L.check(_lib().b200asr_split_tf32(L.ptr(w2), L.ptr(ws), w2.numel(), _stream()), "split_tf32")
+        return WSplit(ws, ws)
+    if prec in _BF16_PRECS:
+        N, K = w2.shape
+        terms = 2 if prec == L.PREC_BF16X3 else 1
+        fwd = torch.empty((terms, N, K), device=w2.device, dtype=torch.bfloat16)
+        bwd = torch.empty((terms, K, (N + 7) // 8 * 8), device=w2.device, dtype=torch.bfloat16) if need_bwd else None
+        L.check(_lib().b200asr_split_bf16(L.ptr(w2), L.ptr(fwd), L.ptr(bwd), N, K, terms, _stream()), "split_bf16")
+        return WSplit(fwd, bwd)
+    return None
 
 
 def linear_fwd(x2, w, b, relu, prec, w_split=None):
     M, K = x2.shape
     N = w.shape[0]
     y = torch.empty((M, N), device=x2.device, dtype=torch.float32)
-    L.check(_lib().b200asr_linear_fwd(L.ptr(x2), L.ptr(w), L.ptr(b), L.ptr(y), M, N, K, int(relu), prec, L.ptr(w_split),
-                                      _stream()), "linear_fwd")
+    L.check(_lib().b200asr_linear_fwd(L.ptr(x2), L.ptr(w), L.ptr(b), L.ptr(y), M, N, K, int(relu), prec,
+                                      L.ptr(w_split.fwd if w_split is not None else None), _stream()), "linear_fwd")
     return y
 
 
@@ -163,7 +180,7 @@ def linear_bwd_data(dy2, w, relu_out, prec, w_split=None):
     K = w.shape[1]
     dx = torch.empty((M, K), device=dy2.device, dtype=torch.float32)
     L.check(_lib().b200asr_linear_bwd_data(L.ptr(dy2), L.ptr(w), L.ptr(relu_out), L.ptr(dx), M, N, K, 0, prec,
-                                           L.ptr(w_split), _stream()), "linear_bwd_data")
+                                           L.ptr(w_split.bwd if w_split is not None else None), _stream()), "linear_bwd_data")
     return dx
 
 
@@ -199,8 +216,14 @@ def linear_bwd_weight(dy2, x2, want_bias, prec, w_sink=None, b_sink=None):
 
 def _linear_prec(N, K):
     """Shape rule (documented in DESIGN.md, not a fallback): TMA needs 16-byte row pitches, i.e. N % 4 == 0 and
-    K % 4 == 0; other shapes (e.g. dim_input = 161 with feat_extractor='') run on the fp32 CUDA-core GEMM."""
-    return config.linear if (N % 4 == 0 and K % 4 == 0) else L.PREC_FP32
+    K % 4 == 0 for fp32 operands (other shapes, e.g. dim_input = 161 with feat_extractor='', run on the fp32 CUDA-core
+    GEMM) and additionally K % 8 == 0 for the bf16 weight operand of the kind::f16 modes (else the matching tf32 grade)."""
+    if not (N % 4 == 0 and K % 4 == 0):
+        return L.PREC_FP32
+    prec = config.linear
+    if prec in _BF16_PRECS and K % 8 != 0:
+        prec = L.PREC_TF32X3 if prec == L.PREC_BF16X3 else L.PREC_TF32
+    return prec
 
 
 class LinearFn(torch.autograd.Function):
@@ -212,16 +235,18 @@ class LinearFn(torch.autograd.Function):
         w2 = _f32c(w.reshape(w.shape[0], -1))
         x2 = _f32c(x).reshape(-1, w2.shape[1])
         ctx.prec = _linear_prec(w2.shape[0], w2.shape[1])
-        ws = split_weight(w2, ctx.prec)
+        ws = split_weight(w2, ctx.prec, need_bwd=ctx.needs_input_grad[0])
         y = linear_fwd(x2, w2, b, False, ctx.prec, ws)
-        ctx.save_for_backward(x2, w2, ws)
+        ctx.save_for_backward(x2, w2)
+        ctx.ws = ws
         ctx.xshape, ctx.wshape, ctx.has_bias = x.shape, w.shape, b is not None
         ctx.params = (w, b)
         return y.view(*x.shape[:-1], w2.shape[0])
 
     @staticmethod
     def backward(ctx, dy):
-        x2, w2, ws = ctx.saved_tensors
+        x2, w2 = ctx.saved_tensors
+        ws, ctx.ws = ctx.ws, None
         dy2 = _f32c(dy).reshape(-1, w2.shape[0])
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
@@ -246,14 +271,16 @@ class FFNFn(torch.autograd.Function):
         ws1, ws2 = split_weight(w1m, ctx.prec), split_weight(w2m, ctx.prec)
         h = linear_fwd(x2, w1m, b1, True, ctx.prec, ws1)
         y = linear_fwd(h, w2m, b2, False, ctx.prec, ws2)
-        ctx.save_for_backward(x2, h, w1m, w2m, ws1, ws2)
+        ctx.save_for_backward(x2, h, w1m, w2m)
+        ctx.ws = (ws1, ws2)
         ctx.shapes = (x.shape, w1.shape, w2.shape)
         ctx.params = (w1, b1, w2, b2)
         return y.view(*x.shape[:-1], w2m.shape[0])
 
     @staticmethod
     def backward(ctx, dy):
-        x2, h, w1m, w2m, ws1, ws2 = ctx.saved_tensors
+        x2, h, w1m, w2m = ctx.saved_tensors
+        (ws1, ws2), ctx.ws = ctx.ws, None
         xs, w1s, w2s = ctx.shapes
         dy2 = _f32c(dy).reshape(-1, w2m.shape[0])
         w1, b1, w2, b2 = ctx.params
@@ -673,7 +700,7 @@ def _conv_geom(x, w, geom):
     KH, KW, SH, SW, PH, PW = geom
     OH, OW = (H + 2 * PH - KH) // SH + 1, (W + 2 * PW - KW) // SW + 1
     K = Ci * KH * KW
-    return B, Ci, H, W, w.shape[0], OH, OW, K, (K + 3) // 4 * 4
+    return B, Ci, H, W, w.shape[0], OH, OW, K, (K + 7) // 8 * 8      # K padded to 8: legal row pitch for fp32 and bf16 operands
 
 
 def _im2col(x, geom, Kp):

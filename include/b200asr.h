@@ -39,6 +39,11 @@ extern "C" {
 #define B200ASR_PREC_FP32 0
 #define B200ASR_PREC_TF32 1
 #define B200ASR_PREC_TF32X3 3
+/* kind::f16 tensor-core modes (fp32 in HBM, operands converted on the way into the tensor core, fp32 accumulate):
+ * BF16 = one bf16 MMA per product (BASELINE.json cfg5 asks for bf16); BF16X3 = 2-term bf16 split x ~ hi + lo (16 significant
+ * bits) with hi*hi + hi*lo + lo*hi -- three MMAs at twice the TF32 rate, product error ~2^-17 (between TF32 and 3xTF32). */
+#define B200ASR_PREC_BF16 2
+#define B200ASR_PREC_BF16X3 6
 
 typedef void* b200asr_stream_t; /* cudaStream_t */
 
@@ -58,14 +63,20 @@ unsigned long long b200asr_launch_count(void);
  * y[M,N] = act(x[M,K] * w[N,K]^T + bias[N]);  bias may be NULL; relu != 0 applies max(0, .)
  */
 int b200asr_linear_fwd(const float* x, const float* w, const float* bias, float* y, int M, int N, int K,
-                       int relu, int precision, const float* w_split, b200asr_stream_t stream);
+                       int relu, int precision, const void* w_split, b200asr_stream_t stream);
 /* dx[M,K] (+)= (dy[M,N] * w[N,K]) .* (relu_out[M,K] > 0 if relu_out != NULL) */
 int b200asr_linear_bwd_data(const float* dy, const float* w, const float* relu_out, float* dx, int M, int N,
-                            int K, int accumulate, int precision, const float* w_split, b200asr_stream_t stream);
-/* w_split (optional, precision 3 only): the weight pre-split for the 3xTF32 path by b200asr_split_tf32 --
- * [2][N][K] = hi = rn_tf32(w) followed by lo = w - hi.  Passing it removes the per-tile weight split from the GEMM
- * (the forward's split is reused by the backward); NULL keeps the split inside the kernel. */
+                            int K, int accumulate, int precision, const void* w_split, b200asr_stream_t stream);
+/* w_split, precision 3 (optional): the weight pre-split for the 3xTF32 path by b200asr_split_tf32 --
+ * [2][N][K] fp32 = hi = rn_tf32(w) followed by lo = w - hi.  Passing it removes the per-tile weight split from the GEMM
+ * (the forward's split is reused by the backward); NULL keeps the split inside the kernel.
+ * w_split, precisions 2 / 6 (REQUIRED): the weight converted to bf16 by b200asr_split_bf16 -- linear_fwd takes `dst`
+ * ([terms][N][K], needs K % 8 == 0), linear_bwd_data takes the transposed `dst_t` ([terms][K][N8], N8 = N rounded up to 8). */
 int b200asr_split_tf32(const float* src, float* dst_hi_lo, long long n, b200asr_stream_t stream);
+/* w [N,K] fp32 -> bf16 operands of the kind::f16 GEMMs: terms = 1: hi = bf16(w); terms = 2: hi followed by lo = bf16(w - hi).
+ * dst [terms][N][K] (K-major for y = x w^T) and/or dst_t [terms][K][N8] (K-major for dx = dy w; zero padded columns);
+ * either may be NULL. */
+int b200asr_split_bf16(const float* w, void* dst, void* dst_t, int N, int K, int terms, b200asr_stream_t stream);
 /* dw[N,K] (+)= dy[M,N]^T * x[M,K];  dbias[N] (+)= column sums of dy (dbias may be NULL) */
 int b200asr_linear_bwd_weight(const float* dy, const float* x, float* dw, float* dbias, int M, int N, int K,
                               int accumulate, int precision, b200asr_stream_t stream);

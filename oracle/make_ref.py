@@ -21,6 +21,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.environ.get("B200ASR_REFERENCE_SRC", "/root/reference")
 DST = os.path.join(HERE, "_ref")
 PARTS = ["models", "utils", "trainer", os.path.join("data", "labels")]
+FILES = [os.path.join("data", "__init__.py"), os.path.join("data", "helper.py")]     # utils/metrics.py:7 imports data.helper
 
 
 def stage(verbose=True):
@@ -42,7 +43,16 @@ def stage(verbose=True):
                 if not (os.path.exists(d) and filecmp.cmp(s, d, shallow=False)):
                     shutil.copyfile(s, d)
                 n += 1
-    # data/__init__.py is not needed: only data/labels/*.json are read (train.py:47-57)
+    for rel in FILES:
+        s, d = os.path.join(SRC, rel), os.path.join(DST, rel)
+        if os.path.exists(s):
+            os.makedirs(os.path.dirname(d), exist_ok=True)
+            if not (os.path.exists(d) and filecmp.cmp(s, d, shallow=False)):
+                shutil.copyfile(s, d)
+            n += 1
+        elif rel.endswith("__init__.py"):
+            os.makedirs(os.path.dirname(d), exist_ok=True)
+            open(d, "a").close()                      # namespace marker only (the reference has no data/__init__.py)
     if verbose:
         print(f"make_ref: {n} files of the unmodified reference staged in {DST}")
     return n

@@ -487,7 +487,7 @@ def test_greedy_decode_matches_reference_greedy_search_fixture(b200):
     ids_cached = dec.greedy_decode_cached(enc.cuda(), steps=300).cpu()
     ids_stop = dec.greedy_decode_cached(enc.cuda(), steps=300, stop_at_eos=True).cpu()
     ids_full = dec.greedy_decode_ids(enc.cuda(), steps=64).cpu()
-    band = 1e-3 * float(margins.abs().max())
+    band = 1e-4 * float(margins.abs().max())             # ~7e-4 on logits of magnitude ~15: a few times the fp32-grade error
     for b in range(enc.shape[0]):
         n = int(ref_len[b])
         safe = int((margins[b] > band).long().cumprod(0).sum())          # steps before the first near-tie
