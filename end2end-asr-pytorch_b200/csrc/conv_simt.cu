@@ -562,6 +562,30 @@ int b200asr_conv3x3_c1_bwd_weight(const float* x, const float* dy, float* dw, fl
   return check_launch("conv3x3_c1_wgrad");
 }
 
+// bf16 variant of conv_repack_k_kernel for the kind::f16 modes: wk16[i] = bf16(w), and (terms == 2) wk16[total + i] =
+// bf16(w - hi); same K-major [tap][n][c] order (fwd) / flipped taps (dgrad)
+__global__ void conv_repack_k_bf16_kernel(const float* __restrict__ w, uint16_t* __restrict__ wk, int Ci, int Co, int dgrad, int terms) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int total = 9 * Ci * Co;
+  if (i >= total) return;
+  float v;
+  if (!dgrad) {
+    int ci = i % Ci, co = (i / Ci) % Co, tap = i / (Co * Ci);
+    v = w[((size_t)co * Ci + ci) * 9 + tap];
+  } else {
+    int co = i % Co, ci = (i / Co) % Ci, tap = i / (Co * Ci);
+    v = w[((size_t)co * Ci + ci) * 9 + (8 - tap)];
+  }
+  const uint32_t r = __float_as_uint(v) + 0x8000u;
+  wk[i] = (uint16_t)(r >> 16);
+  if (terms == 2) {
+    const float lo = v - __uint_as_float(r & 0xFFFF0000u);
+    wk[total + i] = (uint16_t)((__float_as_uint(lo) + 0x8000u) >> 16);
+  }
+}
+
+static bool conv_is_bf16(int precision) { return precision == B200ASR_PREC_BF16 || precision == B200ASR_PREC_BF16X3; }
+
 static int conv_shape_ok(const char* who, int Ci, int Co) {
   B200_REQUIRE(Ci % 16 == 0 && Co % 64 == 0, B200ASR_BAD_SHAPE, "%s: need Ci %% 16 == 0 and Co %% 64 == 0 (Ci=%d Co=%d)", who, Ci, Co);
   return B200ASR_OK;
@@ -579,6 +603,11 @@ int b200asr_conv3x3_fwd(const float* x, const float* w, const float* bias, float
     conv_repack_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, (float*)ws, Ci, Co, 0);
     return conv3x3_simt(x, (const float*)ws, bias, nullptr, y, B, T, F, Ci, Co, relu, st);
   }
+  if (conv_is_bf16(precision)) {
+    B200_REQUIRE(Ci % 32 == 0 && (Co == 64 || Co == 128), B200ASR_BAD_SHAPE, "conv3x3_fwd (bf16): needs Ci %% 32 == 0 and Co in {64,128}");
+    conv_repack_k_bf16_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, (uint16_t*)ws, Ci, Co, 0, precision == B200ASR_PREC_BF16X3 ? 2 : 1);
+    return conv3x3_tc_halo(x, ws, bias, nullptr, y, B, T, F, Ci, Co, relu, precision, st);
+  }
   conv_repack_k_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, (float*)ws, Ci, Co, 0, precision == B200ASR_PREC_TF32X3);
   return conv3x3_tc(x, (const float*)ws, bias, nullptr, y, B, T, F, Ci, Co, relu, precision, st);
 }
@@ -595,6 +624,11 @@ int b200asr_conv3x3_bwd_data(const float* dy, const float* w, const float* relu_
     conv_repack_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, (float*)ws, Ci, Co, 1);
     return conv3x3_simt(dy, (const float*)ws, nullptr, relu_out, dx, B, T, F, Co, Ci, 0, st);
   }
+  if (conv_is_bf16(precision)) {
+    B200_REQUIRE(Co % 32 == 0 && (Ci == 64 || Ci == 128), B200ASR_BAD_SHAPE, "conv3x3_bwd_data (bf16): needs Co %% 32 == 0 and Ci in {64,128}");
+    conv_repack_k_bf16_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, (uint16_t*)ws, Ci, Co, 1, precision == B200ASR_PREC_BF16X3 ? 2 : 1);
+    return conv3x3_tc_halo(dy, ws, nullptr, relu_out, dx, B, T, F, Co, Ci, 0, precision, st);
+  }
   conv_repack_k_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, (float*)ws, Ci, Co, 1, precision == B200ASR_PREC_TF32X3);
   return conv3x3_tc(dy, (const float*)ws, nullptr, relu_out, dx, B, T, F, Co, Ci, 0, precision, st);
 }
@@ -607,6 +641,9 @@ int b200asr_conv3x3_bwd_weight(const float* dy, const float* x, float* dw, float
   cudaMemsetAsync(ws, 0, sizeof(float) * 9 * (size_t)Ci * Co, st);
   int rc;
   int bias_done = 0;
+  // the bf16 modes run the weight gradient (both operands activations) at the matching tf32 grade
+  if (precision == B200ASR_PREC_BF16X3) precision = B200ASR_PREC_TF32X3;
+  if (precision == B200ASR_PREC_BF16) precision = B200ASR_PREC_TF32;
   if (precision == B200ASR_PREC_FP32) rc = conv3x3_wgrad_simt(x, dy, (float*)ws, B, T, F, Ci, Co, st);
   else rc = conv3x3_wgrad_tc(x, dy, (float*)ws, B, T, F, Ci, Co, precision, st, dbias, &bias_done);
   if (rc) return rc;

@@ -36,8 +36,9 @@ int conv3x3_tc(const float* in, const float* wr, const float* bias, const float*
                int Cin, int Cout, int relu, int precision, cudaStream_t st);
 // 3xTF32 forward / data gradient with the input patch (incl. halo) fetched once per 32-channel slice (tc_conv_halo.cu);
 // conv3x3_tc dispatches to it for precision 3 (B200ASR_CONV_HALO=0 selects the tap-shifted engine policy instead).
-int conv3x3_tc_halo(const float* in, const float* wk, const float* bias, const float* mask, float* out, int B, int T, int F,
-                    int Cin, int Cout, int relu, cudaStream_t st);
+// mode 3 = 3xTF32 (fp32 hi | lo weights), 6 = bf16x3 / 2 = bf16 (bf16 weights from conv_repack_k_bf16)
+int conv3x3_tc_halo(const float* in, const void* wk, const float* bias, const float* mask, float* out, int B, int T, int F,
+                    int Cin, int Cout, int relu, int mode, cudaStream_t st);
 int conv3x3_wgrad_tc(const float* x, const float* dy, float* dwr, int B, int T, int F, int Ci, int Co, int precision,
                      cudaStream_t st, float* dbias = nullptr, int* dbias_done = nullptr);
 // dbias: optional [Co] bias gradient; *dbias_done = 1 when the kernel produced it (3xTF32), else the caller must

@@ -207,7 +207,7 @@ int conv3x3_tc(const float* in, const float* wk, const float* bias, const float*
                B200ASR_BAD_ALIGN, "conv3x3_tc: pointers must be 16-byte aligned");
   if (precision == 3) {
     static const int halo = [] { const char* v = getenv("B200ASR_CONV_HALO"); return v ? atoi(v) : 1; }();
-    if (halo) return conv3x3_tc_halo(in, wk, bias, mask, out, B, T, F, Cin, Cout, relu, st);
+    if (halo) return conv3x3_tc_halo(in, wk, bias, mask, out, B, T, F, Cin, Cout, relu, 3, st);
   }
   CUtensorMap ma, mb;
   {

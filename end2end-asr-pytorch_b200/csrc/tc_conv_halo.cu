@@ -42,9 +42,15 @@ struct HaloP {
   int relu, B, T, F, Cin, Cout, nft, ntt, cch;
 };
 
-template <int BN> struct HaloCfg {
-  static constexpr int kBBytes = BN * 128;
-  static constexpr int kStageBytes = 2 * kBBytes;                               // weights hi | lo of one (tap, slice)
+// MODE: 3 = 3xTF32 (fp32 weight tiles hi | lo, 128-byte rows), 6 = bf16x3 (bf16 weight tiles hi | lo, 64-byte rows, three
+// kind::f16 MMAs per product at twice the tf32 rate), 2 = bf16 (one bf16 weight tile, one MMA).  In the bf16 modes the split
+// warps convert the fp32 patch to bf16 and pack two channels per TMEM column.
+template <int BN, int MODE> struct HaloCfg {
+  static constexpr bool kBf16 = MODE != 3;
+  static constexpr int kHalves = MODE == 2 ? 1 : 2;
+  static constexpr int kBBytes = BN * (kBf16 ? 64 : 128);
+  static constexpr int kACols = MODE == 3 ? 64 : (MODE == 6 ? 32 : 16);        // TMEM columns of A (hi | lo) per stage
+  static constexpr int kStageBytes = kHalves * kBBytes;                         // weights hi | lo of one (tap, slice)
   // BN = 64 runs "concatenated": the tensor core is markedly less efficient at N = 64 than at N = 128 (measured: ~57% vs
   // ~87% of the tf32 rate, whatever the rest of the kernel does), so hi*hi and hi*lo are ONE N = 128 MMA against the
   // weight tile [B_hi ; B_lo] (adjacent in the stage, 128 K-major rows) into a 128-column accumulator, lo*hi is an N = 64
@@ -52,9 +58,10 @@ template <int BN> struct HaloCfg {
 #ifndef HALO_CAT
 #define HALO_CAT 1
 #endif
-  static constexpr bool kCat = BN == 64 && HALO_CAT;
+  static constexpr bool kCat = BN == 64 && HALO_CAT && MODE != 2;
   static constexpr int kAccW = kCat ? 128 : BN;                                  // accumulator columns per buffer
-  static constexpr int kMaxByTmem = (512 - 2 * kAccW) / 64;                      // 64 TMEM columns of A (hi | lo) per stage
+  static constexpr int kMaxByTmem0 = (512 - 2 * kAccW) / kACols;
+  static constexpr int kMaxByTmem = kMaxByTmem0 > 8 ? 8 : kMaxByTmem0;
   static constexpr int kBySmem = (200 * 1024 - HPATCH_SLOTS * HPATCH_STAGE) / kStageBytes;
   static constexpr int kRaw = kBySmem < kMaxByTmem ? kBySmem : kMaxByTmem;
   static constexpr int kStages = kRaw - kRaw % HALO_GROUPS;                       // a stage always belongs to one split group
@@ -65,10 +72,10 @@ template <int BN> struct HaloCfg {
   static_assert(kStages >= 2, "stage too large");
 };
 
-template <int BN>
+template <int BN, int MODE>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 tc_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const HaloP p) {
-  using Cfg = HaloCfg<BN>;
+  using Cfg = HaloCfg<BN, MODE>;
   constexpr int S = Cfg::kStages, G = HALO_GROUPS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -135,9 +142,9 @@ tc_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
         mbar_wait(empty_bar(s), ph ^ 1);
         if (leader) {
           const uint32_t sb = smem_base + Cfg::kRingOff + s * Cfg::kStageBytes;
-          mbar_expect_tx(full_bar(s), 2 * Cfg::kBBytes);
+          mbar_expect_tx(full_bar(s), Cfg::kHalves * Cfg::kBBytes);
           tma_load_2d(sb, &mapB, full_bar(s), sl * 32, tap * BN);
-          tma_load_2d(sb + Cfg::kBBytes, &mapB, full_bar(s), sl * 32, (9 + tap) * BN);
+          if (Cfg::kHalves == 2) tma_load_2d(sb + Cfg::kBBytes, &mapB, full_bar(s), sl * 32, (9 + tap) * BN);
         }
         __syncwarp();
         if (++s == S) { s = 0; ph ^= 1; }
@@ -147,10 +154,11 @@ tc_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (see tc_engine.cuh for the idioms)
     const bool leader = elect_one();
-    constexpr uint32_t idesc_ts = make_idesc_tf32(128, BN, false, false);
-    constexpr uint32_t idesc_cat = make_idesc_tf32(128, 128, false, false);
+    constexpr uint32_t idesc_ts = Cfg::kBf16 ? make_idesc_bf16(128, BN, false, false) : make_idesc_tf32(128, BN, false, false);
+    constexpr uint32_t idesc_cat = Cfg::kBf16 ? make_idesc_bf16(128, 128, false, false) : make_idesc_tf32(128, 128, false, false);
     constexpr uint32_t kStageStep = Cfg::kStageBytes >> 4, kLoStep = Cfg::kBBytes >> 4;
-    const uint64_t bd0 = make_smem_desc(smem_base + Cfg::kRingOff, 16, 1024);
+    const uint64_t bd0 = Cfg::kBf16 ? make_smem_desc(smem_base + Cfg::kRingOff, 16, 512, kLayoutSW64)
+                                    : make_smem_desc(smem_base + Cfg::kRingOff, 16, 1024);
     const uint32_t bd_hi = (uint32_t)(bd0 >> 32);
     auto mk = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; };
     uint32_t s = 0, ph = 0, tcount = 0;
@@ -165,7 +173,26 @@ tc_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
         tc_fence_after();
         if (leader) {
           const uint32_t b_lo32 = (uint32_t)bd0 + s * kStageStep;
-          const uint32_t a_t = tmem_base + Cfg::kAccCols + s * 64;
+          const uint32_t a_t = tmem_base + Cfg::kAccCols + s * Cfg::kACols;
+          if constexpr (Cfg::kBf16) {
+            // 32 channels = two 16-deep kind::f16 steps; a TMEM column holds two channels
+#pragma unroll
+            for (int ks = 0; ks < 2; ks++) {
+              const uint64_t b_hi = mk(bd_hi, b_lo32 + ks * 2), b_lo = mk(bd_hi, b_lo32 + kLoStep + ks * 2);
+              const uint32_t a_hi = a_t + ks * 8, a_lo = a_hi + 16;
+              const uint32_t acc0 = (kb | ks) != 0 ? 1u : 0u;
+              if constexpr (MODE == 2) {
+                umma_bf16_ts(d_tmem, a_hi, b_hi, idesc_ts, acc0);
+              } else if constexpr (Cfg::kCat) {
+                umma_bf16_ts(d_tmem, a_hi, b_hi, idesc_cat, acc0);                         // [hi*hi | hi*lo], 128 columns
+                umma_bf16_ts(d_tmem, a_lo, b_hi, idesc_ts, 1u);                            // + lo*hi into the first 64
+              } else {
+                umma_bf16_ts(d_tmem, a_lo, b_hi, idesc_ts, acc0);
+                umma_bf16_ts(d_tmem, a_hi, b_lo, idesc_ts, 1u);
+                umma_bf16_ts(d_tmem, a_hi, b_hi, idesc_ts, 1u);
+              }
+            }
+          } else
 #pragma unroll
           for (int ks = 0; ks < 4; ks++) {
             const uint64_t b_hi = mk(bd_hi, b_lo32 + ks * 2), b_lo = mk(bd_hi, b_lo32 + kLoStep + ks * 2);
@@ -267,7 +294,23 @@ tc_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
           const int s = k % S;
           mbar_wait(empty_bar(s), ((k / S) & 1) ^ 1);       // the MMAs that read this TMEM slot last have completed
           tc_fence_after();
-          const uint32_t acol = tmem_base + ((uint32_t)(quarter * 32) << 16) + Cfg::kAccCols + s * 64;
+          const uint32_t acol = tmem_base + ((uint32_t)(quarter * 32) << 16) + Cfg::kAccCols + s * Cfg::kACols;
+          if constexpr (Cfg::kBf16) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              const float4 v = x[j];
+              if constexpr (MODE == 6) {
+                split_bf16_pair(v.x, v.y, hi[2 * j], lo[2 * j]);
+                split_bf16_pair(v.z, v.w, hi[2 * j + 1], lo[2 * j + 1]);
+              } else {
+                hi[2 * j] = pack_bf16_pair(v.x, v.y);
+                hi[2 * j + 1] = pack_bf16_pair(v.z, v.w);
+              }
+            }
+            tmem_st16u(acol, hi);
+            if constexpr (MODE == 6) tmem_st16u(acol + 16, lo);
+          } else
 #pragma unroll
           for (int half = 0; half < 2; half++) {            // 16 columns at a time keeps the live registers low
             float hi[16], lo[16];
@@ -302,10 +345,10 @@ tc_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
   }
 }
 
-template <int BN>
+template <int BN, int MODE>
 static int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const HaloP& p, cudaStream_t st) {
-  using Cfg = HaloCfg<BN>;
-  auto* kern = tc_conv3x3_halo_kernel<BN>;
+  using Cfg = HaloCfg<BN, MODE>;
+  auto* kern = tc_conv3x3_halo_kernel<BN, MODE>;
   static bool attr_set[kMaxDevices] = {};
   if (int rc = ensure_dynamic_smem((const void*)kern, Cfg::kSmemBytes, attr_set, "tc_conv3x3_halo")) return rc;
   const long long tiles = (long long)p.nft * p.ntt * p.B;
@@ -318,10 +361,12 @@ static int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const HaloP
 
 }  // namespace tc
 
-// wk: [2][9][Cout][Cin] pre-split K-major weights (hi | lo), as for conv3x3_tc with precision 3
-int conv3x3_tc_halo(const float* in, const float* wk, const float* bias, const float* mask, float* out, int B, int T, int F,
-                    int Cin, int Cout, int relu, cudaStream_t st) {
+// wk: mode 3: [2][9][Cout][Cin] fp32 pre-split K-major weights (hi | lo), as for conv3x3_tc with precision 3;
+//     mode 6 / 2: [2 or 1][9][Cout][Cin] bf16 (conv_repack_k_bf16_kernel)
+int conv3x3_tc_halo(const float* in, const void* wk, const float* bias, const float* mask, float* out, int B, int T, int F,
+                    int Cin, int Cout, int relu, int mode, cudaStream_t st) {
   using namespace tc;
+  B200_REQUIRE(mode == 3 || mode == 6 || mode == 2, B200ASR_BAD_ARG, "conv3x3_tc_halo: mode must be 3 (3xTF32), 6 (bf16x3) or 2 (bf16)");
   B200_REQUIRE(Cin % 32 == 0 && (Cout == 64 || Cout == 128), B200ASR_BAD_SHAPE,
                "conv3x3_tc_halo: needs Cin %% 32 == 0 and Cout in {64,128} (Cin=%d Cout=%d)", Cin, Cout);
   B200_REQUIRE(aligned16(in) && aligned16(wk) && aligned16(out) && (!bias || aligned16(bias)) && (!mask || aligned16(mask)),
@@ -335,14 +380,16 @@ int conv3x3_tc_halo(const float* in, const float* wk, const float* bias, const f
     if (rc) return rc;
   }
   {
-    uint64_t dims[2] = {(uint64_t)Cin, (uint64_t)18 * Cout};
+    uint64_t dims[2] = {(uint64_t)Cin, (uint64_t)(mode == 2 ? 9 : 18) * Cout};
     uint64_t strides[1] = {(uint64_t)Cin};
     uint32_t box[2] = {32, (uint32_t)Cout};
-    int rc = make_tensor_map_f32(&mb, wk, 2, dims, strides, box, false, false);
+    int rc = mode == 3 ? make_tensor_map_f32(&mb, wk, 2, dims, strides, box, false, false) : make_tensor_map_bf16(&mb, wk, 2, dims, strides, box);
     if (rc) return rc;
   }
   HaloP p{out, bias, mask, relu, B, T, F, Cin, Cout, ceil_div(F, HF), ceil_div(T, HT), Cin / 32};
-  return Cout == 64 ? launch_halo<64>(ma, mb, p, st) : launch_halo<128>(ma, mb, p, st);
+  if (mode == 3) return Cout == 64 ? launch_halo<64, 3>(ma, mb, p, st) : launch_halo<128, 3>(ma, mb, p, st);
+  if (mode == 6) return Cout == 64 ? launch_halo<64, 6>(ma, mb, p, st) : launch_halo<128, 6>(ma, mb, p, st);
+  return Cout == 64 ? launch_halo<64, 2>(ma, mb, p, st) : launch_halo<128, 2>(ma, mb, p, st);
 }
 
 }  // namespace b200asr

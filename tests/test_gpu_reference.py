@@ -159,7 +159,7 @@ def test_reference_trainer_loop_runs_on_installed_kernels(case):
     results = {}
     with tempfile.TemporaryDirectory() as tmp:
         for installed in (False, True):
-            ns, model, l2i, i2l = _build(flags, vocab, extra=["--cuda", "--warmup", "4", "--k-lr", "1", "--min-lr", "1e-4", "--clip", "--max-norm", "400"])
+            ns, model, l2i, i2l = _build(flags, vocab, extra=["--cuda", "--warmup", "4", "--k-lr", "0.02", "--min-lr", "1e-6", "--clip", "--max-norm", "400"])
             init = {k: v.detach().float().clone() for k, v in model.state_dict().items()}
             model = model.cuda()
             train, valid = _loaders(freq, T, vocab, ns.constant.args.tgt_max_len - 1, 3, B)

@@ -32,7 +32,9 @@ r32 = O.forward_backward(P, ocfg, src, lens, tgt, 0.1)
 g64 = {k: v.float() for k, v in r64[5].items()}
 e32 = grads_rel_err(r32[5], g64)
 print("fp32 oracle vs fp64: pred %.2e grads max %.2e median %.2e" % (rel_err(r32[0], r64[0]), max(e32.values()), sorted(e32.values())[len(e32) // 2]))
+defaults = (ops.config.linear, ops.config.conv, ops.config.attn, ops.config.conv_wgrad, ops.config.attn_bwd)
 for mode in modes:
+    ops.config.linear, ops.config.conv, ops.config.attn, ops.config.conv_wgrad, ops.config.attn_bwd = defaults
     if mode == "default":
         pass
     elif "," in mode:
@@ -49,5 +51,9 @@ for mode in modes:
     for k in order[:12]:
         r, x = g64[k], grads[k].float()
         l2 = float((x - r).norm() / r.norm().clamp_min(1e-30))
-        print(f"   {k:55s} max-rel {errs[k]:.2e}  rel-L2 {l2:.2e}  max|ref| {float(r.abs().max()):.2e}  fp32-oracle {e32[k]:.2e}")
+        rows = ""
+        if r.dim() >= 2:      # are the errors confined to a few rows (= flipped units) or spread over the tensor?
+            d = (x - r).reshape(r.shape[0], -1).abs().max(1).values / r.abs().max()
+            rows = f" rows>1e-3: {int((d > 1e-3).sum())}/{d.numel()} top {[round(float(v), 4) for v in d.topk(min(3, d.numel())).values]} row-median {float(d.median()):.1e}"
+        print(f"   {k:55s} max-rel {errs[k]:.2e}  rel-L2 {l2:.2e}  max|ref| {float(r.abs().max()):.2e}  fp32-oracle {e32[k]:.2e}{rows}")
     print("   best:", ", ".join(f"{k.split('.')[-3:]} {errs[k]:.1e}" for k in order[-4:]))
