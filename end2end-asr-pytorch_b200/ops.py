@@ -102,6 +102,11 @@ class _Profiler:
 
 profiler = _Profiler()
 
+# Test hook: when set to a list, the forwards append (kind, activation) for every discontinuous unit of the path -- post-ReLU
+# FFN / conv outputs, max-pool inputs, post-Hardtanh outputs -- in call order.  The parity tests derive the path's discrete
+# decisions (active units, pooling winners) from them and evaluate the fp64 oracle AT those decisions (oracle.Decisions).
+decision_capture = None
+
 
 class _ProfiledLib:
     def __init__(self, lib):
@@ -270,6 +275,8 @@ class FFNFn(torch.autograd.Function):
         ctx.prec = _linear_prec(w1m.shape[0], w1m.shape[1])
         ws1, ws2 = split_weight(w1m, ctx.prec), split_weight(w2m, ctx.prec)
         h = linear_fwd(x2, w1m, b1, True, ctx.prec, ws1)
+        if decision_capture is not None:
+            decision_capture.append(("relu", h.view(*x.shape[:-1], w1m.shape[0])))
         y = linear_fwd(h, w2m, b2, False, ctx.prec, ws2)
         ctx.save_for_backward(x2, h, w1m, w2m)
         ctx.ws = (ws1, ws2)
@@ -628,6 +635,10 @@ class VggFrontendFn(torch.autograd.Function):
         p2 = new(B, T4, F4, C2)
         L.check(lib.b200asr_maxpool2x2_fwd(L.ptr(y4), L.ptr(p2), B, T2, F2, C2, st), "pool2")
         ctx.save_for_backward(x, y1, y2, p1, y3, y4, w0, w2, w5, w7)
+        if decision_capture is not None:      # channels-last [B,T,F,C] -> the reference's (B,C,F,T)
+            nchw = lambda t: t.permute(0, 3, 2, 1)
+            decision_capture.extend([("relu", nchw(y1)), ("relu", nchw(y2)), ("pool", nchw(y2)), ("relu", nchw(y3)), ("relu", nchw(y4)),
+                                     ("pool", nchw(y4))])
         ctx.prec, ctx.prec_w = prec, config.conv_wgrad
         return p2
 
@@ -805,6 +816,8 @@ class EmbFrontendFn(torch.autograd.Function):
         out = new(B, W2, C * H2)
         L.check(lib.b200asr_flatten_bcft_fwd(L.ptr(a2), L.ptr(out), B, C, H2, W2, st), "emb_flatten")
         ctx.save_for_backward(x, c1, a1, m1, s1, c2, a2, m2, s2, w0, g1, w3, g4)
+        if decision_capture is not None:
+            decision_capture.extend([("hardtanh", a1), ("hardtanh", a2)])
         ctx.gemm = (gemm, config.conv, config.conv_wgrad)
         ctx.training = bool(training)
         ctx.cols = (col1, col2) if gemm else None

@@ -71,19 +71,78 @@ def sinusoid_table(length: int, dim: int, dtype=torch.float32) -> torch.Tensor:
     return table.to(dtype)
 
 
+# --------------------------------------------------------------------------- discontinuities (ReLU / max-pool / Hardtanh)
+class Decisions:
+    """The model's discrete decisions -- which ReLU / Hardtanh units are active, which element each max-pool window takes.
+    They are the only discontinuities of the path: between two arithmetics that agree to ~1e-5 a unit sitting within
+    rounding of its threshold may decide differently, and its whole (O(1)) gradient contribution moves.  `record` mode
+    stores the decisions (and the pre-activations) of a run; `frozen` mode replays given decisions, which makes the
+    function smooth in its inputs -- the parity tests compare the CUDA gradients with the fp64 oracle evaluated AT THE
+    CUDA PATH'S OWN DECISIONS, and separately count and bound the decisions that differ."""
+
+    def __init__(self, frozen: Optional[Dict[str, torch.Tensor]] = None):
+        self.frozen = frozen
+        self.masks: Dict[str, torch.Tensor] = {}     # site -> bool mask (ReLU/Hardtanh: active) or int64 window indices (pool)
+        self.pre: Dict[str, torch.Tensor] = {}       # site -> float32 pre-activation (ReLU) / top-2 window gap (pool)
+        self._n = {}
+
+    def _site(self, kind):
+        i = self._n.get(kind, 0)
+        self._n[kind] = i + 1
+        return f"{kind}.{i}"
+
+    def relu(self, x):
+        site = self._site("relu")
+        if self.frozen is not None:
+            return x * self.frozen[site].to(x.dtype)
+        self.masks[site] = x.detach() > 0
+        self.pre[site] = x.detach().float()
+        return F.relu(x)
+
+    def hardtanh(self, x, lo=0.0, hi=20.0):
+        site = self._site("hardtanh")
+        if self.frozen is not None:
+            m = self.frozen[site]                       # int8: 0 = clamped low, 1 = linear, 2 = clamped high
+            return x * (m == 1).to(x.dtype) + lo * (m == 0).to(x.dtype) + hi * (m == 2).to(x.dtype)
+        self.masks[site] = ((x.detach() > lo).to(torch.int8) + (x.detach() >= hi).to(torch.int8))
+        self.pre[site] = torch.minimum((x.detach() - lo).abs(), (x.detach() - hi).abs()).float()
+        return torch.clamp(x, lo, hi)
+
+    def max_pool(self, x):
+        site = self._site("pool")
+        B, C, H, W = x.shape
+        if self.frozen is not None:
+            idx = self.frozen[site]
+            return x.flatten(2).gather(2, idx.flatten(2)).view(idx.shape)
+        y, idx = F.max_pool2d(x, 2, 2, return_indices=True)
+        self.masks[site] = idx
+        w = x.detach()[:, :, :H // 2 * 2, :W // 2 * 2].reshape(B, C, H // 2, 2, W // 2, 2).permute(0, 1, 2, 4, 3, 5).reshape(B, C, H // 2, W // 2, 4)
+        top = w.topk(2, dim=-1).values
+        self.pre[site] = (top[..., 0] - top[..., 1]).float()
+        return y
+
+
+def _relu(x, dec):
+    return dec.relu(x) if dec is not None else F.relu(x)
+
+
+def _pool(x, dec):
+    return dec.max_pool(x) if dec is not None else F.max_pool2d(x, 2, 2)
+
+
 # --------------------------------------------------------------------------- front end
-def vgg_frontend(spec: torch.Tensor, P: Dict[str, torch.Tensor]) -> torch.Tensor:
+def vgg_frontend(spec: torch.Tensor, P: Dict[str, torch.Tensor], dec: Optional[Decisions] = None) -> torch.Tensor:
     """models/asr/transformer.py:42-53 -- 2x(conv3x3+ReLU), pool, 2x(conv3x3+ReLU), pool."""
-    h = F.relu(F.conv2d(spec, P["conv.0.weight"], P["conv.0.bias"], padding=1))
-    h = F.relu(F.conv2d(h, P["conv.2.weight"], P["conv.2.bias"], padding=1))
-    h = F.max_pool2d(h, 2, 2)
-    h = F.relu(F.conv2d(h, P["conv.5.weight"], P["conv.5.bias"], padding=1))
-    h = F.relu(F.conv2d(h, P["conv.7.weight"], P["conv.7.bias"], padding=1))
-    return F.max_pool2d(h, 2, 2)
+    h = _relu(F.conv2d(spec, P["conv.0.weight"], P["conv.0.bias"], padding=1), dec)
+    h = _relu(F.conv2d(h, P["conv.2.weight"], P["conv.2.bias"], padding=1), dec)
+    h = _pool(h, dec)
+    h = _relu(F.conv2d(h, P["conv.5.weight"], P["conv.5.bias"], padding=1), dec)
+    h = _relu(F.conv2d(h, P["conv.7.weight"], P["conv.7.bias"], padding=1), dec)
+    return _pool(h, dec)
 
 
 def emb_frontend(spec: torch.Tensor, P: Dict[str, torch.Tensor], eps: float = 1e-5, training: bool = True,
-                 state: Optional[Dict[str, torch.Tensor]] = None, momentum: float = 0.1) -> torch.Tensor:
+                 state: Optional[Dict[str, torch.Tensor]] = None, momentum: float = 0.1, dec: Optional[Decisions] = None) -> torch.Tensor:
     """models/asr/transformer.py:33-40 -- strided conv + BatchNorm2d + Hardtanh(0, 20), twice.
     nn.BatchNorm2d semantics: training -> batch statistics, and `state` (conv.{1,4}.running_mean / running_var /
     num_batches_tracked, the module's buffers) is updated in place with momentum 0.1 and the unbiased variance;
@@ -96,9 +155,10 @@ def emb_frontend(spec: torch.Tensor, P: Dict[str, torch.Tensor], eps: float = 1e
         return F.batch_norm(h, rm, rv, P[f"conv.{i}.weight"], P[f"conv.{i}.bias"], training=training, momentum=momentum, eps=eps)
 
     h = F.conv2d(spec, P["conv.0.weight"], P["conv.0.bias"], stride=(2, 2), padding=(0, 10))
-    h = torch.clamp(bn(h, 1), 0.0, 20.0)
+    clamp = (lambda t: dec.hardtanh(t)) if dec is not None else (lambda t: torch.clamp(t, 0.0, 20.0))
+    h = clamp(bn(h, 1))
     h = F.conv2d(h, P["conv.3.weight"], P["conv.3.bias"], stride=(2, 1))
-    return torch.clamp(bn(h, 4), 0.0, 20.0)
+    return clamp(bn(h, 4))
 
 
 def bn_initial_state(dtype=torch.float32) -> Dict[str, torch.Tensor]:
@@ -160,17 +220,17 @@ def multi_head_attention(xq, xk, xv, mask, P, pre: str, H: int, dk: int, dv: int
     return F.layer_norm(o + xq, (d,), P[pre + "layer_norm.weight"], P[pre + "layer_norm.bias"])
 
 
-def conv_ffn(x, P, pre: str):
+def conv_ffn(x, P, pre: str, dec: Optional[Decisions] = None):
     """models/common_layers.py:135-142 -- Conv1d(k=1) == per-token linear; weights (out,in,1)."""
     w1 = P[pre + "conv_1.weight"].squeeze(-1)
     w2 = P[pre + "conv_2.weight"].squeeze(-1)
-    h = F.relu(F.linear(x, w1, P[pre + "conv_1.bias"]))
+    h = _relu(F.linear(x, w1, P[pre + "conv_1.bias"]), dec)
     y = F.linear(h, w2, P[pre + "conv_2.bias"])
     d = x.shape[-1]
     return F.layer_norm(y + x, (d,), P[pre + "layer_norm.weight"], P[pre + "layer_norm.bias"])
 
 
-def encoder_forward(feats, lengths, P, cfg: OracleConfig):
+def encoder_forward(feats, lengths, P, cfg: OracleConfig, dec: Optional[Decisions] = None):
     """models/asr/transformer.py:157-180 and :195-203.  Note quirk Q1: `lengths` are raw
     frame counts compared against the (possibly down-sampled) feature length."""
     B, T, _ = feats.shape
@@ -184,7 +244,7 @@ def encoder_forward(feats, lengths, P, cfg: OracleConfig):
         pre = f"encoder.layers.{l}."
         x = multi_head_attention(x, x, x, mask, P, pre + "self_attn.", cfg.num_heads, cfg.dim_key, cfg.dim_value)
         x = x * keep
-        x = conv_ffn(x, P, pre + "pos_ffn.")
+        x = conv_ffn(x, P, pre + "pos_ffn.", dec)
         x = x * keep
     return x
 
@@ -205,7 +265,7 @@ def preprocess_targets(padded_target: torch.Tensor, tgt_max_len: int) -> Tuple[t
     return seq_in, seq_out
 
 
-def decoder_forward(padded_target, enc_out, enc_lengths, P, cfg: OracleConfig):
+def decoder_forward(padded_target, enc_out, enc_lengths, P, cfg: OracleConfig, dec: Optional[Decisions] = None):
     """models/asr/transformer.py:268-305 and :533-545."""
     seq_in, seq_out = preprocess_targets(padded_target, cfg.tgt_max_len)
     B, Tt = seq_in.shape
@@ -226,22 +286,24 @@ def decoder_forward(padded_target, enc_out, enc_lengths, P, cfg: OracleConfig):
         x = multi_head_attention(x, enc_out, enc_out, cross_mask, P, pre + "encoder_attn.", cfg.num_heads,
                                  cfg.dim_key, cfg.dim_value)
         x = x * keep
-        x = conv_ffn(x, P, pre + "pos_ffn.")
+        x = conv_ffn(x, P, pre + "pos_ffn.", dec)
         x = x * keep
     logits = F.linear(x, P["decoder.output_linear.weight"])                   # :302 (no bias)
     return logits, seq_out
 
 
-def transformer_forward(P, cfg: OracleConfig, spec, lengths, padded_target, training: bool = True, bn_state=None):
-    """models/asr/transformer.py:59-85 -> (pred, gold, hyp_seq).  training / bn_state: BatchNorm mode of the emb_cnn front end."""
+def transformer_forward(P, cfg: OracleConfig, spec, lengths, padded_target, training: bool = True, bn_state=None,
+                        dec: Optional[Decisions] = None):
+    """models/asr/transformer.py:59-85 -> (pred, gold, hyp_seq).  training / bn_state: BatchNorm mode of the emb_cnn front end;
+    dec: record or replay the discrete decisions (class Decisions).  Site order: front end, encoder FFNs, decoder FFNs."""
     if cfg.feat_extractor == "vgg_cnn":
-        h = flatten_features(vgg_frontend(spec, P))
+        h = flatten_features(vgg_frontend(spec, P, dec))
     elif cfg.feat_extractor == "emb_cnn":
-        h = flatten_features(emb_frontend(spec, P, training=training, state=bn_state))
+        h = flatten_features(emb_frontend(spec, P, training=training, state=bn_state, dec=dec))
     else:
         h = flatten_features(spec)
-    enc = encoder_forward(h, lengths, P, cfg)
-    pred, gold = decoder_forward(padded_target, enc, lengths, P, cfg)
+    enc = encoder_forward(h, lengths, P, cfg, dec)
+    pred, gold = decoder_forward(padded_target, enc, lengths, P, cfg, dec)
     hyp = pred.argmax(dim=2)                                                   # :80-82 (topk k=1)
     return pred, gold, hyp
 
@@ -398,12 +460,12 @@ def synthetic_batch(cfg: OracleConfig, batch: int, t_src: int, seed: int = 0, ra
     return spec, lens.to(torch.int32), tgt
 
 
-def forward_backward(P, cfg: OracleConfig, spec, lengths, tgt, smoothing: float):
+def forward_backward(P, cfg: OracleConfig, spec, lengths, tgt, smoothing: float, dec: Optional[Decisions] = None):
     """One oracle training step (no optimizer): returns pred, gold, hyp, loss and grads by name."""
     Pg = {k: v.detach().clone().requires_grad_(True) for k, v in P.items()}
     if cfg.emb_trg_sharing:
         Pg["decoder.output_linear.weight"] = Pg["decoder.trg_embedding.weight"]
-    pred, gold, hyp = transformer_forward(Pg, cfg, spec, lengths, tgt)
+    pred, gold, hyp = transformer_forward(Pg, cfg, spec, lengths, tgt, dec=dec)
     loss, n_word = cross_entropy_loss(pred, gold, smoothing)
     loss.backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in Pg.items()}

@@ -33,3 +33,28 @@ def cuda_step(model, src, lengths, tgt, smoothing):
     torch.cuda.synchronize()
     grads = {n: (p.grad.detach().cpu() if p.grad is not None else torch.zeros_like(p).cpu()) for n, p in model.named_parameters()}
     return pred.detach().cpu(), gold.cpu(), hyp.cpu(), loss.detach().cpu(), stats.cpu(), grads
+
+
+def cuda_step_with_decisions(model, src, lengths, tgt, smoothing):
+    """cuda_step plus the path's own discrete decisions in the oracle's site naming (oracle.Decisions): which ReLU / Hardtanh
+    units are active and which element every max-pool window takes, derived from the activations the kernels produced."""
+    import importlib
+    import torch.nn.functional as F
+    ops = importlib.import_module(b200asr.__name__ + ".ops")
+    ops.decision_capture = []
+    try:
+        out = cuda_step(model, src, lengths, tgt, smoothing)
+        cap = ops.decision_capture
+    finally:
+        ops.decision_capture = None
+    masks, n = {}, {}
+    for kind, t in cap:
+        i = n.get(kind, 0)
+        n[kind] = i + 1
+        if kind == "relu":
+            masks[f"relu.{i}"] = (t > 0).cpu()
+        elif kind == "hardtanh":
+            masks[f"hardtanh.{i}"] = ((t > 0).to(torch.int8) + (t >= 20.0).to(torch.int8)).cpu()
+        else:                                   # first maximum of the window, as ATen (and the pooling kernel) pick it
+            masks[f"pool.{i}"] = F.max_pool2d(t.contiguous(), 2, 2, return_indices=True)[1].cpu()
+    return out, masks

@@ -9,7 +9,7 @@ import torch
 sys.path.insert(0, ".")
 import b200asr  # noqa: E402
 from oracle import asr_oracle as O  # noqa: E402
-from tests.gpu_util import cuda_model, cuda_step  # noqa: E402
+from tests.gpu_util import cuda_model, cuda_step, cuda_step_with_decisions  # noqa: E402
 from tests.helpers import grads_rel_err, rel_err  # noqa: E402
 
 ops = importlib.import_module(b200asr.__name__ + ".ops")
@@ -27,7 +27,9 @@ for k, v in P.items():
         v.add_(0.1 * torch.randn(v.shape, generator=g))
 src, lens, tgt = O.synthetic_batch(ocfg, B, spec["t_src"], seed=0, ragged=True)
 torch.set_num_threads(32)
-r64 = O.forward_backward({k: v.double() for k, v in P.items()}, ocfg, src.double(), lens, tgt, 0.1)
+rec = O.Decisions()
+P64 = {k: v.double() for k, v in P.items()}
+r64 = O.forward_backward(P64, ocfg, src.double(), lens, tgt, 0.1, dec=rec)
 r32 = O.forward_backward(P, ocfg, src, lens, tgt, 0.1)
 g64 = {k: v.float() for k, v in r64[5].items()}
 e32 = grads_rel_err(r32[5], g64)
@@ -43,7 +45,19 @@ for mode in modes:
     else:
         ops.config.set(linear=mode, conv=mode, attn=mode if mode in ("fp32", "tf32", "tf32x3") else "tf32x3", conv_wgrad=mode, attn_bwd="fp32")
     model = cuda_model(ocfg, P)
-    pred, gold, hyp, loss, stats, grads = cuda_step(model, src, lens, tgt, 0.1)
+    (pred, gold, hyp, loss, stats, grads), masks = cuda_step_with_decisions(model, src, lens, tgt, 0.1)
+    # decisions that differ from the fp64 oracle's own, and how close to their threshold those units are in fp64
+    for site in sorted(masks):
+        diff = masks[site] != rec.masks[site]
+        nd = int(diff.sum())
+        if nd:
+            pre = rec.pre[site]
+            print(f"   {site:12s} {nd:7d} of {diff.numel():10d} decisions differ; |pre-activation| / max at those: max {float(pre[diff].abs().max() / pre.abs().max()):.1e}")
+    r64f = O.forward_backward(P64, ocfg, src.double(), lens, tgt, 0.1, dec=O.Decisions(frozen=masks))
+    g64f = {k: v.float() for k, v in r64f[5].items()}
+    errs_unfrozen = grads_rel_err(grads, g64)
+    print(f"   unfrozen: grads max {max(errs_unfrozen.values()):.2e} median {sorted(errs_unfrozen.values())[len(errs_unfrozen) // 2]:.2e}; below: against the fp64 oracle evaluated AT THE PATH'S OWN DECISIONS")
+    g64_saved, g64 = g64, g64f
     errs = grads_rel_err(grads, g64)
     order = sorted(errs, key=errs.get, reverse=True)
     print(f"== {mode}: pred {rel_err(pred, r64[0]):.2e} loss {abs(loss.item() - r64[3].item()) / abs(r64[3].item()):.2e} "
@@ -57,3 +71,7 @@ for mode in modes:
             rows = f" rows>1e-3: {int((d > 1e-3).sum())}/{d.numel()} top {[round(float(v), 4) for v in d.topk(min(3, d.numel())).values]} row-median {float(d.median()):.1e}"
         print(f"   {k:55s} max-rel {errs[k]:.2e}  rel-L2 {l2:.2e}  max|ref| {float(r.abs().max()):.2e}  fp32-oracle {e32[k]:.2e}{rows}")
     print("   best:", ", ".join(f"{k.split('.')[-3:]} {errs[k]:.1e}" for k in order[-4:]))
+    ratio = {k: errs[k] / max(e32[k], 1e-7) for k in errs}
+    kr = max(ratio, key=ratio.get)
+    print(f"   error / fp32-oracle error: max {ratio[kr]:.0f} ({kr}) median {sorted(ratio.values())[len(ratio) // 2]:.0f}")
+    g64 = g64_saved
