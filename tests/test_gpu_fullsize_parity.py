@@ -8,9 +8,19 @@
 
 Batch is the only reduced quantity (utterances are independent): every kernel sees its real row lengths, head
 dims, tile counts along T/F/d and the real vocabulary.  Bars (north_star: "within 1e-3 relative fp32"): pred max-norm,
-loss, EVERY gradient tensor in the max norm (tests/helpers.py::grads_rel_err, floor for mathematically-zero tensors), and
-argmax ids bit-exact wherever the fp64 top-2 margin exceeds twice the measured logit error (ties at random init are not
-decidable by any fp32 implementation, the reference included).
+loss, argmax ids bit-exact wherever the fp64 top-2 margin exceeds twice the measured logit error (ties at random init are
+not decidable by any fp32 implementation, the reference included), and EVERY gradient tensor in the MAX norm
+(tests/helpers.py::grads_rel_err, floor for mathematically-zero tensors).
+
+Gradients and the model's discontinuities.  The path has ~1.3e8 ReLU units and max-pool windows at these sizes; a unit
+whose pre-activation is within rounding (1e-6 .. 1e-5 of the layer's scale) of its threshold decides differently under two
+correct arithmetics, and then its whole O(1) gradient contribution moves (measured at cfg2, B=4: ~150 such units, 2e-3
+median / 3e-2 max gradient difference -- the fp32 oracle against the fp64 one shows the same effect at its own noise
+level).  The test therefore (1) reads the CUDA path's own decisions (active ReLU / Hardtanh units, pooling winners) from
+the activations its kernels produced, (2) counts the decisions that differ from the fp64 oracle's and checks that every
+one of them is a threshold case (|fp64 pre-activation| < 1e-4 of the layer's largest) and that they are a < 1e-5 minority,
+and (3) compares the gradients in the max norm with the fp64 oracle evaluated AT THOSE DECISIONS (oracle.Decisions), where
+the function is smooth: measured 5e-5 (3xTF32) / 7e-5 (bf16x3) / 4e-5 (fp32 kernels) against the 1e-3 bar.
 """
 import time
 
@@ -58,19 +68,20 @@ def _truth(name):
     src, lens, tgt = O.synthetic_batch(ocfg, B, spec["t_src"], seed=0, ragged=True)
     torch.set_num_threads(max(torch.get_num_threads(), 16))
     t0 = time.time()
-    r64 = O.forward_backward({k: v.double() for k, v in P.items()}, ocfg, src.double(), lens, tgt, 0.1)
+    rec = O.Decisions()
+    r64 = O.forward_backward({k: v.double() for k, v in P.items()}, ocfg, src.double(), lens, tgt, 0.1, dec=rec)
     r32 = O.forward_backward(P, ocfg, src, lens, tgt, 0.1)
     print(f"[{name}] oracle fp64+fp32 on the host: {time.time() - t0:.1f} s")
-    _cache[name] = (ocfg, P, src, lens, tgt, r64, r32)
+    _cache[name] = (ocfg, P, src, lens, tgt, r64, r32, rec)
     return _cache[name]
 
 
 def _check(name, precision=None):
     import importlib
     import b200asr
-    from tests.gpu_util import cuda_model, cuda_step
+    from tests.gpu_util import cuda_model, cuda_step_with_decisions
     ops = importlib.import_module(b200asr.__name__ + ".ops")
-    ocfg, P, src, lens, tgt, r64, r32 = _truth(name)
+    ocfg, P, src, lens, tgt, r64, r32, rec = _truth(name)
     pred64, gold, hyp64, loss64, n_word, grads64 = r64
     pred32, _, hyp32, loss32, _, grads32 = r32
     g64 = {k: v.float() for k, v in grads64.items()}
@@ -79,16 +90,32 @@ def _check(name, precision=None):
         if precision is not None:
             ops.config.set(**precision)
         model = cuda_model(ocfg, P)
-        pred, gold_g, hyp, loss, stats, grads = cuda_step(model, src, lens, tgt, 0.1)
+        (pred, gold_g, hyp, loss, stats, grads), masks = cuda_step_with_decisions(model, src, lens, tgt, 0.1)
     finally:
         ops.config.linear, ops.config.conv, ops.config.attn, ops.config.conv_wgrad, ops.config.attn_bwd = old
     assert torch.equal(gold_g, gold)
     e_pred = rel_err(pred, pred64)
     e_loss = abs(loss.item() - loss64.item()) / abs(loss64.item())
-    errs = grads_rel_err(grads, g64)
+    # (2) decisions that differ from the fp64 oracle's own: count them, and check each one is a threshold case
+    assert set(masks) == set(rec.masks), (sorted(masks), sorted(rec.masks))
+    n_flip = n_units = 0
+    worst_band = 0.0
+    for site in masks:
+        diff = masks[site] != rec.masks[site]
+        n_units += diff.numel()
+        nd = int(diff.sum())
+        if nd:
+            n_flip += nd
+            worst_band = max(worst_band, float(rec.pre[site][diff].abs().max() / rec.pre[site].abs().max()))
+    # (3) the fp64 oracle evaluated at the path's own decisions: smooth in the inputs, so the max norm is meaningful
+    t0 = time.time()
+    r64f = O.forward_backward({k: v.double() for k, v in P.items()}, ocfg, src.double(), lens, tgt, 0.1, dec=O.Decisions(frozen=masks))
+    g64f = {k: v.float() for k, v in r64f[5].items()}
+    errs = grads_rel_err(grads, g64f)
     worst = max(errs, key=errs.get)
     med = sorted(errs.values())[len(errs) // 2]
-    ref_errs = grads_rel_err(grads32, g64)            # what the reference's own fp32 arithmetic does against fp64
+    errs_unfrozen = grads_rel_err(grads, g64)
+    ref_errs = grads_rel_err(grads32, g64)            # what the reference's own fp32 arithmetic does against fp64 (its own flips included)
     ref_worst = max(ref_errs, key=ref_errs.get)
     real = gold.ne(O.PAD)
     # argmax: decidable positions = fp64 top-2 margin > 2 x the measured absolute logit error
@@ -98,21 +125,32 @@ def _check(name, precision=None):
     decidable = real & (margin > 2 * abs_err)
     flips_all = int((hyp[real] != hyp64[real]).sum())
     flips_dec = int((hyp[decidable] != hyp64[decidable]).sum())
-    print(f"[{name}] pred {e_pred:.2e} (fp32 oracle {rel_err(pred32, pred64):.2e})  loss {e_loss:.2e}  grads max {errs[worst]:.2e} "
-          f"({worst}) median {med:.2e}  | fp32 oracle grads max {ref_errs[ref_worst]:.2e} ({ref_worst})  "
-          f"argmax flips {flips_all}/{int(real.sum())} (decidable {flips_dec}/{int(decidable.sum())})  n_word {n_word}")
+    print(f"[{name}] pred {e_pred:.2e} (fp32 oracle {rel_err(pred32, pred64):.2e})  loss {e_loss:.2e}  "
+          f"argmax flips {flips_all}/{int(real.sum())} (decidable {flips_dec}/{int(decidable.sum())})  n_word {n_word}\n"
+          f"[{name}] decisions: {n_flip} of {n_units} differ from the fp64 oracle's (largest |pre-activation| / layer max among them {worst_band:.1e})\n"
+          f"[{name}] grads vs fp64 oracle AT THE PATH'S DECISIONS: max {errs[worst]:.2e} ({worst}) median {med:.2e}   "
+          f"[unfrozen: max {max(errs_unfrozen.values()):.2e} median {sorted(errs_unfrozen.values())[len(errs) // 2]:.2e}; "
+          f"fp32 oracle vs fp64, unfrozen: max {ref_errs[ref_worst]:.2e}]  (frozen oracle run {time.time() - t0:.1f} s)")
     assert int(stats[1]) == n_word
     assert e_pred < TOL, e_pred
     assert e_loss < TOL, e_loss
     assert flips_dec == 0
     assert float(decidable.float().sum() / real.float().sum()) > 0.97       # the tie band stays a small minority
-    assert errs[worst] < TOL, (worst, errs[worst])
+    assert n_flip <= 1e-5 * n_units, (n_flip, n_units)                      # differing decisions: a vanishing minority ...
+    assert worst_band < 1e-4, worst_band                                    # ... and every one a unit sitting on its threshold
+    assert errs[worst] < TOL, (worst, errs[worst])                          # every gradient tensor, max norm
     return e_pred, errs
 
 
 @pytest.mark.parametrize("name", ["cfg2", "cfg3", "cfg4", "cfg5"])
 def test_oracle_parity_at_true_baseline_dims(name):
     _check(name)
+
+
+@pytest.mark.parametrize("name", ["cfg2", "cfg4"])
+def test_oracle_parity_bf16x3_gemm_and_conv(name):
+    """The kind::f16 2-term split (bf16x3) for linear forward / data gradient and conv forward / data gradient."""
+    _check(name, dict(linear="bf16x3", conv="bf16x3"))
 
 
 def test_oracle_parity_cfg2_exact_fp32_kernels():
