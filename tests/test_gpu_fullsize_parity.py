@@ -112,6 +112,14 @@ def _check(name, precision=None):
     r64f = O.forward_backward({k: v.double() for k, v in P.items()}, ocfg, src.double(), lens, tgt, 0.1, dec=O.Decisions(frozen=masks))
     g64f = {k: v.float() for k, v in r64f[5].items()}
     errs = grads_rel_err(grads, g64f)
+    # structurally zero gradients (a conv bias in front of BatchNorm, the key biases: the loss does not depend on them) are
+    # sums of O(1e6) cancelling terms -- pure rounding noise in ANY arithmetic (fp32 oracle: 2.5e-3 of the 1e-3 * gmax floor);
+    # bound them absolutely, at 1e-5 of the largest gradient in the model, instead of relative to the floor
+    gmax = max(float(v.abs().max()) for v in g64f.values())
+    for k, r in g64f.items():
+        if float(r.abs().max()) < 1e-6 * gmax:
+            assert float((grads[k].double() - r.double()).abs().max()) < 1e-5 * gmax, k
+            errs[k] = 0.0
     worst = max(errs, key=errs.get)
     med = sorted(errs.values())[len(errs) // 2]
     errs_unfrozen = grads_rel_err(grads, g64)
@@ -148,9 +156,10 @@ def test_oracle_parity_at_true_baseline_dims(name):
 
 
 @pytest.mark.parametrize("name", ["cfg2", "cfg4"])
-def test_oracle_parity_bf16x3_gemm_and_conv(name):
-    """The kind::f16 2-term split (bf16x3) for linear forward / data gradient and conv forward / data gradient."""
-    _check(name, dict(linear="bf16x3", conv="bf16x3"))
+def test_oracle_parity_3xtf32_everywhere(name):
+    """The kind::tf32 3xTF32 split for every contraction (the package default uses the kind::f16 bf16x3 split for the linear
+    and convolution forward / data gradient)."""
+    _check(name, dict(linear="tf32x3", conv="tf32x3", conv_wgrad="tf32x3", attn="tf32x3"))
 
 
 def test_oracle_parity_cfg2_exact_fp32_kernels():
