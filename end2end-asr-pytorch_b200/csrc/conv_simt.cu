@@ -641,9 +641,6 @@ int b200asr_conv3x3_bwd_weight(const float* dy, const float* x, float* dw, float
   cudaMemsetAsync(ws, 0, sizeof(float) * 9 * (size_t)Ci * Co, st);
   int rc;
   int bias_done = 0;
-  // the bf16 modes run the weight gradient (both operands activations) at the matching tf32 grade
-  if (precision == B200ASR_PREC_BF16X3) precision = B200ASR_PREC_TF32X3;
-  if (precision == B200ASR_PREC_BF16) precision = B200ASR_PREC_TF32;
   if (precision == B200ASR_PREC_FP32) rc = conv3x3_wgrad_simt(x, dy, (float*)ws, B, T, F, Ci, Co, st);
   else rc = conv3x3_wgrad_tc(x, dy, (float*)ws, B, T, F, Ci, Co, precision, st, dbias, &bias_done);
   if (rc) return rc;

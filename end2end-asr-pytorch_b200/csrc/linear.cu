@@ -13,11 +13,11 @@ static int gemm_dispatch(const float* A, bool ak, int lda, const float* B, bool 
   if (precision == B200ASR_PREC_TF32 || precision == B200ASR_PREC_TF32X3)
     return gemm_tc(A, ak, lda, B, bk, ldb, C, ldc, M, N, K, bias, relu, mask, accumulate, precision, st,
                    precision == B200ASR_PREC_TF32X3 ? b_split : nullptr, b_rows, rowsum);
-  // weight gradients contract over tokens with both operands activations (MN-major): they run the tf32 grade that matches
-  // the requested bf16 mode (bf16x3 -> 3xTF32, bf16 -> single TF32) until MN-major bf16 tiles exist
-  if (precision == B200ASR_PREC_BF16X3 || precision == B200ASR_PREC_BF16)
-    return gemm_tc(A, ak, lda, B, bk, ldb, C, ldc, M, N, K, bias, relu, mask, accumulate,
-                   precision == B200ASR_PREC_BF16X3 ? 3 : 1, st, nullptr, 0, rowsum);
+  // weight gradients (both operands MN-major fp32 activations): both tiles are converted to bf16 inside the kernel
+  if (precision == B200ASR_PREC_BF16X3 || precision == B200ASR_PREC_BF16) {
+    B200_REQUIRE(!ak && !bk, B200ASR_BAD_ARG, "bf16 GEMM without a pre-converted weight operand needs MN-major operands (weight gradient)");
+    return gemm_tc(A, ak, lda, B, bk, ldb, C, ldc, M, N, K, bias, relu, mask, accumulate, precision, st, nullptr, 0, rowsum);
+  }
   set_error("unknown precision %d", precision);
   return B200ASR_BAD_ARG;
 }
@@ -55,13 +55,10 @@ int b200asr_linear_bwd_weight(const float* dy, const float* x, float* dw, float*
                               int accumulate, int precision, b200asr_stream_t stream) {
   B200_REQUIRE(dy && x && dw && M >= 0 && N > 0 && K > 0, B200ASR_BAD_ARG, "linear_bwd_weight: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  // the bf16 modes run their weight gradients at the matching tf32 grade (see gemm_dispatch)
-  if (precision == B200ASR_PREC_BF16X3) precision = B200ASR_PREC_TF32X3;
-  if (precision == B200ASR_PREC_BF16) precision = B200ASR_PREC_TF32;
   // dw[n,k] = sum_m dy[m,n] x[m,k]: contraction over m; A(n,m) = dy[m*N + n], B(m,k) = x[m*K + k]
   // db[n] = sum_m dy[m,n] = row sums of A: the 3xTF32 kernel produces them from the tiles it stages (one launch and one
   // HBM pass over dy less); other precisions run the column-sum kernel
-  const bool fuse = dbias && precision == B200ASR_PREC_TF32X3 && gemm_tc_fuses_rowsum(false, false, 3) && M > 0;
+  const bool fuse = dbias && precision != B200ASR_PREC_FP32 && gemm_tc_fuses_rowsum(false, false, precision) && M > 0;
   if (fuse && !accumulate) cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)N, st);
   int rc = gemm_dispatch(dy, false, N, x, false, K, dw, K, N, K, M, nullptr, 0, nullptr, accumulate, true, precision, st,
                          nullptr, 0, fuse ? dbias : nullptr);

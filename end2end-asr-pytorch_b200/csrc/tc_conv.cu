@@ -164,6 +164,8 @@ struct WgradPolicy {
   }
   static __device__ __forceinline__ uint64_t a_desc(uint32_t s, int ks) { return make_smem_desc(s + ks * 1024, 4096, 512, kLayoutSW128Base32B); }
   static __device__ __forceinline__ uint64_t b_desc(uint32_t s, int ks) { return make_smem_desc(s + ks * 1024, 4096, 512, kLayoutSW128Base32B); }
+  // bf16 modes: the dy tile converted by the split warps into bf16 MN-major 64-column chunks (tc_engine.cuh)
+  static __device__ __forceinline__ uint64_t b_desc16(uint32_t s, int ks) { return make_smem_desc(s + ks * 2048, 4096, 1024, kLayoutSW128); }
   static __device__ __forceinline__ void store(const Params& p, const Tile& t, int r, int c0, const float (&v)[32]) {
     const int slot = r / CI, ci = r % CI;
     if (slot == 1 && t.tap_b == t.tap_a) return;
@@ -235,7 +237,7 @@ int conv3x3_wgrad_tc(const float* x, const float* dy, float* dwr, int B, int T, 
                      cudaStream_t st, float* dbias, int* dbias_done) {
   using namespace tc;
   if (dbias_done) *dbias_done = 0;
-  B200_REQUIRE(precision == 1 || precision == 3, B200ASR_BAD_ARG, "conv3x3_wgrad_tc: precision must be 1 or 3");
+  B200_REQUIRE(precision == 1 || precision == 3 || precision == 2 || precision == 6, B200ASR_BAD_ARG, "conv3x3_wgrad_tc: precision must be 1, 3 (tf32) or 2, 6 (bf16)");
   B200_REQUIRE((Ci == 64 || Ci == 128) && (Co == 64 || Co == 128), B200ASR_BAD_SHAPE,
                "conv3x3_wgrad_tc: needs Ci, Co in {64,128} (Ci=%d Co=%d)", Ci, Co);
   B200_REQUIRE(aligned16(x) && aligned16(dy) && aligned16(dwr), B200ASR_BAD_ALIGN, "conv3x3_wgrad_tc: alignment");
@@ -255,7 +257,7 @@ int conv3x3_wgrad_tc(const float* x, const float* dy, float* dwr, int B, int T, 
     int rc = make_tensor_map_f32(&mdy, dy, 4, dims, strides, box, true, tf32);
     if (rc) return rc;
   }
-  const bool fuse_bias = dbias != nullptr && precision == 3;
+  const bool fuse_bias = dbias != nullptr && precision != 1;
   if (fuse_bias) {
     cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)Co, st);
     if (dbias_done) *dbias_done = 1;
@@ -264,7 +266,13 @@ int conv3x3_wgrad_tc(const float* x, const float* dy, float* dwr, int B, int T, 
   const long long total = (long long)B * e.nft * e.ntt;
   B200_REQUIRE(total < (1LL << 31), B200ASR_BAD_SHAPE, "conv3x3_wgrad_tc: too many pixel blocks");
   e.total_blocks = (int)total;
-#define WGP(CIv, BNv) return precision == 1 ? launch_wgrad_persistent<CIv, BNv, 1>(mx, mdy, e, st) : launch_wgrad_persistent<CIv, BNv, 3>(mx, mdy, e, st)
+#define WGP(CIv, BNv)                                                                     \
+  switch (precision) {                                                                    \
+    case 1: return launch_wgrad_persistent<CIv, BNv, 1>(mx, mdy, e, st);                  \
+    case 3: return launch_wgrad_persistent<CIv, BNv, 3>(mx, mdy, e, st);                  \
+    case 6: return launch_wgrad_persistent<CIv, BNv, 6>(mx, mdy, e, st);                  \
+    default: return launch_wgrad_persistent<CIv, BNv, 2>(mx, mdy, e, st);                 \
+  }
   if (Ci == 64 && Co == 64) WGP(64, 64);
   if (Ci == 64 && Co == 128) WGP(64, 128);
   if (Ci == 128 && Co == 64) WGP(128, 64);

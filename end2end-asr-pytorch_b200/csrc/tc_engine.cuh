@@ -33,8 +33,12 @@ namespace tc {
 
 // NSPLIT selects the arithmetic: 1 = TF32 (SS-MMA), 3 = 3xTF32 (A split into TMEM, TS-MMA), and the kind::f16 modes
 // 2 = bf16 (A converted to bf16 into TMEM, one TS-MMA) and 6 = bf16x3 (2-term bf16 split, three TS-MMAs at twice the tf32
-// rate).  The bf16 modes need a K-major A tile (fp32, converted by the split warps) and a PRE-CONVERTED K-major bf16 B
-// operand ([hi] or [hi | lo], 64-byte rows, SWIZZLE_64B): Policy::load16 / Policy::b_desc16.
+// rate).  In the bf16 modes the fp32 A tile (K- or MN-major) is converted by the split warps on its way into TMEM, and B is
+//   * either a PRE-CONVERTED K-major bf16 operand ([hi] or [hi | lo], 64-byte rows, SWIZZLE_64B; Policy::load16) -- weights,
+//   * or (Policy::kSplitB, both operands MN-major: the weight-gradient GEMMs, whose operands are activations) the raw fp32
+//     MN-major tile, which the split warps convert into bf16 MN-major tiles (64 columns = 128 bytes per k-line, SWIZZLE_128B)
+//     in a second shared-memory region of the stage.
+// Policy::b_desc16 describes the bf16 B tile either way.
 constexpr bool eng_is_bf16(int nsplit) { return nsplit == 2 || nsplit == 6; }
 constexpr bool eng_has_split_warps(int nsplit) { return nsplit != 1; }
 
@@ -55,7 +59,8 @@ template <class Policy, int NSPLIT> struct EngineCfg {
   static constexpr int kBHalves = (NSPLIT == 3 || NSPLIT == 6) ? 2 : 1;                     // B tiles per stage (hi | lo)
   static constexpr int kBTile = kBf16 ? Policy::BN * 64 : Policy::kBBytes;                   // bf16: 32 k x 2 B = 64-byte rows
   static constexpr int kACols = NSPLIT == 3 ? 64 : (NSPLIT == 6 ? 32 : (NSPLIT == 2 ? 16 : 0));   // TMEM columns of A per stage
-  static constexpr int kStageBytes = Policy::kABytes + kBHalves * kBTile;
+  static constexpr int kBRaw = (kBf16 && Policy::kSplitB) ? Policy::kBBytes : 0;             // bf16 + in-kernel B conversion: raw fp32 tile
+  static constexpr int kStageBytes = Policy::kABytes + kBRaw + kBHalves * kBTile;
   static constexpr int kMaxByTmem = NSPLIT == 1 ? 8 : (512 - 2 * Policy::BN) / kACols;
   static constexpr int kBySmem = (200 * 1024) / kStageBytes;
 #ifndef ENG_MAX_STAGES
@@ -64,17 +69,18 @@ template <class Policy, int NSPLIT> struct EngineCfg {
   static constexpr int kStagesRaw = kBySmem < kMaxByTmem ? kBySmem : kMaxByTmem;
   static constexpr int kStagesCap = kStagesRaw > ENG_MAX_STAGES ? ENG_MAX_STAGES : kStagesRaw;
   static constexpr int kStages = NSPLIT == 1 ? kStagesCap : kStagesCap - kStagesCap % ENG_SPLIT_GROUPS;
-  static constexpr int kOffBhi = Policy::kABytes;
+  static constexpr int kOffBraw = Policy::kABytes;
+  static constexpr int kOffBhi = Policy::kABytes + kBRaw;
   static constexpr int kOffBlo = kOffBhi + kBTile;
   static constexpr int kBarOff = kStages * kStageBytes;
   static constexpr int kSmemBytes = kBarOff + 512 + 1024;
   static constexpr int kAccCols = 2 * Policy::BN;
   static constexpr int kTmemCols = NSPLIT != 1 ? 512 : (kAccCols <= 32 ? 32 : (kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : 256)));
-  static constexpr int kTxBytes = kBf16 ? Policy::kABytes + kBHalves * kBTile
+  static constexpr int kTxBytes = kBf16 ? Policy::kABytes + (Policy::kSplitB ? Policy::kBBytes : kBHalves * kBTile)
                                         : Policy::kABytes + Policy::kBBytes +
                                           (NSPLIT == 3 && !Policy::kSplitB ? Policy::kBBytes : 0);   // pre-split B arrives as hi+lo
-  static_assert(!kBf16 || (!Policy::kAMN && !Policy::kBMN && !Policy::kSplitB),
-                "bf16 modes: K-major fp32 A (converted in the kernel) and a pre-converted K-major bf16 B");
+  static_assert(!kBf16 || (!Policy::kAMN && !Policy::kBMN && !Policy::kSplitB) || (Policy::kAMN && Policy::kBMN && Policy::kSplitB),
+                "bf16 modes: K-major A with a pre-converted K-major bf16 B, or both operands MN-major fp32 (converted in the kernel)");
   static_assert(kStages >= 2, "stage too large");
   // Each split group must see EVERY phase of the full barriers it waits on: mbarrier parity waits only distinguish the
   // current phase from the one before, so a group that skipped a phase of a stage could take a stale completion for the
@@ -128,7 +134,8 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         mbar_wait(empty_bar(s), ((kbg / S) & 1) ^ 1);
         const uint32_t sa = smem_base + s * Cfg::kStageBytes;
         if (leader) mbar_expect_tx(full_bar(s), Cfg::kTxBytes);
-        if constexpr (Cfg::kBf16) Policy::load16(p, tc, &mapA, &mapB, sa, sa + Cfg::kOffBhi, sa + Cfg::kOffBlo, full_bar(s), leader, Cfg::kBHalves);
+        if constexpr (Cfg::kBf16 && !Policy::kSplitB) Policy::load16(p, tc, &mapA, &mapB, sa, sa + Cfg::kOffBhi, sa + Cfg::kOffBlo, full_bar(s), leader, Cfg::kBHalves);
+        else if constexpr (Cfg::kBf16) Policy::load(p, tc, &mapA, &mapB, sa, sa + Cfg::kOffBraw, 0u, full_bar(s), leader);     // raw fp32 A and B tiles
         else Policy::load(p, tc, &mapA, &mapB, sa, sa + Cfg::kOffBhi, sa + Cfg::kOffBlo, full_bar(s), leader);
         __syncwarp();
       }
@@ -144,7 +151,7 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     constexpr uint32_t idesc = make_idesc_tf32(128, BN, Policy::kAMN, Policy::kBMN);
     constexpr uint32_t idesc_ts = make_idesc_tf32(128, BN, false, Policy::kBMN);
     constexpr bool kNeedXfm = NSPLIT != 1;
-    constexpr uint32_t idesc_bf = make_idesc_bf16(128, BN, false, false);
+    constexpr uint32_t idesc_bf = make_idesc_bf16(128, BN, false, Policy::kBMN);
     constexpr uint32_t kStageStep = Cfg::kStageBytes >> 4, kLoStep = Cfg::kBTile >> 4;
     uint64_t bd0, ad0;
     uint32_t b_ks, a_ks;
@@ -229,39 +236,108 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   } else {
     // ------------------------------------------------------------------ operand split warps (3xTF32 only)
     if constexpr (Cfg::kBf16) {
-      // bf16 modes: the thread that owns A-tile row r reads its 32 fp32 k-values (128B-swizzled row), converts them to bf16
-      // (NSPLIT == 6: hi and lo of the 2-term split) and stores them PACKED, two k per 32-bit column, into TMEM.
-      constexpr int G = ENG_SPLIT_GROUPS, WPG = 8 / G;
+      // bf16 modes: the thread that owns A-tile row r reads its 32 fp32 k-values (K-major: one 128B-swizzled row; MN-major:
+      // one element per k-line), converts them to bf16 (NSPLIT == 6: hi and lo of the 2-term split) and stores them PACKED,
+      // two k per 32-bit column, into TMEM.  With Policy::kSplitB the group also converts the raw fp32 MN-major B tile into
+      // the bf16 MN-major tile(s) the tensor core reads.
+      constexpr int G = ENG_SPLIT_GROUPS, WPG = 8 / G, NT = ENG_SPLIT_THREADS / G;
       static_assert(WPG == 4, "bf16 split: one thread per A row and group");
       const int group = (warp - 6) / WPG;
+      const int t = threadIdx.x - 192 - group * NT;
       const int quarter = warp & 3;
       const int row = quarter * 32 + lane;
       uint32_t kbg = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int nkb = Policy::num_kb(p, tile);
+        constexpr bool kSums = Policy::kSumA || Policy::kSumB;
+        typename Policy::Tile stc;
+        bool want = false;
+        if constexpr (kSums) { stc = Policy::tile(p, tile); want = Policy::want_sums(p, stc); }
+        float asum = 0.f;
+        float4 bsum[BN / 32];
+#pragma unroll
+        for (int c = 0; c < BN / 32; c++) bsum[c] = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int kb = 0; kb < nkb; kb++, kbg++) {
           if ((int)(kbg % G) != group) continue;
           const int s = kbg % S;
           mbar_wait(full_bar(s), (kbg / S) & 1);
-          const uint8_t* araw = gen_base + s * Cfg::kStageBytes;
+          uint8_t* stage = gen_base + s * Cfg::kStageBytes;
+          const uint8_t* araw = stage;
           uint32_t hi[16], lo[16];
+          if constexpr (!Policy::kAMN) {
 #pragma unroll
-          for (int j = 0; j < 8; j++) {
-            const float4 x = *reinterpret_cast<const float4*>(araw + row * 128 + ((j ^ (row & 7)) << 4));
-            if constexpr (NSPLIT == 6) {
-              split_bf16_pair(x.x, x.y, hi[2 * j], lo[2 * j]);
-              split_bf16_pair(x.z, x.w, hi[2 * j + 1], lo[2 * j + 1]);
-            } else {
-              hi[2 * j] = pack_bf16_pair(x.x, x.y);
-              hi[2 * j + 1] = pack_bf16_pair(x.z, x.w);
+            for (int j = 0; j < 8; j++) {
+              const float4 x = *reinterpret_cast<const float4*>(araw + row * 128 + ((j ^ (row & 7)) << 4));
+              if constexpr (NSPLIT == 6) {
+                split_bf16_pair(x.x, x.y, hi[2 * j], lo[2 * j]);
+                split_bf16_pair(x.z, x.w, hi[2 * j + 1], lo[2 * j + 1]);
+              } else {
+                hi[2 * j] = pack_bf16_pair(x.x, x.y);
+                hi[2 * j + 1] = pack_bf16_pair(x.z, x.w);
+              }
+            }
+          } else {
+            // MN-major tile: chunk (row/32) of 32 k-lines x 128 B; 32-byte atom a = (row%32)/8 stored at atom (a ^ (k & 3))
+            const uint8_t* cbase = araw + (row >> 5) * 4096 + (row & 7) * 4;
+            const int atom = (row & 31) >> 3;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+              const float x0 = *reinterpret_cast<const float*>(cbase + (2 * j) * 128 + ((atom ^ ((2 * j) & 3)) << 5));
+              const float x1 = *reinterpret_cast<const float*>(cbase + (2 * j + 1) * 128 + ((atom ^ ((2 * j + 1) & 3)) << 5));
+              if constexpr (NSPLIT == 6) split_bf16_pair(x0, x1, hi[j], lo[j]);
+              else hi[j] = pack_bf16_pair(x0, x1);
+              if constexpr (Policy::kSumA) asum += x0 + x1;
             }
           }
           const uint32_t acol = tmem_base + ((uint32_t)(quarter * 32) << 16) + Cfg::kAccCols + s * Cfg::kACols;
           tmem_st16u(acol, hi);
           if constexpr (NSPLIT == 6) tmem_st16u(acol + 16, lo);
+          if constexpr (Policy::kSplitB) {
+            // raw tile: float4 i sits in 4 KB chunk i / 256 (32 columns), k-line (i % 256) / 8, 16-byte slot i % 8, and the
+            // logical 32-byte atom is (slot / 2) ^ (k & 3) (SWIZZLE_128B_ATOM_32B).  bf16 tile: 64-column chunks of 4 KB, k-line
+            // k at k * 128, 16-byte unit (8 columns) u stored at unit u ^ (k & 7) (SWIZZLE_128B).
+            const float4* braw = reinterpret_cast<const float4*>(stage + Cfg::kOffBraw);
+            uint8_t* bhi = stage + Cfg::kOffBhi;
+            uint8_t* blo = stage + Cfg::kOffBlo;
+            constexpr int NF4 = Policy::kBBytes / 16;
+#pragma unroll
+            for (int j = 0; j < NF4 / NT; j++) {
+              const int idx = t + j * NT;
+              const float4 x = braw[idx];
+              const int k = (idx & 255) >> 3, slot = idx & 7;
+              const int n = ((idx >> 8) << 5) + ((((slot >> 1) ^ (k & 3))) << 3) + ((slot & 1) << 2);
+              const int off = ((n >> 6) << 12) + (k << 7) + (((((n & 63) >> 3) ^ (k & 7))) << 4) + ((n & 7) << 1);
+              uint2 h, l;
+              if constexpr (NSPLIT == 6) {
+                split_bf16_pair(x.x, x.y, h.x, l.x);
+                split_bf16_pair(x.z, x.w, h.y, l.y);
+                *reinterpret_cast<uint2*>(blo + off) = l;
+              } else {
+                h.x = pack_bf16_pair(x.x, x.y);
+                h.y = pack_bf16_pair(x.z, x.w);
+              }
+              *reinterpret_cast<uint2*>(bhi + off) = h;
+              if constexpr (Policy::kSumB) {
+                float4& acc = bsum[(j * NT) / 256];
+                acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+              }
+            }
+            fence_proxy_async_smem();
+          }
           tmem_wait_st();
           tc_fence_before();
           mbar_arrive(xfm_bar(s));
+        }
+        if constexpr (kSums) {
+          if (want) {
+            if constexpr (Policy::kSumA) Policy::sum_a_store(p, stc, row, asum);
+            if constexpr (Policy::kSumB) {
+              const int slot = t & 7, kph = (t >> 3) & 3;
+              const int col_in_chunk = (((slot >> 1) ^ kph) << 3) + ((slot & 1) << 2);
+#pragma unroll
+              for (int c = 0; c < BN / 32; c++) Policy::sum_b_store(p, stc, c * 32 + col_in_chunk, bsum[c]);
+            }
+          }
         }
       }
     } else if (NSPLIT == 3) {

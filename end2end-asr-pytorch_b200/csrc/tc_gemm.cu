@@ -138,7 +138,11 @@ struct GemmPolicy {
     tma_load_2d(sb, mapB, bar, k0, n0);
     if (halves == 2) tma_load_2d(sb_lo, mapB, bar, k0, n0 + p.b_rows);
   }
-  static __device__ __forceinline__ uint64_t b_desc16(uint32_t s, int ks) { return make_smem_desc(s + ks * 32, 16, 512, kLayoutSW64); }
+  // bf16 B tile: K-major (pre-converted weights): 64-byte rows, SWIZZLE_64B, a 16-deep k-step = 32 B along the row;
+  // MN-major (converted in the kernel): 64-column chunks of 4 KB, 8-k-line swizzle groups of 1 KB, a k-step = 16 k-lines = 2 KB
+  static __device__ __forceinline__ uint64_t b_desc16(uint32_t s, int ks) {
+    return B_MN ? make_smem_desc(s + ks * 2048, 4096, 1024, kLayoutSW128) : make_smem_desc(s + ks * 32, 16, 512, kLayoutSW64);
+  }
   // every (row, k) of A is staged once by the n-tile-0 tiles (over all k-splits)
   static __device__ __forceinline__ bool want_sums(const Params& p, const Tile& t) { return p.e.rowsum != nullptr && t.n0 == 0; }
   static __device__ __forceinline__ void sum_a_store(const Params& p, const Tile& t, int r, float v) {
@@ -229,14 +233,14 @@ static int launch_persistent(const CUtensorMap& ma, const CUtensorMap& mb, const
 
 }  // namespace tc
 
-bool gemm_tc_fuses_rowsum(bool a_kmaj, bool b_kmaj, int nsplit) { return !a_kmaj && !b_kmaj && nsplit == 3; }
+bool gemm_tc_fuses_rowsum(bool a_kmaj, bool b_kmaj, int nsplit) { return !a_kmaj && !b_kmaj && (nsplit == 3 || nsplit == 6 || nsplit == 2); }
 
 int gemm_tc(const float* A, bool a_kmaj, int lda, const float* B, bool b_kmaj, int ldb, float* C, int ldc, int M, int N,
             int K, const float* bias, int relu, const float* relu_mask, int accumulate, int nsplit, cudaStream_t st,
             const void* b_split, int b_rows, float* rowsum) {
   using namespace tc;
   if (M <= 0 || N <= 0) return B200ASR_OK;
-  if (eng_is_bf16(nsplit)) {
+  if (eng_is_bf16(nsplit) && !(!a_kmaj && !b_kmaj)) {
     // kind::f16 modes: fp32 K-major A converted in the kernel, pre-converted K-major bf16 B
     B200_REQUIRE(a_kmaj && b_split && b_rows >= N, B200ASR_BAD_ARG, "gemm_tc (bf16): needs a K-major A and the bf16 operand from b200asr_split_bf16");
     B200_REQUIRE(aligned16(A) && aligned16(b_split) && lda % 4 == 0 && ldb % 8 == 0, B200ASR_BAD_SHAPE,
@@ -259,7 +263,8 @@ int gemm_tc(const float* A, bool a_kmaj, int lda, const float* B, bool b_kmaj, i
   }
   const bool presplit = b_split != nullptr && nsplit == 3 && a_kmaj;   // fwd (B K-major) and dgrad (B MN-major)
   if (presplit) B = (const float*)b_split;
-  B200_REQUIRE(nsplit == 1 || nsplit == 3, B200ASR_BAD_ARG, "gemm_tc: nsplit must be 1, 3 (tf32) or 2, 6 (bf16)");
+  // (bf16 modes with both operands MN-major -- weight gradients -- take the fp32 maps below: both tiles are converted in the kernel)
+  B200_REQUIRE(nsplit == 1 || nsplit == 3 || nsplit == 2 || nsplit == 6, B200ASR_BAD_ARG, "gemm_tc: nsplit must be 1, 3 (tf32) or 2, 6 (bf16)");
   B200_REQUIRE(aligned16(A) && aligned16(B) && lda % 4 == 0 && ldb % 4 == 0, B200ASR_BAD_SHAPE,
                "gemm_tc: TMA needs 16-byte aligned operands and leading dimensions that are multiples of 4 (lda=%d ldb=%d); "
                "use precision 0 for this shape", lda, ldb);
@@ -303,6 +308,8 @@ int gemm_tc(const float* A, bool a_kmaj, int lda, const float* B, bool b_kmaj, i
     if (!b_mn) return launch_persistent<false, false, 3, true>(ma, mb, e, st, b_rows);
     return launch_persistent<false, true, 3, true>(ma, mb, e, st, b_rows);
   }
+  if (nsplit == 6) GO(true, true, 6);
+  if (nsplit == 2) GO(true, true, 2);
   if (nsplit == 1) {
     if (!a_mn && !b_mn) GO(false, false, 1);
     if (!a_mn && b_mn) GO(false, true, 1);

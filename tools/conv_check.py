@@ -23,6 +23,11 @@ for (B, T, Fq, Ci, Co) in [(1, 16, 8, 32, 64), (2, 37, 21, 64, 64), (2, 40, 40, 
     xn = x.permute(0, 3, 2, 1).double()                            # (B, C, F, T)
     y64 = F.conv2d(xn, w.double(), bias.double(), padding=1).permute(0, 3, 2, 1)
     dx64 = torch.autograd.grad(F.conv2d(xn.requires_grad_(True), w.double(), None, padding=1), xn, dy.permute(0, 3, 2, 1).double())[0].permute(0, 3, 2, 1)
+    xg = xn.detach().clone().requires_grad_(False)
+    w64 = w.double().requires_grad_(True)
+    b64 = bias.double().requires_grad_(True)
+    F.conv2d(xg, w64, b64, padding=1).backward(dy.permute(0, 3, 2, 1).double())
+    dw64, db64 = w64.grad, b64.grad
     ws = torch.empty(lib.b200asr_conv3x3_ws_bytes(max(Ci, Co), max(Ci, Co)) // 4, device="cuda")
     line = f"B={B} T={T} F={Fq} Ci={Ci} Co={Co} |"
     for prec in (0, 1, 3, 2, 6):
@@ -36,5 +41,15 @@ for (B, T, Fq, Ci, Co) in [(1, 16, 8, 32, 64), (2, 37, 21, 64, 64), (2, 40, 40, 
             continue
         ey = float((y.double() - y64).abs().max() / y64.abs().max())
         ex = float((dx.double() - dx64).abs().max() / dx64.abs().max())
-        line += f" p{prec}: fwd {ey:.1e} dgrad {ex:.1e} |"
+        line += f" p{prec}: fwd {ey:.1e} dgrad {ex:.1e}"
+        if Ci % 64 == 0:
+            dw = torch.empty_like(w)
+            db = torch.empty_like(bias)
+            rc3 = lib.b200asr_conv3x3_bwd_weight(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), B, T, Fq, Ci, Co, prec, st)
+            torch.cuda.synchronize()
+            if rc3:
+                line += f" wgrad rc {rc3} {L.last_error()[:50]}"
+            else:
+                line += f" wgrad {float((dw.double() - dw64).abs().max() / dw64.abs().max()):.1e} db {float((db.double() - db64).abs().max() / db64.abs().max()):.1e}"
+        line += " |"
     print(line, flush=True)
