@@ -34,7 +34,7 @@ class _Config:
         self.linear = _PREC_NAMES[os.environ.get("B200ASR_LINEAR", "bf16x3")]
         self.conv = _PREC_NAMES[os.environ.get("B200ASR_CONV", "bf16x3")]
         self.conv_wgrad = _PREC_NAMES[os.environ.get("B200ASR_CONV_WGRAD", "tf32x3")]
-        self.attn = _PREC_NAMES[os.environ.get("B200ASR_ATTN", "tf32x3")]
+        self.attn = _PREC_NAMES[os.environ.get("B200ASR_ATTN", "bf16x3")]
         self.attn_bwd = _PREC_NAMES[os.environ.get("B200ASR_ATTN_BWD", "fp32")]
 
     def set(self, linear=None, conv=None, attn=None, conv_wgrad=None, attn_bwd=None):
@@ -381,6 +381,19 @@ def _sdpa_forward_impl(q, k, v, key_pad, dense_mask, causal, scale, p_drop, head
     # 32-float k-blocks and rows of at most 2048 keys; the TF32 flash kernel keeps the score row in TMEM
     # (Tk <= 448, d in {32,64}); everything else runs on the fp32 CUDA-core kernel
     prec = config.attn
+    if prec == L.PREC_BF16X3 and not (dk == 64 and dv == 64 and Tk <= 448 and not head_major_out):
+        prec = L.PREC_TF32X3     # the fused kind::f16 kernels keep the score row in TMEM (Tk <= 448) and take 64-wide heads
+    if prec == L.PREC_BF16:
+        prec = L.PREC_TF32       # "bf16" (cfg5) attention = the single-pass TF32 flash kernels
+    if prec == L.PREC_BF16X3:
+        lib = _lib()
+        ws16 = torch.empty(lib.b200asr_sdpa_fused_ws_bytes(B, H, Tq, Tk) // 2, device=q.device, dtype=torch.bfloat16)
+        lse = torch.empty((B, H, Tq), device=q.device, dtype=torch.float32)
+        L.check(lib.b200asr_sdpa_fused_fwd(L.ptr(q), L.ptr(k), L.ptr(v), *qs, *ks, *vs, L.ptr(key_pad), L.ptr(dense_mask), int(causal),
+                                           L.ptr(out), *os_, L.ptr(lse), L.ptr(ws16), B, H, Tq, Tk, dk, dv, float(scale), float(p_drop),
+                                           seed, off, _stream()), "sdpa_fused_fwd")
+        return out, dict(mat=False, fused=True, tensors=(q, k, v, out, lse, key_pad, dense_mask, ws16),
+                         meta=(int(causal), float(scale), float(p_drop), seed, off, prec))
     if prec == L.PREC_TF32X3 and not (dk % 32 == 0 and dv % 32 == 0 and dk <= 256 and dv <= 256 and Tk <= 2048):
         prec = L.PREC_FP32
     if prec == L.PREC_TF32 and not (Tk <= 448 and dk in (32, 64) and dv in (32, 64)):
@@ -434,6 +447,14 @@ def _sdpa_backward_impl(state, dout, dq=None, dkk=None, dvv=None):
                                             dk, dv, scale, p_drop, seed, off, prec, _stream()), "sdpa_mat_bwd")
         return dq, dkk, dvv
     lse, key_pad, dense_mask = state["tensors"][4:7]
+    if state.get("fused"):
+        lib = _lib()
+        ws16 = state["tensors"][7]
+        wsb = torch.empty(lib.b200asr_sdpa_fused_bwd_ws_bytes(B, H, Tq) // 4, device=q.device, dtype=torch.float32)
+        L.check(lib.b200asr_sdpa_fused_bwd(L.ptr(dout), L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(out), L.ptr(lse), *qs, *ks, *vs, *os_,
+                                           L.ptr(key_pad), L.ptr(dense_mask), causal, L.ptr(dq), L.ptr(dkk), L.ptr(dvv), L.ptr(ws16),
+                                           L.ptr(wsb), B, H, Tq, Tk, dk, dv, scale, p_drop, seed, off, _stream()), "sdpa_fused_bwd")
+        return dq, dkk, dvv
     delta = torch.empty((B, H, Tq), device=q.device, dtype=torch.float32)
     L.check(_lib().b200asr_sdpa_bwd(L.ptr(dout), L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(out), L.ptr(lse), *qs, *ks, *vs, *os_,
                                     L.ptr(key_pad), L.ptr(dense_mask), causal, L.ptr(dq), L.ptr(dkk), L.ptr(dvv),

@@ -129,6 +129,29 @@ int b200asr_sdpa_bwd(const float* dout, const float* q, const float* k, const fl
                      float* delta_ws, int B, int H, int Tq, int Tk, int dk, int dv, float scale, float p_drop,
                      uint64_t seed, uint64_t offset, int precision, b200asr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused attention at fp32 grade (the default path): ScaledDotProductAttention.forward, models/common_layers.py:211-225,
+ * as ONE forward kernel (QK^T and PV on tcgen05 kind::f16 with the 2-term bf16 split, masks + softmax + dropout on the
+ * accumulator in tensor memory) and TWO backward kernels that recompute the probabilities from Q, K and the forward's
+ * log-sum-exp.  Same view / mask / dropout conventions as b200asr_sdpa_fwd.  Needs dk = dv = 64 and (forward) Tk <= 448.
+ * ws16: b200asr_sdpa_fused_ws_bytes(B,H,Tq,Tk) bytes -- the bf16 hi / lo copies of q, k, v the forward makes; the SAME
+ * buffer must be handed to the backward.  ws_bwd: b200asr_sdpa_fused_bwd_ws_bytes(B,H,Tq) bytes of scratch.
+ */
+size_t b200asr_sdpa_fused_ws_bytes(int B, int H, int Tq, int Tk);
+size_t b200asr_sdpa_fused_bwd_ws_bytes(int B, int H, int Tq);
+int b200asr_sdpa_fused_fwd(const float* q, const float* k, const float* v, long long q_bs, long long q_hs, long long q_rs,
+                           long long k_bs, long long k_hs, long long k_rs, long long v_bs, long long v_hs, long long v_rs,
+                           const uint8_t* key_pad, const uint8_t* dense_mask, int causal, float* out, long long o_bs,
+                           long long o_hs, long long o_rs, float* lse, void* ws16, int B, int H, int Tq, int Tk, int dk,
+                           int dv, float scale, float p_drop, uint64_t seed, uint64_t offset, b200asr_stream_t stream);
+int b200asr_sdpa_fused_bwd(const float* dout, const float* q, const float* k, const float* v, const float* out,
+                           const float* lse, long long q_bs, long long q_hs, long long q_rs, long long k_bs,
+                           long long k_hs, long long k_rs, long long v_bs, long long v_hs, long long v_rs, long long o_bs,
+                           long long o_hs, long long o_rs, const uint8_t* key_pad, const uint8_t* dense_mask, int causal,
+                           float* dq, float* dk_out, float* dv_out, const void* ws16, void* ws_bwd, int B, int H, int Tq,
+                           int Tk, int dk, int dv, float scale, float p_drop, uint64_t seed, uint64_t offset,
+                           b200asr_stream_t stream);
+
 /* Materialised attention (precision 1 = TF32, 3 = 3xTF32): the same contract as b200asr_sdpa_fwd/_bwd
  * (models/common_layers.py:211-225; head views addressed by strides; dropout drawn from the same counter stream, so
  * both paths produce identical masks), computed op for op like the reference -- bmm, masked softmax, dropout, bmm --

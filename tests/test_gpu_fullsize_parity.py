@@ -76,7 +76,7 @@ def _truth(name):
     return _cache[name]
 
 
-def _check(name, precision=None):
+def _check(name, precision=None, tol=TOL, tol_grad=TOL, fp32_grade=True):
     import importlib
     import b200asr
     from tests.gpu_util import cuda_model, cuda_step_with_decisions
@@ -140,13 +140,14 @@ def _check(name, precision=None):
           f"[unfrozen: max {max(errs_unfrozen.values()):.2e} median {sorted(errs_unfrozen.values())[len(errs) // 2]:.2e}; "
           f"fp32 oracle vs fp64, unfrozen: max {ref_errs[ref_worst]:.2e}]  (frozen oracle run {time.time() - t0:.1f} s)")
     assert int(stats[1]) == n_word
-    assert e_pred < TOL, e_pred
-    assert e_loss < TOL, e_loss
+    assert e_pred < tol, e_pred
+    assert e_loss < tol, e_loss
     assert flips_dec == 0
-    assert float(decidable.float().sum() / real.float().sum()) > 0.97       # the tie band stays a small minority
-    assert n_flip <= 1e-5 * n_units, (n_flip, n_units)                      # differing decisions: a vanishing minority ...
-    assert worst_band < 1e-4, worst_band                                    # ... and every one a unit sitting on its threshold
-    assert errs[worst] < TOL, (worst, errs[worst])                          # every gradient tensor, max norm
+    if fp32_grade:
+        assert float(decidable.float().sum() / real.float().sum()) > 0.97   # the tie band stays a small minority
+        assert n_flip <= 1e-5 * n_units, (n_flip, n_units)                  # differing decisions: a vanishing minority ...
+        assert worst_band < 1e-4, worst_band                                # ... and every one a unit sitting on its threshold
+    assert errs[worst] < tol_grad, (worst, errs[worst])                     # every gradient tensor, max norm
     return e_pred, errs
 
 
@@ -160,6 +161,15 @@ def test_oracle_parity_3xtf32_everywhere(name):
     """The kind::tf32 3xTF32 split for every contraction (the package default uses the kind::f16 bf16x3 split for the linear
     and convolution forward / data gradient)."""
     _check(name, dict(linear="tf32x3", conv="tf32x3", conv_wgrad="tf32x3", attn="tf32x3"))
+
+
+def test_cfg5_in_bf16_as_baseline_json_asks():
+    """BASELINE.json configs[4] is quoted in bf16: one kind::f16 MMA per product (bf16 operands, fp32 accumulate, fp32 master
+    weights and activations in HBM) for every linear / convolution GEMM incl. the weight gradients, single-pass TF32 flash
+    attention.  Tolerance stated separately, as SURVEY.md 8d asks -- bf16 cannot meet 1e-3: measured logits 9e-3, loss 2e-4,
+    gradients 2e-2 (max norm, at the path's own decisions); bars 3e-2 / 3e-2 / 6e-2."""
+    _check("cfg5", dict(linear="bf16", conv="bf16", conv_wgrad="bf16", attn="tf32", attn_bwd="tf32"), tol=3e-2, tol_grad=6e-2,
+           fp32_grade=False)
 
 
 def test_oracle_parity_cfg2_exact_fp32_kernels():

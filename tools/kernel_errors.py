@@ -19,8 +19,9 @@ def err(a, b):
     return "%.1e [%.1e]" % (float((a - b).abs().max() / b.abs().max()), float((a - b).norm() / b.norm()))
 
 
+only_attn = "--attn" in sys.argv
 print("---- linear: y = x w^T + b, dx = dy w, dw = dy^T x, db")
-for (M, N, K) in [(400, 512, 512), (800, 1536, 512), (6400, 2048, 512), (6400, 512, 2048), (400, 4364, 512), (800, 512, 5120)]:
+for (M, N, K) in [] if only_attn else [(400, 512, 512), (800, 1536, 512), (6400, 2048, 512), (6400, 512, 2048), (400, 4364, 512), (800, 512, 5120)]:
     x = torch.randn(M, K, device="cuda")
     w = torch.randn(N, K, device="cuda") * K ** -0.5
     b = torch.randn(N, device="cuda")
@@ -37,7 +38,7 @@ for (M, N, K) in [(400, 512, 512), (800, 1536, 512), (6400, 2048, 512), (6400, 5
         print(f"M={M:5d} N={N:5d} K={K:5d} p{prec}: fwd {err(y, y64)}  dgrad {err(dx, dx64)}  wgrad {err(dw, dw64)}  dbias {err(db, db64)}", flush=True)
 
 print("---- attention (B=4, H=8): out, dq, dk, dv")
-for (Tq, Tk, causal) in [(200, 200, False), (100, 100, True), (100, 200, False)]:
+for (Tq, Tk, causal) in [(200, 200, False), (100, 100, True), (100, 200, False), (250, 250, False), (400, 400, False), (37, 150, False)]:
     B, H, d = 4, 8, 64
     q = torch.randn(B, Tq, H, d, device="cuda").permute(0, 2, 1, 3)
     k = torch.randn(B, Tk, H, d, device="cuda").permute(0, 2, 1, 3)
@@ -50,7 +51,7 @@ for (Tq, Tk, causal) in [(200, 200, False), (100, 100, True), (100, 200, False)]
             s = s.masked_fill(torch.triu(torch.ones(Tq, Tk, device="cuda", dtype=torch.bool), 1), float("-inf"))
         o64 = torch.softmax(s, -1) @ v64
         o64.backward(do.double())
-        for attn in ("fp32", "tf32x3", "tf32"):
+        for attn in ("fp32", "tf32x3", "bf16x3", "tf32"):
             ops.config.set(attn=attn, attn_bwd="tf32" if attn == "tf32" else "fp32")
             qq = (q * qs).detach().clone().requires_grad_(True); kk = k.detach().clone().requires_grad_(True); vv = v.detach().clone().requires_grad_(True)
             o = ops.SdpaFn.apply(qq, kk, vv, None, None, causal, 1.0 / 8.0, 0.0)
