@@ -19,11 +19,19 @@ class FlatParams:
     The gradient buffer carries `extra` trailing floats (used for [sum-loss, n_tokens]) so that they ride in
     the same all-reduce as the gradients."""
 
-    def __init__(self, module: torch.nn.Module, extra: int = 2):
+    def __init__(self, module: torch.nn.Module, extra: int = 2, tail=("conv",)):
+        """tail: names of submodules whose parameters go to the END of the buffers (default: the CNN front end `conv`).  Their
+        gradients are the last ones backward produces, so everything before `tail_offset` can be all-reduced while the front
+        end's backward is still running (parallel.DataParallelStep)."""
         seen, params = set(), []
+        tail_ids = set()
+        for name in tail:
+            sub = getattr(module, name, None)
+            if isinstance(sub, torch.nn.Module):
+                tail_ids.update(id(p) for p in sub.parameters())
 
-        def take(p):
-            if p is not None and p.requires_grad and id(p) not in seen:
+        def take(p, tail_pass=False):
+            if p is not None and p.requires_grad and id(p) not in seen and (tail_pass or id(p) not in tail_ids):
                 seen.add(id(p))
                 params.append(p)
 
@@ -38,6 +46,9 @@ class FlatParams:
                     take(l.bias)
         for p in module.parameters():
             take(p)
+        n_head = len(params)
+        for p in module.parameters():
+            take(p, tail_pass=True)
         self.params = params
         dev = params[0].device
         sizes = [p.numel() for p in params]
@@ -47,6 +58,7 @@ class FlatParams:
             self.offsets.append(off)
             off += (n + 3) // 4 * 4
         self.numel = off
+        self.tail_offset = self.offsets[n_head] if n_head < len(params) else off      # first element of the tail parameters
         self.extra = extra
         self.flat = torch.zeros(off, device=dev, dtype=torch.float32)
         self.flat_grad = torch.zeros(off + extra, device=dev, dtype=torch.float32)

@@ -42,6 +42,8 @@ class DataParallelStep:
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.clip = clip_max_norm
+        self.overlap = True          # all-reduce the transformer's gradients under the CNN front end's backward
+        self._early = None
         self._scale = torch.zeros(4, device=self.flat.flat.device, dtype=torch.float32)    # [scale, grad norm, scratch, -]
         self._host_tail = loss_fn is not None or adam_factory is not None                  # CPU stand-ins (gloo tests)
         if self.world > 1:
@@ -52,18 +54,38 @@ class DataParallelStep:
             # ... but draw DIFFERENT dropout masks for their shards (the kernels' counter-based generator is seeded per process)
             ops.rng.seed = (ops.rng.seed ^ (0x9E3779B97F4A7C15 * (dist.get_rank(process_group) + 1))) & 0xFFFFFFFFFFFFFFFF
 
+    def _reduce_head_early(self):
+        """Runs at the start of the CNN front end's backward (ops.frontend_backward_hook): every gradient before
+        flat.tail_offset is final, so their all-reduce is issued now, on NCCL's own stream, under the convolution backward."""
+        if self.world > 1 and self._early is None and 0 < self.flat.tail_offset < self.flat.numel:
+            self._early = dist.all_reduce(self.flat.flat_grad[:self.flat.tail_offset], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+
     def forward_backward(self, src, lengths, tgt):
         """Local shard fwd+bwd with the un-normalised loss; gradients land in the flat buffer."""
         self.flat.zero_grad()
         pred, gold, hyp, _ = self.model(src, lengths, tgt)
         loss_sum, stats = self.loss_fn(pred, gold, self.smoothing, reduction="sum")
-        loss_sum.backward()
+        self._early = None
+        prev, ops.frontend_backward_hook = ops.frontend_backward_hook, (self._reduce_head_early if self.overlap else None)
+        try:
+            loss_sum.backward()
+        finally:
+            ops.frontend_backward_hook = prev
         self.flat.ensure_grad_views()
         self.flat.extras.copy_(stats[0:2])            # [sum-loss, n_tokens] ride with the gradients
         return pred, hyp, stats
 
     def all_reduce(self):
-        if self.world > 1:
+        """ONE logical all-reduce(SUM) of [flat grads | sum-loss | n_tokens] per step (the reference's --parallel reduce,
+        utils/functions.py:154-160): issued as a head part that overlaps the front end's backward (when forward_backward
+        could launch it) and the remaining tail (front-end gradients + the two scalars), or in one piece otherwise."""
+        if self.world <= 1:
+            return
+        if self._early is not None:
+            dist.all_reduce(self.flat.flat_grad[self.flat.tail_offset:], op=dist.ReduceOp.SUM, group=self.pg)
+            self._early.wait()
+            self._early = None
+        else:
             dist.all_reduce(self.flat.flat_grad, op=dist.ReduceOp.SUM, group=self.pg)
 
     def optimizer_step(self):

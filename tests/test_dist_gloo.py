@@ -28,6 +28,34 @@ class TinyModel(torch.nn.Module):
         return pred, tgt, pred.argmax(-1), tgt
 
 
+class _FrontEndBoundary(torch.autograd.Function):
+    """Stands in for the CNN front end's backward entry (ops.VggFrontendFn.backward calls ops.frontend_backward_hook first)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        import importlib
+        ops = importlib.import_module(b200asr.__name__ + ".ops")
+        if ops.frontend_backward_hook is not None:
+            ops.frontend_backward_hook()
+        return g
+
+
+class TinyModelWithFrontEnd(TinyModel):
+    """A `conv` front end in front of the rest: its parameters go to the tail of the flat buffers and the head part of the
+    gradient all-reduce is launched while its backward is still to run (DataParallelStep._reduce_head_early)."""
+
+    def __init__(self, V=11):
+        super().__init__(V)
+        self.conv = torch.nn.Linear(6, 6)
+
+    def forward(self, src, lengths, tgt):
+        return super().forward(_FrontEndBoundary.apply(self.conv(src)), lengths, tgt)
+
+
 def cpu_loss(pred, gold, smoothing, reduction="mean"):
     loss, n = O.cross_entropy_loss(pred, gold, smoothing)
     s = loss * n
@@ -70,24 +98,29 @@ def run_steps(model, world_group, rank, world, steps=3):
     return losses, dp.flat.flat.clone()
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, cls="TinyModel"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.manual_seed(rank)          # ranks build DIFFERENT replicas: DataParallelStep broadcasts rank 0's (seed 0) parameters
-    model = TinyModel()
+    model = globals()[cls]()
     losses, flat = run_steps(model, None, rank, world)
     q.put((rank, losses, flat))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_rank_step_equals_single_rank_global_batch():
+@pytest.mark.parametrize("cls", ["TinyModel", "TinyModelWithFrontEnd"])
+def test_two_rank_step_equals_single_rank_global_batch(cls):
     torch.manual_seed(0)
-    ref_losses, ref_flat = run_steps(TinyModel(), None, 0, 1)
+    ref_model = globals()[cls]()
+    ref_losses, ref_flat = run_steps(ref_model, None, 0, 1)
+    if cls == "TinyModelWithFrontEnd":
+        flat = b200asr.FlatParams(globals()[cls]())
+        assert 0 < flat.tail_offset < flat.numel and flat.params[-1].shape == (6,)      # conv.weight, conv.bias at the tail
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, cls)) for r in range(2)]
     for p in procs:
         p.start()
     results = [q.get(timeout=120) for _ in range(2)]
