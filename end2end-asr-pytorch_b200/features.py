@@ -43,6 +43,7 @@ def spectrogram_batch(waves: Sequence[torch.Tensor] | torch.Tensor, lengths: tor
     out = torch.empty((B, 1, nb, t_max), device=wave.device, dtype=torch.float32)
     frames = torch.empty(B, device=wave.device, dtype=torch.int32)
     prec = ops.config.linear if precision is None else precision
+    prec = {L.PREC_BF16X3: L.PREC_TF32X3, L.PREC_BF16: L.PREC_TF32}.get(prec, prec)      # the DFT basis is an fp32 operand: tf32 grades
     L.check(lib.b200asr_stft_features(L.ptr(wave), L.ptr(lens), L.ptr(out), L.ptr(frames), L.ptr(ws), B, Lmax, t_max, n_fft, hop,
                                       int(reflect), int(normalize), int(window_periodic), prec, ops._stream()), "stft_features")
     return out, frames.float() / float(t_max), frames

@@ -25,6 +25,13 @@ class _Config:
     gradient, "tf32x3" (kind::tf32) for the weight gradients and the attention contractions.  Measured at the TRUE cfg2
     dims against the fp64 oracle (tests/test_gpu_fullsize_parity.py): logits 1.7e-5, every gradient tensor < 7e-5 in the
     max norm at the path's own ReLU / pooling decisions (3xTF32 everywhere: 1.2e-5 / 5e-5; fp32 CUDA cores: 1.5e-6 / 4e-5).
+    Attention: the default "tf32x3" is the materialised path (batched 3xTF32 GEMMs around exact fp32 softmax kernels; at
+    these shapes -- T <= 250, 256 heads -- the 41 MB score tensor stays in the 126 MB L2); "bf16x3" selects the fused
+    kind::f16 kernels (tc_attention16.cu: QK^T / PV with masks, softmax and dropout on the accumulator in tensor memory, the
+    backward recomputing the probabilities).  Measured at cfg2: outputs and gradients ~1e-5 at kernel level, but the
+    flash-style delta = rowsum(dO o O) injects a row-constant error into dS that the near-uniform attention of this model
+    amplifies (Q/K projection gradients: up to 1.7e-3 at cfg4 against 3e-5 for the materialised path), and its softmax runs
+    on 4 warps per SM (fwd 131 us vs 60 us per call): opt-in, not default.
     Alternatives per family: "fp32" = CUDA-core kernels (exact fp32; attention = the flash-style kernel, which is also
     what shapes outside the tensor-core shape rules run on), "tf32" = single-pass TF32 (convolutions: logits 3e-4 but
     gradients ~6e-3; attention = the single-kernel flash forward/backward with S/P resident in TMEM, gradients ~3e-3
@@ -34,7 +41,7 @@ class _Config:
         self.linear = _PREC_NAMES[os.environ.get("B200ASR_LINEAR", "bf16x3")]
         self.conv = _PREC_NAMES[os.environ.get("B200ASR_CONV", "bf16x3")]
         self.conv_wgrad = _PREC_NAMES[os.environ.get("B200ASR_CONV_WGRAD", "tf32x3")]
-        self.attn = _PREC_NAMES[os.environ.get("B200ASR_ATTN", "bf16x3")]
+        self.attn = _PREC_NAMES[os.environ.get("B200ASR_ATTN", "tf32x3")]          # "bf16x3" = the fused single-kernel path (opt-in)
         self.attn_bwd = _PREC_NAMES[os.environ.get("B200ASR_ATTN_BWD", "fp32")]
 
     def set(self, linear=None, conv=None, attn=None, conv_wgrad=None, attn_bwd=None):

@@ -155,6 +155,53 @@ def test_attention_materialised_3xtf32(L, B, H, Tq, Tk, dk, dv, mode):
         assert rel_err(got, ref) < 2e-5
 
 
+@pytest.mark.parametrize("B,H,Tq,Tk,mode", [
+    (2, 2, 50, 50, "keypad"), (3, 4, 13, 13, "causal+keypad"), (2, 8, 100, 200, "keypad"), (2, 3, 70, 70, "dense"),
+    (2, 2, 100, 100, "causal"), (1, 1, 200, 200, "keypad"), (1, 2, 300, 448, "keypad"), (2, 2, 257, 400, "none"), (1, 2, 129, 65, "none"),
+])
+def test_attention_fused_bf16x3(L, B, H, Tq, Tk, mode):
+    """The fused kind::f16 attention (tc_attention16.cu: one forward kernel, two backward kernels, scores / probabilities
+    only ever in tensor memory): fp32-grade against the oracle -- 3e-5 (the 2-term bf16 split carries 16 significant bits)."""
+    import importlib
+    import b200asr
+    from tests.test_gpu_parity import _attention_case
+    ops = importlib.import_module(b200asr.__name__ + ".ops")
+    old = ops.config.attn
+    ops.config.set(attn="bf16x3")
+    try:
+        pairs = _attention_case(ops, B, H, Tq, Tk, 64, 64, mode)
+    finally:
+        ops.config.attn = old
+    for got, ref in pairs:
+        assert rel_err(got, ref) < 3e-5
+
+
+def test_attention_fused_bf16x3_dropout_matches_cuda_core_kernel(L):
+    """Same counter-based dropout stream as the other attention paths (forward and both recomputing backward kernels)."""
+    import importlib
+    import b200asr
+    ops = importlib.import_module(b200asr.__name__ + ".ops")
+    B, H, d, Tq, Tk = 2, 3, 64, 70, 132
+    g = torch.Generator().manual_seed(9)
+    base = [torch.randn(B, H, t, d, generator=g).cuda() for t in (Tq, Tk, Tk)]
+    do = torch.randn(B, H, Tq, d, generator=g).cuda()
+    key_pad = (torch.arange(Tk)[None, :] >= torch.tensor([Tk, Tk - 7])[:, None]).to(torch.uint8).cuda()
+    outs = {}
+    old = ops.config.attn
+    try:
+        for mode in ("fp32", "bf16x3"):
+            ops.config.set(attn=mode)
+            ops.rng.seed, ops.rng.offset = 77, 5
+            q, k, v = (t.clone().requires_grad_(True) for t in base)
+            o = ops.SdpaFn.apply(q, k, v, key_pad, None, False, 0.125, 0.3)
+            o.backward(do)
+            outs[mode] = (o.detach(), q.grad, k.grad, v.grad)
+    finally:
+        ops.config.attn = old
+    for a, b in zip(outs["bf16x3"], outs["fp32"]):
+        assert rel_err(a, b) < 3e-5
+
+
 @pytest.mark.parametrize("Tq,Tk,causal", [(40, 40, True), (33, 70, False), (64, 101, False)])
 def test_attention_materialised_dropout_matches_cuda_core_kernel(L, Tq, Tk, causal):
     """Both attention paths index the same counter-based dropout stream: with the same (seed, offset) the materialised
