@@ -31,6 +31,7 @@ SIGNATURES = {
     "b200asr_linear_bwd_data": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "b200asr_split_tf32": (_i, [_vp, _vp, _ll, _vp]),
     "b200asr_split_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "b200asr_split_bf16_batched": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "b200asr_linear_bwd_weight": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200asr_add_ln_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _u64, _u64, _vp]),
     "b200asr_add_ln_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _u64, _u64, _i, _vp]),

@@ -109,6 +109,57 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
   }
 }
 
+// All weight matrices of a flat parameter buffer in ONE launch: desc[d] = {src offset, N, K, terms, dst offset, dst_t offset}
+// (elements; dst / dst_t relative to `out`), tile_prefix[d] = number of 32 x 32 tiles of matrices 0 .. d-1.
+__global__ void __launch_bounds__(256) split_bf16_batched_kernel(const float* __restrict__ base, uint16_t* __restrict__ out,
+                                                                 const long long* __restrict__ desc, const int* __restrict__ tile_prefix,
+                                                                 int ndesc) {
+  __shared__ uint16_t th[32][33], tl[32][33];
+  int lo = 0, hi = ndesc - 1;                                  // last d with tile_prefix[d] <= blockIdx.x
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tile_prefix[mid] <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const long long* d = desc + 6 * lo;
+  const float* w = base + d[0];
+  const int N = (int)d[1], K = (int)d[2], terms = (int)d[3];
+  uint16_t* dst = out + d[4];
+  uint16_t* dst_t = out + d[5];
+  const int N8 = (N + 7) / 8 * 8;
+  const int local = (int)blockIdx.x - tile_prefix[lo], kt = (K + 31) / 32;
+  const int k0 = (local % kt) * 32, n0 = (local / kt) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int i = ty; i < 32; i += 8) {
+    const int n = n0 + i, k = k0 + tx;
+    uint16_t h = 0, l = 0;
+    if (n < N && k < K) {
+      const float x = w[(size_t)n * K + k];
+      const uint32_t r = __float_as_uint(x) + 0x8000u;
+      h = (uint16_t)(r >> 16);
+      const float lo_f = x - __uint_as_float(r & 0xFFFF0000u);
+      l = (uint16_t)((__float_as_uint(lo_f) + 0x8000u) >> 16);
+      dst[(size_t)n * K + k] = h;
+      if (terms == 2) dst[(size_t)N * K + (size_t)n * K + k] = l;
+    }
+    th[i][tx] = h; tl[i][tx] = l;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int k = k0 + i, n = n0 + tx;
+    if (k < K && n < N8) {
+      dst_t[(size_t)k * N8 + n] = th[tx][i];
+      if (terms == 2) dst_t[(size_t)K * N8 + (size_t)k * N8 + n] = tl[tx][i];
+    }
+  }
+}
+
+int b200asr_split_bf16_batched(const float* base, void* out, const long long* desc, const int* tile_prefix, int ndesc,
+                               int total_tiles, b200asr_stream_t stream) {
+  B200_REQUIRE(base && out && desc && tile_prefix && ndesc > 0 && total_tiles > 0, B200ASR_BAD_ARG, "split_bf16_batched: bad arguments");
+  split_bf16_batched_kernel<<<total_tiles, 256, 0, (cudaStream_t)stream>>>(base, (uint16_t*)out, desc, tile_prefix, ndesc);
+  return check_launch("split_bf16_batched");
+}
+
 int b200asr_split_bf16(const float* w, void* dst, void* dst_t, int N, int K, int terms, b200asr_stream_t stream) {
   B200_REQUIRE(w && (dst || dst_t) && N > 0 && K > 0 && (terms == 1 || terms == 2), B200ASR_BAD_ARG, "split_bf16: bad arguments");
   const int N8 = (N + 7) / 8 * 8;

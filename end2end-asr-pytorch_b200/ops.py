@@ -170,7 +170,82 @@ class WSplit:
         self.fwd, self.bwd = fwd, bwd
 
 
+class WeightOperandCache:
+    """bf16 tensor-core operands of every weight matrix that lives in a FlatParams buffer, refreshed by ONE kernel launch per
+    optimizer step (b200asr_split_bf16_batched) instead of one conversion launch per weight and step.
+
+    A matrix is registered the first time split_weight() is asked for it (that request is served by the per-weight kernel);
+    from the next refresh on its operands are views of one bf16 buffer.  Freshness: the Adam kernel writes through raw
+    pointers, so FusedAdam.step() calls refresh() itself; any other in-place change of a weight (load_state_dict, manual
+    edits) bumps that tensor's autograd version counter, which get() compares with the one it last saw."""
+
+    def __init__(self, flat):
+        self.flat = flat                      # optim.FlatParams
+        self.entries, self.pending = {}, []   # key -> (src_off, N, K, terms, dst_off, dstT_off)
+        self.buf = self.desc = self.prefix = None
+        self.tiles = 0
+        self.gen = 0                          # number of refreshes so far
+        self.seen = {}                        # key -> [tensor version last seen, refresh generation at that time]
+
+    def owns(self, w2):
+        f = self.flat.flat
+        return w2.is_contiguous() and f.data_ptr() <= w2.data_ptr() and w2.data_ptr() + w2.numel() * 4 <= f.data_ptr() + f.numel() * 4
+
+    def refresh(self):
+        if self.pending:
+            off = 0 if self.buf is None else self.buf.numel()
+            for key in self.pending:
+                ptr, N, K, terms = key
+                n8 = (N + 7) // 8 * 8
+                self.entries[key] = ((ptr - self.flat.flat.data_ptr()) // 4, N, K, terms, off, off + terms * N * K)
+                off += (terms * N * K + terms * K * n8 + 63) // 64 * 64
+            self.pending = []
+            dev = self.flat.flat.device
+            self.buf = torch.empty(off, device=dev, dtype=torch.bfloat16)
+            rows, prefix, tiles = [], [], 0
+            for (so, N, K, terms, do, dto) in self.entries.values():
+                rows.append([so, N, K, terms, do, dto])
+                prefix.append(tiles)
+                tiles += ((K + 31) // 32) * (((N + 7) // 8 * 8 + 31) // 32)
+            self.desc = torch.tensor(rows, dtype=torch.int64, device=dev)
+            self.prefix = torch.tensor(prefix, dtype=torch.int32, device=dev)
+            self.tiles = tiles
+        if self.entries:
+            L.check(_lib().b200asr_split_bf16_batched(L.ptr(self.flat.flat), L.ptr(self.buf), L.ptr(self.desc), L.ptr(self.prefix),
+                                                      len(self.entries), self.tiles, _stream()), "split_bf16_batched")
+        self.gen += 1
+
+    def after_optimizer_step(self):
+        if self.entries or self.pending:
+            self.refresh()
+
+    def get(self, w2, prec):
+        N, K = w2.shape
+        terms = 2 if prec == L.PREC_BF16X3 else 1
+        key = (w2.data_ptr(), N, K, terms)
+        e = self.entries.get(key)
+        if e is None:
+            if key not in self.pending:
+                self.pending.append(key)
+            return None
+        seen = self.seen.get(key)
+        if seen is None or seen[0] != w2._version:
+            if seen is None or seen[1] == self.gen:      # changed in place since the last conversion (not by our optimizer)
+                self.refresh()
+            self.seen[key] = [w2._version, self.gen]
+        _, _, _, _, do, dto = e
+        n8 = (N + 7) // 8 * 8
+        return WSplit(self.buf[do:do + terms * N * K].view(terms, N, K), self.buf[dto:dto + terms * K * n8].view(terms, K, n8))
+
+
+weight_cache = None       # set by optim.FlatParams
+
+
 def split_weight(w2, prec, need_bwd=True):
+    if prec in _BF16_PRECS and weight_cache is not None and weight_cache.owns(w2):
+        ws = weight_cache.get(w2, prec)
+        if ws is not None:
+            return ws
     if prec == L.PREC_TF32X3:
         ws = torch.empty((2,) + tuple(w2.shape), device=w2.device, dtype=torch.float32)
         L.check(_lib().b200asr_split_tf32(L.ptr(w2), L.ptr(ws), w2.numel(), _stream()), "split_tf32")

@@ -68,6 +68,8 @@ class FlatParams:
                 p.data = self.flat[o:o + n].view(p.shape)
                 p.grad = self.flat_grad[o:o + n].view(p.shape)
                 p._b200_flat_grad = True      # opt-in for ops._grad_sink: backward kernels may accumulate straight into .grad
+        if dev.type == "cuda":
+            ops.weight_cache = ops.WeightOperandCache(self)     # bf16 operands of all weights: one conversion launch per step
 
     @property
     def extras(self) -> torch.Tensor:
@@ -109,6 +111,8 @@ class FusedAdam:
                                            float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
                                            self.t, float(grad_scale), L.ptr(grad_scale_dev),
                                            torch.cuda.current_stream().cuda_stream), "adam_step")
+        if ops.weight_cache is not None and ops.weight_cache.flat is f:
+            ops.weight_cache.after_optimizer_step()
 
     def grad_sumsq(self) -> torch.Tensor:
         out = torch.zeros(1, device=self.flat.flat.device, dtype=torch.float32)

@@ -77,6 +77,12 @@ int b200asr_split_tf32(const float* src, float* dst_hi_lo, long long n, b200asr_
  * dst [terms][N][K] (K-major for y = x w^T) and/or dst_t [terms][K][N8] (K-major for dx = dy w; zero padded columns);
  * either may be NULL. */
 int b200asr_split_bf16(const float* w, void* dst, void* dst_t, int N, int K, int terms, b200asr_stream_t stream);
+/* The same conversion for MANY matrices of one flat parameter buffer in a single launch (once per optimizer step):
+ * desc [ndesc][6] int64 on the device = {src offset, N, K, terms, dst offset, dst_t offset} in elements (src relative to
+ * `base`, dst / dst_t relative to `out`, both orientations are written); tile_prefix [ndesc] int32 = number of 32x32 tiles
+ * (ceil(K/32) * ceil(N8/32) each) of the matrices before d; total_tiles = their sum. */
+int b200asr_split_bf16_batched(const float* base, void* out, const long long* desc, const int* tile_prefix, int ndesc,
+                               int total_tiles, b200asr_stream_t stream);
 /* dw[N,K] (+)= dy[M,N]^T * x[M,K];  dbias[N] (+)= column sums of dy (dbias may be NULL) */
 int b200asr_linear_bwd_weight(const float* dy, const float* x, float* dw, float* dbias, int M, int N, int K,
                               int accumulate, int precision, b200asr_stream_t stream);
