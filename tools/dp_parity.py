@@ -28,30 +28,31 @@ for i in range(B):
     tgt[i, 5 + (7 * i) % 15:] = 0                      # ranks see different token counts
 
 
-def make():
-    torch.manual_seed(123456)
+def make(group=None, seed=123456):
+    torch.manual_seed(seed)
     m = b200asr.build_model(cfg).to(dev)
     m.train()
-    return b200asr.DataParallelStep(m, model_size=cfg.dim_input, warmup=10, k_lr=1.0, min_lr=1e-6, smoothing=0.1)
+    return b200asr.DataParallelStep(m, model_size=cfg.dim_input, warmup=10, k_lr=1.0, min_lr=1e-6, smoothing=0.1, process_group=group)
 
 
-dp = make()
+solo = dist.new_group([0])                               # rank 0 alone: the single-rank reference step (collective call: all ranks)
+dp = make(seed=123456 + rank)                            # ranks build different replicas; the constructor broadcasts rank 0's
 s, l, t = b200asr.shard_batch(src, lens, tgt, rank, world)
 dp.step(s.to(dev), l, t.to(dev))
 loss_dp = float(dp.global_loss())
-g_dp = (dp.flat.flat_grad[:dp.flat.numel] * dp._inv_tokens).clone()
+g_dp = (dp.flat.flat_grad[:dp.flat.numel] * dp._scale[0]).clone()
 p_dp = dp.flat.flat.clone()
 if rank == 0:
-    ref = make()
-    ref.world = 1                                       # single-rank step on the whole batch: no collective
+    ref = make(group=solo)                              # single-rank step on the whole batch: no collective
+    assert ref.world == 1
     ref.step(src.to(dev), lens, tgt.to(dev))
-    g_ref = ref.flat.flat_grad[:ref.flat.numel] * ref._inv_tokens
+    g_ref = ref.flat.flat_grad[:ref.flat.numel] * ref._scale[0]
     print("world %d: loss dp %.6f vs single %.6f | grad rel err %.2e | params-after-step rel err %.2e | n_tokens %d" % (
         world, loss_dp, float(ref.global_loss()), rel_err(g_dp, g_ref), rel_err(p_dp, ref.flat.flat), int(dp.flat.extras[1])))
     assert abs(loss_dp - float(ref.global_loss())) < 1e-4 * abs(loss_dp)
     # parameters: the first Adam step is lr * g / (|g| + 1e-9), i.e. sign-like; entries whose gradient is rounding noise
     # (mathematically zero, e.g. key biases) may step in either direction, so the bound is a few learning rates, not 1e-4
     assert rel_err(g_dp, g_ref) < 1e-3 and rel_err(p_dp, ref.flat.flat) < 1e-2
-    print("DP PARITY OK")
+    print("DP PARITY OK (gradient all-reduce overlapped with the front-end backward: %s)" % (dp.overlap and dp.flat.tail_offset < dp.flat.numel))
 dist.barrier()
 dist.destroy_process_group()
