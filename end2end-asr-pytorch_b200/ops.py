@@ -291,6 +291,30 @@ def _grad_sink(param):
     return g
 
 
+class _WgradStream:
+    """Weight-gradient GEMMs of the dense layers are off the critical path of the backward pass (nothing downstream reads
+    them before the optimizer).  When `enabled` (parallel.DataParallelStep turns it on around loss.backward()) the ones that
+    accumulate straight into the flat gradient buffer are queued on a second stream: their CTAs fill the SMs that the
+    data-gradient GEMMs of the main stream leave idle in their last, partial wave (100 / 200 / 300-tile problems on 148 SMs)
+    and run under the small LayerNorm / softmax kernels.  sync() makes the current stream wait for all of them."""
+
+    def __init__(self):
+        self.enabled, self.stream, self.used = False, None, False
+
+    def get(self, device):
+        if self.stream is None or self.stream.device != device:
+            self.stream = torch.cuda.Stream(device=device)
+        return self.stream
+
+    def sync(self):
+        if self.used and self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        self.used = False
+
+
+wgrad_stream = _WgradStream()
+
+
 def linear_bwd_weight(dy2, x2, want_bias, prec, w_sink=None, b_sink=None):
     """dW = dy^T x (+ column sums).  With sinks the kernels ACCUMULATE into the given .grad tensors and (None, None) is
     returned for them, so autograd has nothing left to add."""
@@ -298,6 +322,15 @@ def linear_bwd_weight(dy2, x2, want_bias, prec, w_sink=None, b_sink=None):
     K = x2.shape[1]
     direct = w_sink is not None and (not want_bias or b_sink is not None)
     if direct:
+        if wgrad_stream.enabled:
+            side, cur = wgrad_stream.get(dy2.device), torch.cuda.current_stream()
+            side.wait_stream(cur)                        # dy2 / x2 were produced on the main stream
+            dy2.record_stream(side); x2.record_stream(side)      # the caching allocator must not recycle them under the kernel
+            with torch.cuda.stream(side):
+                L.check(_lib().b200asr_linear_bwd_weight(L.ptr(dy2), L.ptr(x2), L.ptr(w_sink), L.ptr(b_sink) if want_bias else None,
+                                                         M, N, K, 1, prec, _stream()), "linear_bwd_weight")
+            wgrad_stream.used = True
+            return None, None
         L.check(_lib().b200asr_linear_bwd_weight(L.ptr(dy2), L.ptr(x2), L.ptr(w_sink), L.ptr(b_sink) if want_bias else None, M, N, K,
                                                  1, prec, _stream()), "linear_bwd_weight")
         return None, None
