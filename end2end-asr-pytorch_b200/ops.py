@@ -296,7 +296,10 @@ class _WgradStream:
     them before the optimizer).  When `enabled` (parallel.DataParallelStep turns it on around loss.backward()) the ones that
     accumulate straight into the flat gradient buffer are queued on a second stream: their CTAs fill the SMs that the
     data-gradient GEMMs of the main stream leave idle in their last, partial wave (100 / 200 / 300-tile problems on 148 SMs)
-    and run under the small LayerNorm / softmax kernels.  sync() makes the current stream wait for all of them."""
+    and run under the small LayerNorm / softmax kernels.  sync() makes the current stream wait for all of them.
+    MEASURED AND REJECTED as a default (cfg2: 18.0 -> 20.1 ms/step): the engine kernels are persistent (one CTA per SM for
+    the whole tile list, ~200 KB of shared memory each), so a weight-gradient kernel that got the SMs first holds them until
+    its last tile and the critical-path data-gradient kernel queues behind it.  Kept behind B200ASR_ASYNC_WGRAD=1."""
 
     def __init__(self):
         self.enabled, self.stream, self.used = False, None, False

@@ -8,6 +8,8 @@ gathered global batch (trainer.py:84 + metrics.py:127-130).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -42,8 +44,10 @@ class DataParallelStep:
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.clip = clip_max_norm
-        self.overlap = True          # all-reduce the transformer's gradients under the CNN front end's backward
-        self.async_wgrad = True      # dense-layer weight gradients on a second stream (ops._WgradStream)
+        # all-reduce the transformer's gradients under the CNN front end's backward / dense-layer weight gradients on a second
+        # stream (ops._WgradStream); the environment switches exist for A/B measurements
+        self.overlap = os.environ.get("B200ASR_DP_OVERLAP", "1") != "0"
+        self.async_wgrad = os.environ.get("B200ASR_ASYNC_WGRAD", "0") != "0"    # measured and rejected, see ops._WgradStream
         self._early = None
         self._scale = torch.zeros(4, device=self.flat.flat.device, dtype=torch.float32)    # [scale, grad norm, scratch, -]
         self._host_tail = loss_fn is not None or adam_factory is not None                  # CPU stand-ins (gloo tests)
