@@ -129,22 +129,34 @@ __device__ __forceinline__ float block_sum256(float v, float* red) {
 // normalisation, as ATen), and -- when the running buffers are given -- the nn.BatchNorm2d state update
 //   running_mean <- (1-m) running_mean + m mean,   running_var <- (1-m) running_var + m var * n/(n-1),   num_batches_tracked += 1.
 // training == 0 (model.eval(), the reference's validation loop trainer.py:123): normalise with the running statistics.
+// Tensors are [B, C, H, W] with a ROW PITCH per tensor (>= W; the implicit-GEMM convolutions need pitches that are
+// multiples of 4 floats); a warp walks one row, the block's warps stride over the B*H rows of channel c.
+struct BnIdx {
+  int B, C, H, W;
+  __device__ __forceinline__ size_t at(int row, int w, int c, int pitch) const {      // row = b * H + h
+    return (((size_t)(row / H) * C + c) * H + (row % H)) * pitch + w;
+  }
+};
+
 __global__ void __launch_bounds__(256) bn_clamp_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float* __restrict__ y,
                                                            float* __restrict__ mean_out, float* __restrict__ invstd_out,
                                                            float* __restrict__ running_mean, float* __restrict__ running_var,
-                                                           long long* __restrict__ num_batches, int B, int C, int HW, float eps,
+                                                           long long* __restrict__ num_batches, BnIdx g, int xp, int yp, float eps,
                                                            float momentum, int training, float lo, float hi) {
   __shared__ float red[8];
-  const int c = blockIdx.x;
-  const long long n = (long long)B * HW;
+  const int c = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows = g.B * g.H;
+  const long long n = (long long)rows * g.W;
   float mean, invstd;
   if (training) {
     float s = 0.f;
-    for (long long j = threadIdx.x; j < n; j += 256) s += x[((size_t)(j / HW) * C + c) * HW + (j % HW)];
+    for (int r = warp; r < rows; r += 8)
+      for (int w = lane; w < g.W; w += 32) s += x[g.at(r, w, c, xp)];
     mean = block_sum256(s, red) / (float)n;
     float q = 0.f;
-    for (long long j = threadIdx.x; j < n; j += 256) { float d = x[((size_t)(j / HW) * C + c) * HW + (j % HW)] - mean; q += d * d; }
+    for (int r = warp; r < rows; r += 8)
+      for (int w = lane; w < g.W; w += 32) { const float d = x[g.at(r, w, c, xp)] - mean; q += d * d; }
     const float var = block_sum256(q, red) / (float)n;
     invstd = rsqrtf(var + eps);
     if (threadIdx.x == 0 && running_mean && running_var) {
@@ -159,41 +171,42 @@ __global__ void __launch_bounds__(256) bn_clamp_fwd_kernel(const float* __restri
   }
   if (threadIdx.x == 0) { mean_out[c] = mean; invstd_out[c] = invstd; }
   const float ga = gamma[c], be = beta[c];
-  for (long long j = threadIdx.x; j < n; j += 256) {
-    size_t o = ((size_t)(j / HW) * C + c) * HW + (j % HW);
-    float v = (x[o] - mean) * invstd * ga + be;
-    y[o] = fminf(fmaxf(v, lo), hi);
-  }
+  for (int r = warp; r < rows; r += 8)
+    for (int w = lane; w < g.W; w += 32) {
+      const float v = (x[g.at(r, w, c, xp)] - mean) * invstd * ga + be;
+      y[g.at(r, w, c, yp)] = fminf(fmaxf(v, lo), hi);
+    }
 }
 
 __global__ void __launch_bounds__(256) bn_clamp_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                            const float* __restrict__ y, const float* __restrict__ gamma,
                                                            const float* __restrict__ mean_in, const float* __restrict__ invstd_in,
                                                            float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                           int B, int C, int HW, int training, float lo, float hi) {
+                                                           BnIdx g, int dyp, int xp, int yp, int dxp, int training, float lo, float hi) {
   __shared__ float red[8];
-  const int c = blockIdx.x;
-  const long long n = (long long)B * HW;
+  const int c = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows = g.B * g.H;
+  const long long n = (long long)rows * g.W;
   const float mean = mean_in[c], invstd = invstd_in[c], ga = gamma[c];
   float s1 = 0.f, s2 = 0.f;
-  for (long long j = threadIdx.x; j < n; j += 256) {
-    size_t o = ((size_t)(j / HW) * C + c) * HW + (j % HW);
-    float yv = y[o];
-    float g = (yv > lo && yv < hi) ? dy[o] : 0.f;
-    float xh = (x[o] - mean) * invstd;
-    s1 += g; s2 += g * xh;
-  }
+  for (int r = warp; r < rows; r += 8)
+    for (int w = lane; w < g.W; w += 32) {
+      const float yv = y[g.at(r, w, c, yp)];
+      const float gg = (yv > lo && yv < hi) ? dy[g.at(r, w, c, dyp)] : 0.f;
+      const float xh = (x[g.at(r, w, c, xp)] - mean) * invstd;
+      s1 += gg; s2 += gg * xh;
+    }
   s1 = block_sum256(s1, red);
   s2 = block_sum256(s2, red);
   if (threadIdx.x == 0) { dbeta[c] = s1; dgamma[c] = s2; }
   const float inv_n = training ? 1.f / (float)n : 0.f;      // eval mode: the statistics are constants of the graph
-  for (long long j = threadIdx.x; j < n; j += 256) {
-    size_t o = ((size_t)(j / HW) * C + c) * HW + (j % HW);
-    float yv = y[o];
-    float g = (yv > lo && yv < hi) ? dy[o] : 0.f;
-    float xh = (x[o] - mean) * invstd;
-    dx[o] = ga * invstd * (g - s1 * inv_n - xh * s2 * inv_n);
-  }
+  for (int r = warp; r < rows; r += 8)
+    for (int w = lane; w < g.W; w += 32) {
+      const float yv = y[g.at(r, w, c, yp)];
+      const float gg = (yv > lo && yv < hi) ? dy[g.at(r, w, c, dyp)] : 0.f;
+      const float xh = (x[g.at(r, w, c, xp)] - mean) * invstd;
+      dx[g.at(r, w, c, dxp)] = ga * invstd * (gg - s1 * inv_n - xh * s2 * inv_n);
+    }
 }
 
 // y[b][t][c*F+f] = x[b][c][f][t]  (32x32 smem transpose over (cf, t))
@@ -361,20 +374,25 @@ int b200asr_transpose_cp(const float* src, float* dst, int B, int C, int P, int 
 }
 
 int b200asr_bn_clamp_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* invstd,
-                         float* running_mean, float* running_var, long long* num_batches_tracked, int B, int C, int HW, float eps,
-                         float momentum, int training, float lo, float hi, b200asr_stream_t stream) {
-  B200_REQUIRE(x && gamma && beta && y && mean && invstd && B > 0 && C > 0 && HW > 0, B200ASR_BAD_ARG, "bn_clamp_fwd: bad arguments");
+                         float* running_mean, float* running_var, long long* num_batches_tracked, int B, int C, int H, int W,
+                         int x_pitch, int y_pitch, float eps, float momentum, int training, float lo, float hi,
+                         b200asr_stream_t stream) {
+  B200_REQUIRE(x && gamma && beta && y && mean && invstd && B > 0 && C > 0 && H > 0 && W > 0 && x_pitch >= W && y_pitch >= W,
+               B200ASR_BAD_ARG, "bn_clamp_fwd: bad arguments");
   B200_REQUIRE(training || (running_mean && running_var), B200ASR_BAD_ARG, "bn_clamp_fwd: eval mode needs the running statistics");
   bn_clamp_fwd_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, y, mean, invstd, running_mean, running_var,
-                                                           num_batches_tracked, B, C, HW, eps, momentum, training, lo, hi);
+                                                           num_batches_tracked, BnIdx{B, C, H, W}, x_pitch, y_pitch, eps, momentum,
+                                                           training, lo, hi);
   return check_launch("bn_clamp_fwd");
 }
 
 int b200asr_bn_clamp_bwd(const float* dy, const float* x, const float* y, const float* gamma, const float* mean,
-                         const float* invstd, float* dx, float* dgamma, float* dbeta, int B, int C, int HW, int training, float lo,
-                         float hi, b200asr_stream_t stream) {
+                         const float* invstd, float* dx, float* dgamma, float* dbeta, int B, int C, int H, int W, int dy_pitch,
+                         int x_pitch, int y_pitch, int dx_pitch, int training, float lo, float hi, b200asr_stream_t stream) {
   B200_REQUIRE(dy && x && y && gamma && mean && invstd && dx && dgamma && dbeta, B200ASR_BAD_ARG, "bn_clamp_bwd: null pointer");
-  bn_clamp_bwd_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(dy, x, y, gamma, mean, invstd, dx, dgamma, dbeta, B, C, HW, training, lo, hi);
+  B200_REQUIRE(dy_pitch >= W && x_pitch >= W && y_pitch >= W && dx_pitch >= W, B200ASR_BAD_ARG, "bn_clamp_bwd: row pitches must cover W");
+  bn_clamp_bwd_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(dy, x, y, gamma, mean, invstd, dx, dgamma, dbeta, BnIdx{B, C, H, W}, dy_pitch,
+                                                           x_pitch, y_pitch, dx_pitch, training, lo, hi);
   return check_launch("bn_clamp_bwd");
 }
 

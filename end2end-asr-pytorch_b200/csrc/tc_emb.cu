@@ -1,0 +1,327 @@
+// emb_cnn front end, second convolution (models/asr/transformer.py:37: Conv2d(32, 32, kernel (21, 11), stride (2, 1)) on the
+// NCHW activation) as IMPLICIT GEMMs on the persistent tcgen05 engine -- no im2col matrix, no col2im scatter.
+//
+// Geometry: x [B, 32, H, W], w [32, 32, KH, KW], y [B, 32, OH, OW] with OH = (H - KH) / SH + 1, OW = W - KW + 1 (stride 1
+// along W, no padding).  Because the stride along W is 1, the GEMM row index can be the output column:
+//
+//   forward        y[b, :, oh, ow0 + m]  = sum_{kh, kw} sum_ci  x[b, ci, SH*oh + kh, ow0 + m + kw] * w[:, ci, kh, kw]
+//     one k-block = one (kh, kw): the A tile (128 m x 32 ci, MN-major) is ONE strided window of the activation -- 4 TMA
+//     boxes {32 w, 1 h, 32 c} at (ow0 + kw, SH*oh + kh) -- and the B tile the 32 x 32 weight slice of that tap (K-major,
+//     pre-converted: bf16 hi | lo for the kind::f16 modes, tf32 hi | lo for 3xTF32).
+//   data gradient  dx[b, :, h, w0 + m]   = sum_{kh == h (mod SH), kw} sum_co  dy[b, co, (h - kh) / SH, w0 + m - kw] * w[co, :, kh, kw]
+//     the same kernel: a gather over the taps whose row parity matches h; boxes that reach outside dy are zero-filled by TMA.
+//   weight gradient dw[:, ci, kh, kw]    = sum_{b, oh, ow} dy[b, :, oh, ow] * x[b, ci, SH*oh + kh, ow + kw]
+//     GEMM rows = (kw, ci) -- four taps x 32 channels per 128-row tile --, columns = co, contraction = output pixels along ow:
+//     both operands K-major fp32 windows (3xTF32, B split in the kernel), partial sums added to dw with fp32 atomics.
+//
+// MMA N = 32 (the layer has 32 output channels); the engine's conversion warps turn the fp32 A tile into the tensor-memory
+// operand exactly as for the other policies.  TMA needs 16-byte row pitches, so the NCHW tensors these kernels touch are
+// PITCHED: rows of `pitch` floats (a multiple of 4) of which the first W are valid (W = 205 / 195 at cfg3).
+#include "../../include/b200asr.h"
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_common.cuh"
+#include "tc_engine.cuh"
+
+namespace b200asr {
+namespace tc {
+
+constexpr int EC = 32;                     // channels in and out
+
+struct EmbG {
+  int B, H, W, OH, OW, KH, KW, SH;
+  int xp, yp;            // row pitch (floats) of the [B,32,H,W] tensor (x / dx) and of the [B,32,OH,OW] tensor (y / dy)
+};
+
+struct EmbConvP {
+  float* out;            // forward: y [B, 32, OH, OW]; data gradient: dx [B, 32, H, W]
+  const float* bias;     // forward only (may be null)
+  EmbG g;
+  int rows, width, pitch, tiles_w;      // output rows per image (OH / H), output width (OW / W) and row pitch, 128-wide tiles per row
+  int b_rows;                    // rows of one half (hi or lo) of the repacked weight matrix = KH * KW * 32
+};
+
+// forward (DGRAD = false) and data gradient (DGRAD = true)
+template <bool DGRAD>
+struct EmbConvPolicy {
+  static constexpr int BN = EC, kABytes = 4 * 4096, kBBytes = EC * 128;
+  static constexpr bool kSplitA = true, kSplitB = false, kAMN = true, kBMN = false, kSumA = false, kSumB = false;
+  struct Params { EmbConvP e; };
+  static __device__ __forceinline__ int num_tiles(const Params& p) { return p.e.g.B * p.e.rows * p.e.tiles_w; }
+  struct Tile { int w0, r, b, kh, kw, nkh, kh0; };
+  // taps along H that reach output row r: forward all KH; data gradient kh == h (mod SH) with 0 <= (h - kh) / SH < OH
+  static __device__ __forceinline__ void kh_range(const EmbG& g, int r, int& kh0, int& nkh) {
+    if (!DGRAD) { kh0 = 0; nkh = g.KH; return; }
+    int lo = max(0, r - g.SH * (g.OH - 1));
+    lo += ((r - lo) % g.SH + g.SH) % g.SH;                 // first kh >= lo with (r - kh) % SH == 0
+    const int hi = min(g.KH - 1, r);
+    kh0 = lo;
+    nkh = hi >= lo ? (hi - lo) / g.SH + 1 : 0;
+  }
+  static __device__ __forceinline__ Tile tile(const Params& p, int tile) {
+    Tile t;
+    t.w0 = (tile % p.e.tiles_w) * 128;
+    const int q = tile / p.e.tiles_w;
+    t.r = q % p.e.rows; t.b = q / p.e.rows;
+    kh_range(p.e.g, t.r, t.kh0, t.nkh);
+    t.kh = t.kh0; t.kw = 0;
+    return t;
+  }
+  static __device__ __forceinline__ int num_kb(const Params& p, int tile) {
+    int kh0, nkh;
+    kh_range(p.e.g, (tile / p.e.tiles_w) % p.e.rows, kh0, nkh);
+    return nkh * p.e.g.KW;
+  }
+  static __device__ __forceinline__ void load_a(const Params& p, const Tile& t, const CUtensorMap* mapA, uint32_t sa, uint32_t bar) {
+    const int w = DGRAD ? t.w0 - t.kw : t.w0 + t.kw;
+    const int h = DGRAD ? (t.r - t.kh) / p.e.g.SH : t.r * p.e.g.SH + t.kh;
+#pragma unroll
+    for (int c = 0; c < 4; c++) tma_load_4d(sa + c * 4096, mapA, bar, w + 32 * c, h, 0, t.b);
+  }
+  static __device__ __forceinline__ void advance(const Params& p, Tile& t) {
+    if (++t.kw == p.e.g.KW) { t.kw = 0; t.kh += DGRAD ? p.e.g.SH : 1; }
+  }
+  // 3xTF32: fp32 hi | lo weight slices (128-byte rows)
+  static __device__ __forceinline__ void load(const Params& p, Tile& t, const CUtensorMap* mapA, const CUtensorMap* mapB,
+                                              uint32_t sa, uint32_t sb, uint32_t sb_lo, uint32_t bar, bool leader) {
+    if (leader) {
+      load_a(p, t, mapA, sa, bar);
+      const int row = (t.kh * p.e.g.KW + t.kw) * EC;
+      tma_load_2d(sb, mapB, bar, 0, row);
+      tma_load_2d(sb_lo, mapB, bar, 0, row + p.e.b_rows);
+    }
+    advance(p, t);
+  }
+  // kind::f16 modes: bf16 hi (| lo) weight slices (64-byte rows)
+  static __device__ __forceinline__ void load16(const Params& p, Tile& t, const CUtensorMap* mapA, const CUtensorMap* mapB,
+                                                uint32_t sa, uint32_t sb, uint32_t sb_lo, uint32_t bar, bool leader, int halves) {
+    if (leader) {
+      load_a(p, t, mapA, sa, bar);
+      const int row = (t.kh * p.e.g.KW + t.kw) * EC;
+      tma_load_2d(sb, mapB, bar, 0, row);
+      if (halves == 2) tma_load_2d(sb_lo, mapB, bar, 0, row + p.e.b_rows);
+    }
+    advance(p, t);
+  }
+  static __device__ __forceinline__ uint64_t a_desc(uint32_t s, int ks) { return make_smem_desc(s + ks * 1024, 4096, 512, kLayoutSW128Base32B); }
+  static __device__ __forceinline__ uint64_t b_desc(uint32_t s, int ks) { return make_smem_desc(s + ks * 32, 16, 1024); }
+  static __device__ __forceinline__ uint64_t b_desc16(uint32_t s, int ks) { return make_smem_desc(s + ks * 32, 16, 512, kLayoutSW64); }
+  static __device__ __forceinline__ void store(const Params& p, const Tile& t, int r, int c0, const float (&v)[32]) {
+    const int w = t.w0 + r;
+    if (w >= p.e.width) return;
+    // NCHW output: consecutive lanes = consecutive w -> every channel's store is one coalesced 128-byte row segment
+    float* o = p.e.out + (((size_t)t.b * EC + c0) * p.e.rows + t.r) * p.e.pitch + w;
+    const size_t cs = (size_t)p.e.rows * p.e.pitch;
+#pragma unroll
+    for (int j = 0; j < 32; j++) o[j * cs] = v[j] + (p.e.bias ? __ldg(p.e.bias + c0 + j) : 0.f);
+  }
+};
+
+struct EmbWgP {
+  float* dw;             // [32 co, 32 ci, KH, KW], zeroed by the caller
+  EmbG g;
+  int m_tiles, splits, rows_per_split, owb;      // ceil(KW / 4); splits of the B*OH output rows; 32-wide ow blocks per row
+};
+
+struct EmbWgradPolicy {
+  static constexpr int BN = EC, kABytes = 4 * 4096, kBBytes = EC * 128;
+  static constexpr bool kSplitA = true, kSplitB = true, kAMN = false, kBMN = false, kSumA = false, kSumB = false;
+  struct Params { EmbWgP e; };
+  static __device__ __forceinline__ int num_tiles(const Params& p) { return p.e.g.KH * p.e.m_tiles * p.e.splits; }
+  struct Tile { int kh, mt, row, row_end, ob; };          // tap row, kw group, (b, oh) row cursor, ow-block cursor
+  static __device__ __forceinline__ Tile tile(const Params& p, int tile) {
+    Tile t;
+    t.kh = tile % p.e.g.KH;
+    const int q = tile / p.e.g.KH;
+    t.mt = q % p.e.m_tiles;
+    const int z = q / p.e.m_tiles;
+    t.row = z * p.e.rows_per_split;
+    t.row_end = min(p.e.g.B * p.e.g.OH, t.row + p.e.rows_per_split);
+    t.ob = 0;
+    return t;
+  }
+  static __device__ __forceinline__ int num_kb(const Params& p, int tile) {
+    const int z = tile / (p.e.g.KH * p.e.m_tiles);
+    const int r0 = z * p.e.rows_per_split, r1 = min(p.e.g.B * p.e.g.OH, r0 + p.e.rows_per_split);
+    return max(0, r1 - r0) * p.e.owb;
+  }
+  static __device__ __forceinline__ void load(const Params& p, Tile& t, const CUtensorMap* mapX, const CUtensorMap* mapDy,
+                                              uint32_t sa, uint32_t sb, uint32_t, uint32_t bar, bool leader) {
+    if (leader) {
+      const int b = t.row / p.e.g.OH, oh = t.row % p.e.g.OH, ow0 = t.ob * 32;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int kw = t.mt * 4 + j;
+        // taps beyond KW: a box at channel coordinate 32 is entirely out of bounds -> zero rows, same byte count
+        tma_load_4d(sa + j * 4096, mapX, bar, ow0 + kw, p.e.g.SH * oh + t.kh, kw < p.e.g.KW ? 0 : EC, b);
+      }
+      tma_load_4d(sb, mapDy, bar, ow0, oh, 0, b);
+    }
+    if (++t.ob == p.e.owb) { t.ob = 0; t.row++; }
+  }
+  static __device__ __forceinline__ uint64_t a_desc(uint32_t s, int ks) { return make_smem_desc(s + ks * 32, 16, 1024); }
+  static __device__ __forceinline__ uint64_t b_desc(uint32_t s, int ks) { return make_smem_desc(s + ks * 32, 16, 1024); }
+  static __device__ __forceinline__ void store(const Params& p, const Tile& t, int r, int c0, const float (&v)[32]) {
+    const int kw = t.mt * 4 + r / EC, ci = r % EC;
+    if (kw >= p.e.g.KW) return;
+    float* o = p.e.dw + ((size_t)ci * p.e.g.KH + t.kh) * p.e.g.KW + kw;        // + co * (32 * KH * KW)
+    const size_t cs = (size_t)EC * p.e.g.KH * p.e.g.KW;
+#pragma unroll
+    for (int j = 0; j < 32; j++) atomicAdd(o + (size_t)(c0 + j) * cs, v[j]);
+  }
+};
+
+// w [32 co, 32 ci, KH, KW] -> tap-major 32 x 32 slices: forward [(kh, kw)][co][ci], data gradient [(kh, kw)][ci][co];
+// mode 3: fp32 (rn_tf32(w) | w - hi); modes 6 / 2: bf16 (hi | lo) / hi
+__global__ void emb_repack_kernel(const float* __restrict__ w, void* __restrict__ out, int KH, int KW, int dgrad, int mode) {
+  const int taps = KH * KW, total = taps * EC * EC;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int inner = i % EC, outer = (i / EC) % EC, tap = i / (EC * EC);
+  const int co = dgrad ? inner : outer, ci = dgrad ? outer : inner;
+  const float v = w[((size_t)co * EC + ci) * taps + tap];
+  if (mode == 3) {
+    float* o = (float*)out;
+    const float hi = tf32_rn(v);
+    o[i] = hi;
+    o[total + i] = v - hi;
+  } else {
+    uint16_t* o = (uint16_t*)out;
+    const uint32_t r = __float_as_uint(v) + 0x8000u;
+    o[i] = (uint16_t)(r >> 16);
+    if (mode == 6) {
+      const float lo = v - __uint_as_float(r & 0xFFFF0000u);
+      o[total + i] = (uint16_t)((__float_as_uint(lo) + 0x8000u) >> 16);
+    }
+  }
+}
+
+__global__ void emb_bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ db, int B, int H, int W, int P) {
+  __shared__ float red[8];
+  const int c = blockIdx.x;
+  float s = 0.f;
+  for (long long j = threadIdx.x; j < (long long)B * H * W; j += 256) {
+    const int w = (int)(j % W);
+    const long long r = j / W;
+    s += dy[(((size_t)(r / H) * EC + c) * H + (r % H)) * P + w];
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; w++) t += red[w];
+    db[c] = t;
+  }
+}
+
+static int nchw_map(CUtensorMap* m, const float* base, int W, int P, int H, int B, bool atom32) {
+  uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)EC, (uint64_t)B};
+  uint64_t strides[3] = {(uint64_t)P, (uint64_t)H * P, (uint64_t)EC * H * P};
+  uint32_t box[4] = {32, 1, EC, 1};
+  return make_tensor_map_f32(m, base, 4, dims, strides, box, atom32, false);
+}
+
+template <bool DGRAD>
+static int launch_emb_conv(const CUtensorMap& ma, const CUtensorMap& mb, const EmbConvP& e, int mode, cudaStream_t st) {
+  using Pol = EmbConvPolicy<DGRAD>;
+  typename Pol::Params p{e};
+  const long long tiles = (long long)e.g.B * e.rows * e.tiles_w;
+  if (tiles >= (1LL << 31)) { set_error("conv2d_tc: too many tiles"); return B200ASR_BAD_SHAPE; }
+  if (mode == 3) return launch_engine<Pol, 3>(ma, mb, p, (int)tiles, st, "conv2d_tc");
+  if (mode == 6) return launch_engine<Pol, 6>(ma, mb, p, (int)tiles, st, "conv2d_tc");
+  return launch_engine<Pol, 2>(ma, mb, p, (int)tiles, st, "conv2d_tc");
+}
+
+static int emb_geom(EmbG& g, const char* who, int B, int Ci, int H, int W, int Co, int KH, int KW, int SH, int xp, int yp) {
+  B200_REQUIRE(Ci == EC && Co == EC, B200ASR_BAD_SHAPE, "%s: the implicit-GEMM kernels take 32 input and 32 output channels (Ci=%d Co=%d)", who, Ci, Co);
+  B200_REQUIRE(B > 0 && KH > 0 && KW > 0 && SH > 0 && H >= KH && W >= KW, B200ASR_BAD_SHAPE, "%s: bad geometry", who);
+  g = EmbG{B, H, W, (H - KH) / SH + 1, W - KW + 1, KH, KW, SH, xp, yp};
+  B200_REQUIRE(xp >= W && yp >= g.OW && xp % 4 == 0 && yp % 4 == 0, B200ASR_BAD_SHAPE,
+               "%s: row pitches must be multiples of 4 floats (TMA) and cover the rows (x pitch %d for W=%d, y pitch %d for OW=%d)", who, xp, W, yp, g.OW);
+  return B200ASR_OK;
+}
+
+}  // namespace tc
+}  // namespace b200asr
+
+using namespace b200asr;
+using namespace b200asr::tc;
+
+extern "C" {
+
+size_t b200asr_conv2d_tc_ws_bytes(int KH, int KW) { return sizeof(float) * 2 * (size_t)KH * KW * EC * EC; }
+
+int b200asr_conv2d_tc_fwd(const float* x, const float* w, const float* bias, float* y, void* ws, int B, int Ci, int H, int W, int Co,
+                          int KH, int KW, int SH, int x_pitch, int y_pitch, int precision, b200asr_stream_t stream) {
+  B200_REQUIRE(x && w && y && ws, B200ASR_BAD_ARG, "conv2d_tc_fwd: null pointer");
+  B200_REQUIRE(precision == 3 || precision == 6 || precision == 2, B200ASR_BAD_ARG, "conv2d_tc_fwd: precision must be 3, 6 or 2");
+  EmbG g;
+  if (int rc = emb_geom(g, "conv2d_tc_fwd", B, Ci, H, W, Co, KH, KW, SH, x_pitch, y_pitch)) return rc;
+  B200_REQUIRE(aligned16(x) && aligned16(ws), B200ASR_BAD_ALIGN, "conv2d_tc_fwd: alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int total = KH * KW * EC * EC;
+  emb_repack_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, ws, KH, KW, 0, precision);
+  note_launch(1);
+  CUtensorMap ma, mb;
+  if (int rc = nchw_map(&ma, x, W, x_pitch, H, B, true)) return rc;
+  {
+    uint64_t dims[2] = {(uint64_t)EC, (uint64_t)(precision == 2 ? 1 : 2) * KH * KW * EC}, strides[1] = {(uint64_t)EC};
+    uint32_t box[2] = {EC, EC};
+    int rc = precision == 3 ? make_tensor_map_f32(&mb, ws, 2, dims, strides, box, false, false) : make_tensor_map_bf16(&mb, ws, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  EmbConvP e{y, bias, g, g.OH, g.OW, y_pitch, ceil_div(g.OW, 128), KH * KW * EC};
+  return launch_emb_conv<false>(ma, mb, e, precision, st);
+}
+
+int b200asr_conv2d_tc_bwd_data(const float* dy, const float* w, float* dx, void* ws, int B, int Ci, int H, int W, int Co, int KH,
+                               int KW, int SH, int x_pitch, int y_pitch, int precision, b200asr_stream_t stream) {
+  B200_REQUIRE(dy && w && dx && ws, B200ASR_BAD_ARG, "conv2d_tc_bwd_data: null pointer");
+  B200_REQUIRE(precision == 3 || precision == 6 || precision == 2, B200ASR_BAD_ARG, "conv2d_tc_bwd_data: precision must be 3, 6 or 2");
+  EmbG g;
+  if (int rc = emb_geom(g, "conv2d_tc_bwd_data", B, Ci, H, W, Co, KH, KW, SH, x_pitch, y_pitch)) return rc;
+  B200_REQUIRE(aligned16(dy) && aligned16(ws), B200ASR_BAD_ALIGN, "conv2d_tc_bwd_data: alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int total = KH * KW * EC * EC;
+  emb_repack_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, ws, KH, KW, 1, precision);
+  note_launch(1);
+  CUtensorMap ma, mb;
+  if (int rc = nchw_map(&ma, dy, g.OW, y_pitch, g.OH, B, true)) return rc;
+  {
+    uint64_t dims[2] = {(uint64_t)EC, (uint64_t)(precision == 2 ? 1 : 2) * KH * KW * EC}, strides[1] = {(uint64_t)EC};
+    uint32_t box[2] = {EC, EC};
+    int rc = precision == 3 ? make_tensor_map_f32(&mb, ws, 2, dims, strides, box, false, false) : make_tensor_map_bf16(&mb, ws, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  EmbConvP e{dx, nullptr, g, H, W, x_pitch, ceil_div(W, 128), KH * KW * EC};
+  return launch_emb_conv<true>(ma, mb, e, precision, st);
+}
+
+int b200asr_conv2d_tc_bwd_weight(const float* dy, const float* x, float* dw, float* dbias, int B, int Ci, int H, int W, int Co, int KH,
+                                 int KW, int SH, int x_pitch, int y_pitch, b200asr_stream_t stream) {
+  B200_REQUIRE(dy && x && dw, B200ASR_BAD_ARG, "conv2d_tc_bwd_weight: null pointer");
+  EmbG g;
+  if (int rc = emb_geom(g, "conv2d_tc_bwd_weight", B, Ci, H, W, Co, KH, KW, SH, x_pitch, y_pitch)) return rc;
+  B200_REQUIRE(aligned16(dy) && aligned16(x), B200ASR_BAD_ALIGN, "conv2d_tc_bwd_weight: alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)EC * EC * KH * KW, st);
+  CUtensorMap mx, mdy;
+  if (int rc = nchw_map(&mx, x, W, x_pitch, H, B, false)) return rc;          // K-major tiles: plain 128B swizzle
+  if (int rc = nchw_map(&mdy, dy, g.OW, y_pitch, g.OH, B, false)) return rc;
+  EmbWgP e{dw, g, ceil_div(KW, 4), 1, B * g.OH, ceil_div(g.OW, 32)};
+  const int base = KH * e.m_tiles, rows = B * g.OH;
+  int splits = max(1, (3 * device_sm_count()) / base);
+  e.rows_per_split = max(8, ceil_div(rows, splits));
+  e.splits = ceil_div(rows, e.rows_per_split);
+  EmbWgradPolicy::Params p{e};
+  int rc = launch_engine<EmbWgradPolicy, 3>(mx, mdy, p, base * e.splits, st, "conv2d_tc_wgrad");
+  if (rc) return rc;
+  if (dbias) {
+    emb_bias_grad_kernel<<<EC, 256, 0, st>>>(dy, dbias, B, g.OH, g.OW, y_pitch);
+    return check_launch("conv2d_tc_bias_grad");
+  }
+  return B200ASR_OK;
+}
+
+}  // extern "C"

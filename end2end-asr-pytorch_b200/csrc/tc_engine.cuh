@@ -79,8 +79,8 @@ template <class Policy, int NSPLIT> struct EngineCfg {
   static constexpr int kTxBytes = kBf16 ? Policy::kABytes + (Policy::kSplitB ? Policy::kBBytes : kBHalves * kBTile)
                                         : Policy::kABytes + Policy::kBBytes +
                                           (NSPLIT == 3 && !Policy::kSplitB ? Policy::kBBytes : 0);   // pre-split B arrives as hi+lo
-  static_assert(!kBf16 || (!Policy::kAMN && !Policy::kBMN && !Policy::kSplitB) || (Policy::kAMN && Policy::kBMN && Policy::kSplitB),
-                "bf16 modes: K-major A with a pre-converted K-major bf16 B, or both operands MN-major fp32 (converted in the kernel)");
+  static_assert(!kBf16 || (!Policy::kBMN && !Policy::kSplitB) || (Policy::kAMN && Policy::kBMN && Policy::kSplitB),
+                "bf16 modes: a pre-converted K-major bf16 B (A of either major), or both operands MN-major fp32 (converted in the kernel)");
   static_assert(kStages >= 2, "stage too large");
   // Each split group must see EVERY phase of the full barriers it waits on: mbarrier parity waits only distinguish the
   // current phase from the one before, so a group that skipped a phase of a stage could take a stale completion for the

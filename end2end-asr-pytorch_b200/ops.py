@@ -916,8 +916,9 @@ class EmbFrontendFn(torch.autograd.Function):
     num_batches_tracked buffers (bn1, bn2 = (running_mean, running_var, num_batches_tracked, momentum) or None) are
     updated in the kernel; eval -> the running statistics normalise (the reference validates with model.eval(),
     trainer.py:123, and Transformer.evaluate reads the same buffers through the stock nn.BatchNorm2d).
-    The convolutions run as im2col + tensor-core GEMM (config.conv / config.conv_wgrad) or, for precision "fp32", as
-    direct CUDA-core kernels."""
+    Tensor-core modes: the first convolution (C_in = 1, K = 451) runs as im2col + the GEMM of the linear layers; the second
+    (32 -> 32 channels, 21 x 11 taps, 88% of the front end's FLOPs) as IMPLICIT GEMMs for forward, data gradient and weight
+    gradient (tc_emb.cu) on row-pitched NCHW tensors -- no column matrix.  Precision "fp32": direct CUDA-core kernels."""
 
     G1, G2 = (41, 11, 2, 2, 0, 10), (21, 11, 2, 1, 0, 0)
 
@@ -941,34 +942,44 @@ class EmbFrontendFn(torch.autograd.Function):
         new = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
         C = w0.shape[0]
         gemm = config.conv != L.PREC_FP32 and C % 4 == 0
+        implicit = gemm and C == 32 and w3.shape[1] == 32            # tc_emb.cu takes 32 -> 32 channels
         H1, W1 = (H - 41) // 2 + 1, (W + 20 - 11) // 2 + 1
+        H2, W2 = (H1 - 21) // 2 + 1, (W1 - 11) // 1 + 1
+        P1, P2 = ((W1 + 3) // 4 * 4, (W2 + 3) // 4 * 4) if implicit else (W1, W2)      # TMA: 16-byte row pitches
+        col1 = None
         if gemm:
             c1, col1 = _conv_gemm_fwd(x, w0, b0, EmbFrontendFn.G1, config.conv)
         else:
             c1 = new(B, C, H1, W1)
             L.check(lib.b200asr_conv2d_fwd(L.ptr(x), L.ptr(_f32c(w0)), L.ptr(b0), L.ptr(c1), B, 1, H, W, C, 41, 11, 2, 2, 0, 10, st), "emb_conv1")
-        a1, m1, s1 = new(B, C, H1, W1), new(C), new(C)
+        a1, m1, s1 = new(B, C, H1, P1), new(C), new(C)
         rm, rv, nbt, mom = bn_args(bn1)
         L.check(lib.b200asr_bn_clamp_fwd(L.ptr(c1), L.ptr(g1), L.ptr(be1), L.ptr(a1), L.ptr(m1), L.ptr(s1), L.ptr(rm), L.ptr(rv),
-                                         L.ptr(nbt), B, C, H1 * W1, eps, mom, int(training), 0.0, 20.0, st), "emb_bn1")
-        H2, W2 = (H1 - 21) // 2 + 1, (W1 - 11) // 1 + 1
-        if gemm:
+                                         L.ptr(nbt), B, C, H1, W1, W1, P1, eps, mom, int(training), 0.0, 20.0, st), "emb_bn1")
+        col2 = None
+        c2 = new(B, C, H2, P2)
+        if implicit:
+            prec2 = config.conv if config.conv in (L.PREC_TF32X3, L.PREC_BF16X3, L.PREC_BF16) else L.PREC_TF32X3
+            ws = torch.empty(lib.b200asr_conv2d_tc_ws_bytes(21, 11) // 4, device=dev, dtype=torch.float32)
+            L.check(lib.b200asr_conv2d_tc_fwd(L.ptr(a1), L.ptr(_f32c(w3)), L.ptr(b3), L.ptr(c2), L.ptr(ws), B, C, H1, W1, C, 21, 11, 2,
+                                              P1, P2, prec2, st), "emb_conv2_tc")
+        elif gemm:
             c2, col2 = _conv_gemm_fwd(a1, w3, b3, EmbFrontendFn.G2, config.conv)
         else:
-            c2 = new(B, C, H2, W2)
             L.check(lib.b200asr_conv2d_fwd(L.ptr(a1), L.ptr(_f32c(w3)), L.ptr(b3), L.ptr(c2), B, C, H1, W1, C, 21, 11, 2, 1, 0, 0, st), "emb_conv2")
         a2, m2, s2 = new(B, C, H2, W2), new(C), new(C)
         rm, rv, nbt, mom = bn_args(bn2)
         L.check(lib.b200asr_bn_clamp_fwd(L.ptr(c2), L.ptr(g4), L.ptr(be4), L.ptr(a2), L.ptr(m2), L.ptr(s2), L.ptr(rm), L.ptr(rv),
-                                         L.ptr(nbt), B, C, H2 * W2, eps, mom, int(training), 0.0, 20.0, st), "emb_bn2")
+                                         L.ptr(nbt), B, C, H2, W2, P2, W2, eps, mom, int(training), 0.0, 20.0, st), "emb_bn2")
         out = new(B, W2, C * H2)
         L.check(lib.b200asr_flatten_bcft_fwd(L.ptr(a2), L.ptr(out), B, C, H2, W2, st), "emb_flatten")
         ctx.save_for_backward(x, c1, a1, m1, s1, c2, a2, m2, s2, w0, g1, w3, g4)
         if decision_capture is not None:
-            decision_capture.extend([("hardtanh", a1), ("hardtanh", a2)])
-        ctx.gemm = (gemm, config.conv, config.conv_wgrad)
+            decision_capture.extend([("hardtanh", a1[..., :W1]), ("hardtanh", a2)])
+        ctx.gemm = (gemm, implicit, config.conv, config.conv_wgrad)
+        ctx.geom = (H1, W1, P1, H2, W2, P2)
         ctx.training = bool(training)
-        ctx.cols = (col1, col2) if gemm else None
+        ctx.cols = (col1, col2)
         return out
 
     @staticmethod
@@ -976,28 +987,38 @@ class EmbFrontendFn(torch.autograd.Function):
         if frontend_backward_hook is not None:
             frontend_backward_hook()
         x, c1, a1, m1, s1, c2, a2, m2, s2, w0, g1, w3, g4 = ctx.saved_tensors
-        gemm, prec, prec_w = ctx.gemm
+        gemm, implicit, prec, prec_w = ctx.gemm
+        H1, W1, P1, H2, W2, P2 = ctx.geom
         lib, st = _lib(), _stream()
         B, _, H, W = x.shape
         C = w0.shape[0]
-        _, _, H1, W1 = c1.shape
-        _, _, H2, W2 = c2.shape
         dev = x.device
         new = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
         dout = _f32c(dout)
+        tr = int(ctx.training)
         da2 = new(B, C, H2, W2)
         L.check(lib.b200asr_flatten_bcft_bwd(L.ptr(dout), L.ptr(da2), B, C, H2, W2, st), "emb_flatten_bwd")
-        dc2, dg4, dbe4 = new(B, C, H2, W2), new(C), new(C)
-        L.check(lib.b200asr_bn_clamp_bwd(L.ptr(da2), L.ptr(c2), L.ptr(a2), L.ptr(g4), L.ptr(m2), L.ptr(s2), L.ptr(dc2), L.ptr(dg4), L.ptr(dbe4), B, C, H2 * W2, int(ctx.training), 0.0, 20.0, st), "emb_bn2_bwd")
-        if gemm:
+        dc2, dg4, dbe4 = new(B, C, H2, P2), new(C), new(C)
+        L.check(lib.b200asr_bn_clamp_bwd(L.ptr(da2), L.ptr(c2), L.ptr(a2), L.ptr(g4), L.ptr(m2), L.ptr(s2), L.ptr(dc2), L.ptr(dg4), L.ptr(dbe4),
+                                         B, C, H2, W2, W2, P2, W2, P2, tr, 0.0, 20.0, st), "emb_bn2_bwd")
+        da1 = new(B, C, H1, P1)
+        if implicit:
+            dw3, db3 = torch.empty_like(w3), new(C)
+            L.check(lib.b200asr_conv2d_tc_bwd_weight(L.ptr(dc2), L.ptr(a1), L.ptr(dw3), L.ptr(db3), B, C, H1, W1, C, 21, 11, 2, P1, P2, st),
+                    "emb_conv2_tc_wgrad")
+            prec2 = prec if prec in (L.PREC_TF32X3, L.PREC_BF16X3, L.PREC_BF16) else L.PREC_TF32X3
+            ws = torch.empty(lib.b200asr_conv2d_tc_ws_bytes(21, 11) // 4, device=dev, dtype=torch.float32)
+            L.check(lib.b200asr_conv2d_tc_bwd_data(L.ptr(dc2), L.ptr(_f32c(w3)), L.ptr(da1), L.ptr(ws), B, C, H1, W1, C, 21, 11, 2, P1, P2,
+                                                   prec2, st), "emb_conv2_tc_dgrad")
+        elif gemm:
             da1, dw3, db3 = _conv_gemm_bwd(dc2, a1, w3, ctx.cols[1], EmbFrontendFn.G2, prec, prec_w, True)
         else:
             dw3, db3 = torch.empty_like(w3), new(C)
             L.check(lib.b200asr_conv2d_bwd_weight(L.ptr(dc2), L.ptr(a1), L.ptr(dw3), L.ptr(db3), B, C, H1, W1, C, 21, 11, 2, 1, 0, 0, st), "emb_conv2_wgrad")
-            da1 = new(B, C, H1, W1)
             L.check(lib.b200asr_conv2d_bwd_data(L.ptr(dc2), L.ptr(_f32c(w3)), L.ptr(da1), B, C, H1, W1, C, 21, 11, 2, 1, 0, 0, st), "emb_conv2_dgrad")
         dc1, dg1, dbe1 = new(B, C, H1, W1), new(C), new(C)
-        L.check(lib.b200asr_bn_clamp_bwd(L.ptr(da1), L.ptr(c1), L.ptr(a1), L.ptr(g1), L.ptr(m1), L.ptr(s1), L.ptr(dc1), L.ptr(dg1), L.ptr(dbe1), B, C, H1 * W1, int(ctx.training), 0.0, 20.0, st), "emb_bn1_bwd")
+        L.check(lib.b200asr_bn_clamp_bwd(L.ptr(da1), L.ptr(c1), L.ptr(a1), L.ptr(g1), L.ptr(m1), L.ptr(s1), L.ptr(dc1), L.ptr(dg1), L.ptr(dbe1),
+                                         B, C, H1, W1, P1, W1, P1, W1, tr, 0.0, 20.0, st), "emb_bn1_bwd")
         if gemm:
             _, dw0, db0 = _conv_gemm_bwd(dc1, x, w0, ctx.cols[0], EmbFrontendFn.G1, prec, prec_w, False)
             ctx.cols = None

@@ -221,17 +221,33 @@ int b200asr_conv2d_bwd_data(const float* dy, const float* w, float* dx, int B, i
 int b200asr_conv2d_bwd_weight(const float* dy, const float* x, float* dw, float* dbias, int B, int Ci, int H,
                               int W, int Co, int KH, int KW, int SH, int SW, int PH, int PW,
                               b200asr_stream_t stream);
-/* y = clamp(BN(x), lo, hi); x,y [B,C,HW]; mean/invstd [C] are outputs (the statistics used: saved for backward).
+/* y = clamp(BN(x), lo, hi); x,y [B,C,H,W] with a row pitch each (floats, >= W; dense tensors pass W); mean/invstd [C] are
+ * outputs (the statistics used: saved for backward).
  * training != 0: batch statistics (biased variance, as ATen) and, if the buffers are given, the nn.BatchNorm2d state
  * update running_mean/var <- (1-momentum) old + momentum new (unbiased variance), num_batches_tracked (int64) += 1.
  * training == 0 (model.eval(), trainer.py:123): normalise with running_mean / running_var. */
 int b200asr_bn_clamp_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean,
                          float* invstd, float* running_mean, float* running_var, long long* num_batches_tracked,
-                         int B, int C, int HW, float eps, float momentum, int training, float lo, float hi,
-                         b200asr_stream_t stream);
+                         int B, int C, int H, int W, int x_pitch, int y_pitch, float eps, float momentum, int training,
+                         float lo, float hi, b200asr_stream_t stream);
 int b200asr_bn_clamp_bwd(const float* dy, const float* x, const float* y, const float* gamma,
                          const float* mean, const float* invstd, float* dx, float* dgamma, float* dbeta,
-                         int B, int C, int HW, int training, float lo, float hi, b200asr_stream_t stream);
+                         int B, int C, int H, int W, int dy_pitch, int x_pitch, int y_pitch, int dx_pitch, int training,
+                         float lo, float hi, b200asr_stream_t stream);
+/* The second emb_cnn convolution (models/asr/transformer.py:37, Conv2d(32, 32, (KH, KW), stride (SH, 1)), no padding) as
+ * implicit GEMMs on tcgen05 -- no im2col matrix.  x / dx [B,32,H,W] with row pitch x_pitch, y / dy [B,32,OH,OW] with row
+ * pitch y_pitch (floats, multiples of 4: TMA); w [32,32,KH,KW].  precision 6 (bf16x3), 3 (3xTF32) or 2 (bf16) for forward
+ * and data gradient; the weight gradient runs 3xTF32 and accumulates with atomics (dw is zeroed here).
+ * ws: b200asr_conv2d_tc_ws_bytes(KH, KW) bytes (the repacked weight slices). */
+size_t b200asr_conv2d_tc_ws_bytes(int KH, int KW);
+int b200asr_conv2d_tc_fwd(const float* x, const float* w, const float* bias, float* y, void* ws, int B, int Ci, int H,
+                          int W, int Co, int KH, int KW, int SH, int x_pitch, int y_pitch, int precision,
+                          b200asr_stream_t stream);
+int b200asr_conv2d_tc_bwd_data(const float* dy, const float* w, float* dx, void* ws, int B, int Ci, int H, int W, int Co,
+                               int KH, int KW, int SH, int x_pitch, int y_pitch, int precision,
+                               b200asr_stream_t stream);
+int b200asr_conv2d_tc_bwd_weight(const float* dy, const float* x, float* dw, float* dbias, int B, int Ci, int H, int W,
+                                 int Co, int KH, int KW, int SH, int x_pitch, int y_pitch, b200asr_stream_t stream);
 /* x [B,C,F,T] -> y [B,T,C*F] and its inverse (gradient) */
 int b200asr_flatten_bcft_fwd(const float* x, float* y, int B, int C, int F, int T, b200asr_stream_t stream);
 int b200asr_flatten_bcft_bwd(const float* dy, float* dx, int B, int C, int F, int T, b200asr_stream_t stream);

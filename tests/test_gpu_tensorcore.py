@@ -289,3 +289,41 @@ def test_linear_with_presplit_weights(L, M, N, K):
     dx = torch.full((M, K), float("nan"), device="cuda")
     L.check(lib.b200asr_linear_bwd_data(L.ptr(dy), L.ptr(w), None, L.ptr(dx), M, N, K, 0, 3, L.ptr(ws), _stream()), "dgrad")
     assert rel_err(dx, dy.double() @ w.double()) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ emb_cnn implicit GEMM
+@pytest.mark.parametrize("B,H,W,KH,KW,SH", [(2, 61, 45, 21, 11, 2), (1, 30, 205, 21, 11, 2), (3, 25, 140, 5, 3, 1), (2, 23, 131, 21, 11, 2)])
+@pytest.mark.parametrize("prec,tol", [(3, 3e-5), (6, 3e-5), (2, 1e-2)])
+def test_conv2d_implicit_gemm_32ch(L, B, H, W, KH, KW, SH, prec, tol):
+    """tc_emb.cu through the raw C ABI: forward, data gradient and weight gradient of Conv2d(32, 32, (KH, KW), stride (SH, 1))
+    on row-pitched NCHW tensors against float64 (W and OW deliberately not multiples of 4 / 32 / 128)."""
+    import torch.nn.functional as F
+    lib = L.load()
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator().manual_seed(B * 1000 + W)
+    OH, OW = (H - KH) // SH + 1, W - KW + 1
+    xp, yp = (W + 3) // 4 * 4, (OW + 3) // 4 * 4
+    x = torch.randn(B, 32, H, W, generator=g).cuda()
+    w = (torch.randn(32, 32, KH, KW, generator=g) * (32 * KH * KW) ** -0.5).cuda()
+    b = torch.randn(32, generator=g).cuda()
+    dy = torch.randn(B, 32, OH, OW, generator=g).cuda()
+    x64 = x.double().requires_grad_(True)
+    w64 = w.double().requires_grad_(True)
+    y64 = F.conv2d(x64, w64, b.double(), stride=(SH, 1))
+    y64.backward(dy.double())
+    # pitched copies, pad columns poisoned with NaN: nothing may read them
+    xpad = torch.full((B, 32, H, xp), float("nan"), device="cuda"); xpad[..., :W] = x
+    dypad = torch.full((B, 32, OH, yp), float("nan"), device="cuda"); dypad[..., :OW] = dy
+    ypad = torch.full((B, 32, OH, yp), float("nan"), device="cuda")
+    dxpad = torch.full((B, 32, H, xp), float("nan"), device="cuda")
+    ws = torch.empty(lib.b200asr_conv2d_tc_ws_bytes(KH, KW) // 4, device="cuda")
+    L.check(lib.b200asr_conv2d_tc_fwd(L.ptr(xpad), L.ptr(w), L.ptr(b), L.ptr(ypad), L.ptr(ws), B, 32, H, W, 32, KH, KW, SH, xp, yp, prec, st), "fwd")
+    assert rel_err(ypad[..., :OW], y64) < tol
+    L.check(lib.b200asr_conv2d_tc_bwd_data(L.ptr(dypad), L.ptr(w), L.ptr(dxpad), L.ptr(ws), B, 32, H, W, 32, KH, KW, SH, xp, yp, prec, st), "dgrad")
+    assert rel_err(dxpad[..., :W], x64.grad) < tol
+    if prec == 3:
+        dw = torch.empty_like(w)
+        db = torch.empty(32, device="cuda")
+        L.check(lib.b200asr_conv2d_tc_bwd_weight(L.ptr(dypad), L.ptr(xpad), L.ptr(dw), L.ptr(db), B, 32, H, W, 32, KH, KW, SH, xp, yp, st), "wgrad")
+        assert rel_err(dw, w64.grad) < tol
+        assert rel_err(db, dy.double().sum((0, 2, 3))) < 1e-5
