@@ -91,8 +91,11 @@ def algorithmic_flops(name, a):
     if name == "linear_fwd" or name == "linear_bwd_data" or name == "linear_bwd_weight":
         M, N, K = a[4], a[5], a[6]
         return 2.0 * M * N * K
-    if name in ("conv3x3_fwd", "conv3x3_bwd_data", "conv3x3_bwd_weight"):
+    if name == "conv3x3_fwd":
         B, T, F, Ci, Co = a[5], a[6], a[7], a[8], a[9]
+        return 2.0 * 9 * B * T * F * Ci * Co
+    if name in ("conv3x3_bwd_data", "conv3x3_bwd_weight"):       # one more pointer (the bf16 pair output / input) before the dims
+        B, T, F, Ci, Co = a[6], a[7], a[8], a[9], a[10]
         return 2.0 * 9 * B * T * F * Ci * Co
     if name == "conv3x3_c1_fwd" or name == "conv3x3_c1_bwd_weight":
         off = 4

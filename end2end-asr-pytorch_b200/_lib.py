@@ -58,11 +58,11 @@ SIGNATURES = {
     "b200asr_conv3x3_c1_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200asr_conv3x3_c1_bwd_weight": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "b200asr_conv3x3_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "b200asr_conv3x3_bwd_data": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
-    "b200asr_conv3x3_bwd_weight": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "b200asr_conv3x3_bwd_data": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "b200asr_conv3x3_bwd_weight": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "b200asr_conv3x3_ws_bytes": (_sz, [_i, _i]),
     "b200asr_maxpool2x2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
-    "b200asr_maxpool2x2_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "b200asr_maxpool2x2_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200asr_conv2d_fwd": (_i, [_vp, _vp, _vp, _vp] + [_i] * 11 + [_vp]),
     "b200asr_conv2d_bwd_data": (_i, [_vp, _vp, _vp] + [_i] * 11 + [_vp]),
     "b200asr_conv2d_bwd_weight": (_i, [_vp, _vp, _vp, _vp] + [_i] * 11 + [_vp]),

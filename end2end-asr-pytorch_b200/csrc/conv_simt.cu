@@ -429,8 +429,24 @@ __global__ void maxpool2x2_fwd_kernel(const float* __restrict__ x, float* __rest
 
 // one thread = one 2x2 window x 4 channels; writes all four dx positions (and zeroes are written for the odd tails
 // by the tail kernel below).  ATen scans the window freq-major (h = freq outer, w = time inner) and keeps the first max.
+// fp32 value -> (bf16 hi, bf16 lo) with hi + lo ~ x to 16 significant bits (the operand split of the kind::f16 kernels)
+__device__ __forceinline__ void pair_of(float x, uint16_t& h, uint16_t& l) {
+  const uint32_t r = __float_as_uint(x) + 0x8000u;
+  h = (uint16_t)(r >> 16);
+  const float lo = x - __uint_as_float(r & 0xFFFF0000u);
+  l = (uint16_t)((__float_as_uint(lo) + 0x8000u) >> 16);
+}
+__device__ __forceinline__ void store_pairs4(uint16_t* __restrict__ hi, size_t lo_off, size_t idx, const float4& v) {
+  uint16_t h[4], l[4];
+  pair_of(v.x, h[0], l[0]); pair_of(v.y, h[1], l[1]); pair_of(v.z, h[2], l[2]); pair_of(v.w, h[3], l[3]);
+  *reinterpret_cast<uint2*>(hi + idx) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+  *reinterpret_cast<uint2*>(hi + lo_off + idx) = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+}
+
+// dx16 (optional): the same gradient additionally as bf16 hi | lo pairs [2][B,T,F,C] -- the B operand of the convolution
+// weight gradient in the bf16 modes arrives from there by TMA (tc_conv.cu WgradPairPolicy)
 __global__ void maxpool2x2_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx,
-                                      int B, int T, int F, int C, int relu_mask) {
+                                      uint16_t* __restrict__ dx16, int B, int T, int F, int C, int relu_mask) {
   const int T2 = T / 2, F2 = F / 2, C4 = C / 4;
   long long n = (long long)B * T2 * F2 * C4;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -463,9 +479,14 @@ __global__ void maxpool2x2_bwd_kernel(const float* __restrict__ dy, const float*
   route(v[0].w, v[1].w, v[2].w, v[3].w, g.w, out[0].w, out[1].w, out[2].w, out[3].w);
 #pragma unroll
   for (int k = 0; k < 4; k++) *reinterpret_cast<float4*>(dx + base + offs[k]) = out[k];
+  if (dx16) {
+    const size_t lo_off = (size_t)B * T * F * C;
+#pragma unroll
+    for (int k = 0; k < 4; k++) store_pairs4(dx16, lo_off, base + offs[k], out[k]);
+  }
 }
 // zero the rows/cols that floor-mode pooling never reads (odd T or F): only those positions are visited
-__global__ void maxpool2x2_bwd_tail_kernel(float* __restrict__ dx, int B, int T, int F, int C) {
+__global__ void maxpool2x2_bwd_tail_kernel(float* __restrict__ dx, uint16_t* __restrict__ dx16, int B, int T, int F, int C) {
   const int C4 = C / 4;
   const int odd_f = F & 1, odd_t = T & 1;
   const int Te = (T / 2) * 2;                                    // rows with t < Te only need the odd freq column
@@ -482,7 +503,12 @@ __global__ void maxpool2x2_bwd_tail_kernel(float* __restrict__ dx, int B, int T,
     c = (int)(i % C4) * 4; long long r = i / C4;
     f = (int)(r % F); b = (int)(r / F); t = T - 1;
   }
-  *reinterpret_cast<float4*>(dx + (((size_t)b * T + t) * F + f) * C + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+  const size_t idx = (((size_t)b * T + t) * F + f) * C + c;
+  *reinterpret_cast<float4*>(dx + idx) = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (dx16) {
+    *reinterpret_cast<uint2*>(dx16 + idx) = make_uint2(0u, 0u);
+    *reinterpret_cast<uint2*>(dx16 + (size_t)B * T * F * C + idx) = make_uint2(0u, 0u);
+  }
 }
 
 __global__ void relu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dx, long long n4) {
@@ -612,7 +638,7 @@ int b200asr_conv3x3_fwd(const float* x, const float* w, const float* bias, float
   return conv3x3_tc(x, (const float*)ws, bias, nullptr, y, B, T, F, Ci, Co, relu, precision, st);
 }
 
-int b200asr_conv3x3_bwd_data(const float* dy, const float* w, const float* relu_out, float* dx, void* ws, int B, int T,
+int b200asr_conv3x3_bwd_data(const float* dy, const float* w, const float* relu_out, float* dx, void* dx16, void* ws, int B, int T,
                              int F, int Ci, int Co, int precision, b200asr_stream_t stream) {
   B200_REQUIRE(dy && w && dx && ws, B200ASR_BAD_ARG, "conv3x3_bwd_data: null pointer");
   int rc = conv_shape_ok("conv3x3_bwd_data", Co, Ci);   // roles swap: contraction over Co, output channels Ci
@@ -627,14 +653,15 @@ int b200asr_conv3x3_bwd_data(const float* dy, const float* w, const float* relu_
   if (conv_is_bf16(precision)) {
     B200_REQUIRE(Co % 32 == 0 && (Ci == 64 || Ci == 128), B200ASR_BAD_SHAPE, "conv3x3_bwd_data (bf16): needs Co %% 32 == 0 and Ci in {64,128}");
     conv_repack_k_bf16_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, (uint16_t*)ws, Ci, Co, 1, precision == B200ASR_PREC_BF16X3 ? 2 : 1);
-    return conv3x3_tc_halo(dy, ws, nullptr, relu_out, dx, B, T, F, Co, Ci, 0, precision, st);
+    return conv3x3_tc_halo(dy, ws, nullptr, relu_out, dx, B, T, F, Co, Ci, 0, precision, st, dx16);
   }
+  B200_REQUIRE(!dx16, B200ASR_BAD_ARG, "conv3x3_bwd_data: the bf16 pair output exists in the bf16 modes only");
   conv_repack_k_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, (float*)ws, Ci, Co, 1, precision == B200ASR_PREC_TF32X3);
   return conv3x3_tc(dy, (const float*)ws, nullptr, relu_out, dx, B, T, F, Co, Ci, 0, precision, st);
 }
 
-int b200asr_conv3x3_bwd_weight(const float* dy, const float* x, float* dw, float* dbias, void* ws, int B, int T, int F,
-                               int Ci, int Co, int precision, b200asr_stream_t stream) {
+int b200asr_conv3x3_bwd_weight(const float* dy, const void* dy16, const float* x, float* dw, float* dbias, void* ws, int B, int T,
+                               int F, int Ci, int Co, int precision, b200asr_stream_t stream) {
   B200_REQUIRE(dy && x && dw && ws, B200ASR_BAD_ARG, "conv3x3_bwd_weight: null pointer");
   B200_REQUIRE(Ci % 64 == 0 && Co % 64 == 0, B200ASR_BAD_SHAPE, "conv3x3_bwd_weight: Ci=%d Co=%d must be multiples of 64", Ci, Co);
   cudaStream_t st = (cudaStream_t)stream;
@@ -642,7 +669,7 @@ int b200asr_conv3x3_bwd_weight(const float* dy, const float* x, float* dw, float
   int rc;
   int bias_done = 0;
   if (precision == B200ASR_PREC_FP32) rc = conv3x3_wgrad_simt(x, dy, (float*)ws, B, T, F, Ci, Co, st);
-  else rc = conv3x3_wgrad_tc(x, dy, (float*)ws, B, T, F, Ci, Co, precision, st, dbias, &bias_done);
+  else rc = conv3x3_wgrad_tc(x, dy, (float*)ws, B, T, F, Ci, Co, precision, st, dbias, &bias_done, dy16);
   if (rc) return rc;
   int total = 9 * Ci * Co;
   conv_unpack_wgrad_kernel<<<ceil_div(total, 256), 256, 0, st>>>((const float*)ws, dw, Ci, Co);
@@ -664,15 +691,15 @@ int b200asr_maxpool2x2_fwd(const float* x, float* y, int B, int T, int F, int C,
   return check_launch("maxpool2x2_fwd");
 }
 
-int b200asr_maxpool2x2_bwd(const float* dy, const float* x, float* dx, int B, int T, int F, int C, int relu_mask,
+int b200asr_maxpool2x2_bwd(const float* dy, const float* x, float* dx, void* dx16, int B, int T, int F, int C, int relu_mask,
                            b200asr_stream_t stream) {
   B200_REQUIRE(dy && x && dx && C % 4 == 0, B200ASR_BAD_ARG, "maxpool2x2_bwd: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   long long n = (long long)B * (T / 2) * (F / 2) * (C / 4);
-  if (n > 0) maxpool2x2_bwd_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, st>>>(dy, x, dx, B, T, F, C, relu_mask);
+  if (n > 0) maxpool2x2_bwd_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, st>>>(dy, x, dx, (uint16_t*)dx16, B, T, F, C, relu_mask);
   if ((T & 1) || (F & 1)) {
     long long tot = ((F & 1) ? (long long)B * (T / 2) * 2 * (C / 4) : 0) + ((T & 1) ? (long long)B * F * (C / 4) : 0);
-    maxpool2x2_bwd_tail_kernel<<<(unsigned)ceil_div_ll(tot, 256), 256, 0, st>>>(dx, B, T, F, C);
+    maxpool2x2_bwd_tail_kernel<<<(unsigned)ceil_div_ll(tot, 256), 256, 0, st>>>(dx, (uint16_t*)dx16, B, T, F, C);
     note_launch(1);
   }
   return check_launch("maxpool2x2_bwd");

@@ -176,6 +176,39 @@ struct WgradPolicy {
   }
 };
 
+// The same weight gradient with the dy operand arriving as bf16 hi | lo "pairs" that its producer (max-pool backward, the
+// convolution data gradient) wrote next to the fp32 tensor: [2][B,T,F,Co] bf16, hi first.  The tile is the bf16 MN-major
+// image the tensor core reads (64-channel chunks of 4 KB, one 128-byte k-line per pixel, 128B swizzle) straight from TMA
+// -- no conversion of B in the kernel, which is what bound the bf16 variant of WgradPolicy (tc_engine.cuh).
+template <int CI, int BN_>
+struct WgradPairPolicy : WgradPolicy<CI, BN_> {
+  using Base = WgradPolicy<CI, BN_>;
+  using typename Base::Params;
+  using typename Base::Tile;
+  static constexpr bool kSplitB = false, kSumB = true;
+  static __device__ __forceinline__ void load16(const Params& p, Tile& t, const CUtensorMap* mapX, const CUtensorMap* mapDy16,
+                                                uint32_t sa, uint32_t sb, uint32_t sb_lo, uint32_t bar, bool leader, int halves) {
+    const int f0 = t.ft * WG_PF, t0 = t.tt * WG_PT;
+    if (leader) {
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const int tap = (c * 32) / CI == 0 ? t.tap_a : t.tap_b;
+        tma_load_4d(sa + c * 4096, mapX, bar, (c * 32) % CI, f0 + tap / 3 - 1, t0 + tap % 3 - 1, t.b);
+      }
+#pragma unroll
+      for (int c = 0; c < BN_ / 64; c++) {
+        tma_load_4d(sb + c * 4096, mapDy16, bar, c * 64, f0, t0, t.b);
+        if (halves == 2) tma_load_4d(sb_lo + c * 4096, mapDy16, bar, c * 64, f0, t0, t.b + p.e.B);     // lo = second half of the batch axis
+      }
+    }
+    if (++t.ft == p.e.nft) {
+      t.ft = 0;
+      if (++t.tt == p.e.ntt) { t.tt = 0; t.b++; }
+    }
+  }
+  static __device__ __forceinline__ void sum_b_store1(const Params& p, const Tile&, int col, float v) { atomicAdd(p.e.dbias + col, v); }
+};
+
 template <int BN, int NSPLIT>
 static int launch_conv_persistent(const CUtensorMap& ma, const CUtensorMap& mb, const ConvEpi& e, cudaStream_t st) {
   typename ConvPolicy<BN, NSPLIT>::Params p{e, ceil_div(e.F, CT_F), ceil_div(e.T, CT_T), e.Cin / 32};
@@ -193,6 +226,17 @@ static int launch_wgrad_persistent(const CUtensorMap& mx, const CUtensorMap& mdy
   splits = ceil_div(e.total_blocks, e.blocks_per_cta);
   typename Pol::Params p{e, splits};
   return launch_engine<Pol, NSPLIT>(mx, mdy, p, Pol::kGroups * splits, st, "tc_conv3x3_wgrad");
+}
+
+template <int CI, int BN, int NSPLIT>
+static int launch_wgrad_pairs(const CUtensorMap& mx, const CUtensorMap& mdy, WgP e, cudaStream_t st) {
+  using Pol = WgradPairPolicy<CI, BN>;
+  const int sms = device_sm_count();
+  int splits = max(1, (2 * sms) / Pol::kGroups);
+  e.blocks_per_cta = max(64, ceil_div(e.total_blocks, splits));
+  splits = ceil_div(e.total_blocks, e.blocks_per_cta);
+  typename Pol::Params p{e, splits};
+  return launch_engine<Pol, NSPLIT>(mx, mdy, p, Pol::kGroups * splits, st, "tc_conv3x3_wgrad_pairs");
 }
 
 }  // namespace tc
@@ -234,9 +278,41 @@ int conv3x3_tc(const float* in, const float* wk, const float* bias, const float*
 // dbias (optional, 3xTF32 only): [Co], zeroed here and accumulated by the kernel; returns with *dbias_done = 1 when the
 // kernel took care of it (the caller runs the separate column-sum pass otherwise)
 int conv3x3_wgrad_tc(const float* x, const float* dy, float* dwr, int B, int T, int F, int Ci, int Co, int precision,
-                     cudaStream_t st, float* dbias, int* dbias_done) {
+                     cudaStream_t st, float* dbias, int* dbias_done, const void* dy16) {
   using namespace tc;
   if (dbias_done) *dbias_done = 0;
+  if (dy16 && (precision == 6 || precision == 2)) {
+    // dy as bf16 pairs [2][B,T,F,Co] written by its producer: B tiles by TMA, no conversion in the kernel
+    B200_REQUIRE((Ci == 64 || Ci == 128) && (Co == 64 || Co == 128), B200ASR_BAD_SHAPE, "conv3x3_wgrad_tc: needs Ci, Co in {64,128} (Ci=%d Co=%d)", Ci, Co);
+    B200_REQUIRE(aligned16(x) && aligned16(dy16) && aligned16(dwr), B200ASR_BAD_ALIGN, "conv3x3_wgrad_tc: alignment");
+    CUtensorMap mx, mdy;
+    {
+      uint64_t dims[4] = {(uint64_t)Ci, (uint64_t)F, (uint64_t)T, (uint64_t)B};
+      uint64_t strides[3] = {(uint64_t)Ci, (uint64_t)F * Ci, (uint64_t)T * F * Ci};
+      uint32_t box[4] = {32, WG_PF, WG_PT, 1};
+      if (int rc = make_tensor_map_f32(&mx, x, 4, dims, strides, box, true, false)) return rc;
+    }
+    {
+      uint64_t dims[4] = {(uint64_t)Co, (uint64_t)F, (uint64_t)T, (uint64_t)2 * B};
+      uint64_t strides[3] = {(uint64_t)Co, (uint64_t)F * Co, (uint64_t)T * F * Co};
+      uint32_t box[4] = {64, WG_PF, WG_PT, 1};
+      if (int rc = make_tensor_map_bf16(&mdy, dy16, 4, dims, strides, box)) return rc;
+    }
+    if (dbias) {
+      cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)Co, st);
+      if (dbias_done) *dbias_done = 1;
+    }
+    WgP e{dwr, dbias, B, T, F, Ci, Co, ceil_div(F, WG_PF), ceil_div(T, WG_PT), 0, 0};
+    const long long total = (long long)B * e.nft * e.ntt;
+    B200_REQUIRE(total < (1LL << 31), B200ASR_BAD_SHAPE, "conv3x3_wgrad_tc: too many pixel blocks");
+    e.total_blocks = (int)total;
+#define WGPP(CIv, BNv) return precision == 6 ? launch_wgrad_pairs<CIv, BNv, 6>(mx, mdy, e, st) : launch_wgrad_pairs<CIv, BNv, 2>(mx, mdy, e, st)
+    if (Ci == 64 && Co == 64) WGPP(64, 64);
+    if (Ci == 64 && Co == 128) WGPP(64, 128);
+    if (Ci == 128 && Co == 64) WGPP(128, 64);
+    WGPP(128, 128);
+#undef WGPP
+  }
   B200_REQUIRE(precision == 1 || precision == 3 || precision == 2 || precision == 6, B200ASR_BAD_ARG, "conv3x3_wgrad_tc: precision must be 1, 3 (tf32) or 2, 6 (bf16)");
   B200_REQUIRE((Ci == 64 || Ci == 128) && (Co == 64 || Co == 128), B200ASR_BAD_SHAPE,
                "conv3x3_wgrad_tc: needs Ci, Co in {64,128} (Ci=%d Co=%d)", Ci, Co);

@@ -36,6 +36,7 @@ constexpr int HPATCH_SLOTS = 3;                        // the patch of slice i+1
 constexpr int HALO_GROUPS = HALO_GROUPS_N, HALO_SPLIT = 128 * HALO_GROUPS, HALO_THREADS = 192 + HALO_SPLIT;
 
 struct HaloP {
+  uint16_t* out16;       // optional bf16 hi | lo pairs of the output, [2][pixels][Cout] (lo at + npix * Cout), or nullptr
   float* out;
   const float* bias;
   const float* mask;
@@ -227,6 +228,8 @@ tc_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
       const bool valid = tt < p.T && ff < p.F;
       const size_t pix = ((size_t)b * p.T + tt) * p.F + ff;
       float* orow = p.out + pix * p.Cout;
+      uint16_t* orow16 = p.out16 ? p.out16 + pix * p.Cout : nullptr;
+      const size_t lo_off = (size_t)p.B * p.T * p.F * p.Cout;
       const float* mrow = p.mask ? p.mask + pix * p.Cout : nullptr;
       mbar_wait(tfull_bar(buf), (tcount >> 1) & 1);
       tc_fence_after();
@@ -262,6 +265,13 @@ tc_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
             o[0] = mm[q].x > 0.f ? o[0] : 0.f; o[1] = mm[q].y > 0.f ? o[1] : 0.f;
             o[2] = mm[q].z > 0.f ? o[2] : 0.f; o[3] = mm[q].w > 0.f ? o[3] : 0.f;
             *reinterpret_cast<float4*>(orow + col) = make_float4(o[0], o[1], o[2], o[3]);
+            if (orow16) {       // the same values as bf16 pairs: the weight-gradient kernel's B operand (WgradPairPolicy)
+              uint2 ph, pl;
+              split_bf16_pair(o[0], o[1], ph.x, pl.x);
+              split_bf16_pair(o[2], o[3], ph.y, pl.y);
+              *reinterpret_cast<uint2*>(orow16 + col) = ph;
+              *reinterpret_cast<uint2*>(orow16 + lo_off + col) = pl;
+            }
           }
         }
       }
@@ -364,7 +374,7 @@ static int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const HaloP
 // wk: mode 3: [2][9][Cout][Cin] fp32 pre-split K-major weights (hi | lo), as for conv3x3_tc with precision 3;
 //     mode 6 / 2: [2 or 1][9][Cout][Cin] bf16 (conv_repack_k_bf16_kernel)
 int conv3x3_tc_halo(const float* in, const void* wk, const float* bias, const float* mask, float* out, int B, int T, int F,
-                    int Cin, int Cout, int relu, int mode, cudaStream_t st) {
+                    int Cin, int Cout, int relu, int mode, cudaStream_t st, void* out16) {
   using namespace tc;
   B200_REQUIRE(mode == 3 || mode == 6 || mode == 2, B200ASR_BAD_ARG, "conv3x3_tc_halo: mode must be 3 (3xTF32), 6 (bf16x3) or 2 (bf16)");
   B200_REQUIRE(Cin % 32 == 0 && (Cout == 64 || Cout == 128), B200ASR_BAD_SHAPE,
@@ -386,7 +396,7 @@ int conv3x3_tc_halo(const float* in, const void* wk, const float* bias, const fl
     int rc = mode == 3 ? make_tensor_map_f32(&mb, wk, 2, dims, strides, box, false, false) : make_tensor_map_bf16(&mb, wk, 2, dims, strides, box);
     if (rc) return rc;
   }
-  HaloP p{out, bias, mask, relu, B, T, F, Cin, Cout, ceil_div(F, HF), ceil_div(T, HT), Cin / 32};
+  HaloP p{(uint16_t*)out16, out, bias, mask, relu, B, T, F, Cin, Cout, ceil_div(F, HF), ceil_div(T, HT), Cin / 32};
   if (mode == 3) return Cout == 64 ? launch_halo<64, 3>(ma, mb, p, st) : launch_halo<128, 3>(ma, mb, p, st);
   if (mode == 6) return Cout == 64 ? launch_halo<64, 6>(ma, mb, p, st) : launch_halo<128, 6>(ma, mb, p, st);
   return Cout == 64 ? launch_halo<64, 2>(ma, mb, p, st) : launch_halo<128, 2>(ma, mb, p, st);

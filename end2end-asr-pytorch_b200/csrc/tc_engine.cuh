@@ -38,7 +38,9 @@ namespace tc {
 //   * or (Policy::kSplitB, both operands MN-major: the weight-gradient GEMMs, whose operands are activations) the raw fp32
 //     MN-major tile, which the split warps convert into bf16 MN-major tiles (64 columns = 128 bytes per k-line, SWIZZLE_128B)
 //     in a second shared-memory region of the stage.
-// Policy::b_desc16 describes the bf16 B tile either way.
+//   * or (Policy::kBMN without kSplitB) MN-major bf16 hi | lo tiles that the PRODUCER of the activation already wrote next to
+//     the fp32 tensor ("pairs"): loaded by TMA like the weights, no conversion at all (convolution weight gradient).
+// Policy::b_desc16 describes the bf16 B tile in every case.
 constexpr bool eng_is_bf16(int nsplit) { return nsplit == 2 || nsplit == 6; }
 constexpr bool eng_has_split_warps(int nsplit) { return nsplit != 1; }
 
@@ -79,8 +81,9 @@ template <class Policy, int NSPLIT> struct EngineCfg {
   static constexpr int kTxBytes = kBf16 ? Policy::kABytes + (Policy::kSplitB ? Policy::kBBytes : kBHalves * kBTile)
                                         : Policy::kABytes + Policy::kBBytes +
                                           (NSPLIT == 3 && !Policy::kSplitB ? Policy::kBBytes : 0);   // pre-split B arrives as hi+lo
-  static_assert(!kBf16 || (!Policy::kBMN && !Policy::kSplitB) || (Policy::kAMN && Policy::kBMN && Policy::kSplitB),
-                "bf16 modes: a pre-converted K-major bf16 B (A of either major), or both operands MN-major fp32 (converted in the kernel)");
+  static_assert(!kBf16 || !Policy::kSplitB || (Policy::kAMN && Policy::kBMN),
+                "bf16 modes: a pre-converted bf16 B (K-major weights, or MN-major activation pairs), or both operands MN-major fp32 "
+                "with B converted in the kernel");
   static_assert(kStages >= 2, "stage too large");
   // Each split group must see EVERY phase of the full barriers it waits on: mbarrier parity waits only distinguish the
   // current phase from the one before, so a group that skipped a phase of a stage could take a stale completion for the
@@ -292,6 +295,22 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           const uint32_t acol = tmem_base + ((uint32_t)(quarter * 32) << 16) + Cfg::kAccCols + s * Cfg::kACols;
           tmem_st16u(acol, hi);
           if constexpr (NSPLIT == 6) tmem_st16u(acol + 16, lo);
+          if constexpr (Policy::kSumB && !Policy::kSplitB) {
+            // column sums of a bf16 MN-major B tile that arrived by TMA (hi + lo = the 16-bit value the MMAs use): thread t
+            // owns column t -- 64-column chunks of 4 KB, k-line k at k * 128, 16-byte unit u stored at u ^ (k & 7)
+            if (want && t < BN) {
+              const uint8_t* bh = stage + Cfg::kOffBhi + ((t >> 6) << 12) + ((t & 7) << 1);
+              const int unit = (t & 63) >> 3;
+              float sum = 0.f;
+#pragma unroll 8
+              for (int k = 0; k < 32; k++) {
+                const uint8_t* q = bh + (k << 7) + ((unit ^ (k & 7)) << 4);
+                sum += __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(q)) << 16);
+                if constexpr (NSPLIT == 6) sum += __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(q + Cfg::kBTile)) << 16);
+              }
+              bsum[0].x += sum;
+            }
+          }
           if constexpr (Policy::kSplitB) {
             // raw tile: float4 i sits in 4 KB chunk i / 256 (32 columns), k-line (i % 256) / 8, 16-byte slot i % 8, and the
             // logical 32-byte atom is (slot / 2) ^ (k & 3) (SWIZZLE_128B_ATOM_32B).  bf16 tile: 64-column chunks of 4 KB, k-line
@@ -331,11 +350,14 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         if constexpr (kSums) {
           if (want) {
             if constexpr (Policy::kSumA) Policy::sum_a_store(p, stc, row, asum);
-            if constexpr (Policy::kSumB) {
+            if constexpr (Policy::kSumB && Policy::kSplitB) {
               const int slot = t & 7, kph = (t >> 3) & 3;
               const int col_in_chunk = (((slot >> 1) ^ kph) << 3) + ((slot & 1) << 2);
 #pragma unroll
               for (int c = 0; c < BN / 32; c++) Policy::sum_b_store(p, stc, c * 32 + col_in_chunk, bsum[c]);
+            }
+            if constexpr (Policy::kSumB && !Policy::kSplitB) {
+              if (t < BN) Policy::sum_b_store1(p, stc, t, bsum[0].x);
             }
           }
         }

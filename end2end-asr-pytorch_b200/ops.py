@@ -801,31 +801,35 @@ class VggFrontendFn(torch.autograd.Function):
         new = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
         ws = new(lib.b200asr_conv3x3_ws_bytes(C2, C2) // 4)
         dp2 = _f32c(dp2)
-        d4 = new(B, T2, F2, C2)
-        L.check(lib.b200asr_maxpool2x2_bwd(L.ptr(dp2), L.ptr(y4), L.ptr(d4), B, T2, F2, C2, 1, st), "pool2_bwd")
+        # bf16 weight gradient: the producers of the three dy tensors (both max-pool backward passes, conv4's data gradient)
+        # also write them as bf16 hi | lo pairs, which the weight-gradient kernel takes as its B operand by TMA
+        pairs = prec_w in _BF16_PRECS and prec in _BF16_PRECS
+        new16 = lambda *s_: torch.empty((2,) + s_, device=dev, dtype=torch.bfloat16) if pairs else None
+        d4, d4p = new(B, T2, F2, C2), new16(B, T2, F2, C2)
+        L.check(lib.b200asr_maxpool2x2_bwd(L.ptr(dp2), L.ptr(y4), L.ptr(d4), L.ptr(d4p), B, T2, F2, C2, 1, st), "pool2_bwd")
         dw7, db7 = torch.empty_like(w7), new(C2)
-        L.check(lib.b200asr_conv3x3_bwd_weight(L.ptr(d4), L.ptr(y3), L.ptr(dw7), L.ptr(db7), L.ptr(ws), B, T2, F2, C2, C2,
+        L.check(lib.b200asr_conv3x3_bwd_weight(L.ptr(d4), L.ptr(d4p), L.ptr(y3), L.ptr(dw7), L.ptr(db7), L.ptr(ws), B, T2, F2, C2, C2,
                                                prec_w, st), "conv4_wgrad")
-        d3 = new(B, T2, F2, C2)
-        L.check(lib.b200asr_conv3x3_bwd_data(L.ptr(d4), L.ptr(_f32c(w7)), L.ptr(y3), L.ptr(d3), L.ptr(ws), B, T2, F2, C2, C2,
+        d3, d3p = new(B, T2, F2, C2), new16(B, T2, F2, C2)
+        L.check(lib.b200asr_conv3x3_bwd_data(L.ptr(d4), L.ptr(_f32c(w7)), L.ptr(y3), L.ptr(d3), L.ptr(d3p), L.ptr(ws), B, T2, F2, C2, C2,
                                              prec, st), "conv4_dgrad")
-        del d4
+        del d4, d4p
         dw5, db5 = torch.empty_like(w5), new(C2)
-        L.check(lib.b200asr_conv3x3_bwd_weight(L.ptr(d3), L.ptr(p1), L.ptr(dw5), L.ptr(db5), L.ptr(ws), B, T2, F2, C1, C2,
+        L.check(lib.b200asr_conv3x3_bwd_weight(L.ptr(d3), L.ptr(d3p), L.ptr(p1), L.ptr(dw5), L.ptr(db5), L.ptr(ws), B, T2, F2, C1, C2,
                                                prec_w, st), "conv3_wgrad")
         dp1 = new(B, T2, F2, C1)
-        L.check(lib.b200asr_conv3x3_bwd_data(L.ptr(d3), L.ptr(_f32c(w5)), None, L.ptr(dp1), L.ptr(ws), B, T2, F2, C1, C2,
+        L.check(lib.b200asr_conv3x3_bwd_data(L.ptr(d3), L.ptr(_f32c(w5)), None, L.ptr(dp1), None, L.ptr(ws), B, T2, F2, C1, C2,
                                              prec, st), "conv3_dgrad")
-        del d3
-        d2 = new(B, T, F, C1)
-        L.check(lib.b200asr_maxpool2x2_bwd(L.ptr(dp1), L.ptr(y2), L.ptr(d2), B, T, F, C1, 1, st), "pool1_bwd")
+        del d3, d3p
+        d2, d2p = new(B, T, F, C1), new16(B, T, F, C1)
+        L.check(lib.b200asr_maxpool2x2_bwd(L.ptr(dp1), L.ptr(y2), L.ptr(d2), L.ptr(d2p), B, T, F, C1, 1, st), "pool1_bwd")
         dw2, db2 = torch.empty_like(w2), new(C1)
-        L.check(lib.b200asr_conv3x3_bwd_weight(L.ptr(d2), L.ptr(y1), L.ptr(dw2), L.ptr(db2), L.ptr(ws), B, T, F, C1, C1,
+        L.check(lib.b200asr_conv3x3_bwd_weight(L.ptr(d2), L.ptr(d2p), L.ptr(y1), L.ptr(dw2), L.ptr(db2), L.ptr(ws), B, T, F, C1, C1,
                                                prec_w, st), "conv2_wgrad")
         d1 = new(B, T, F, C1)
-        L.check(lib.b200asr_conv3x3_bwd_data(L.ptr(d2), L.ptr(_f32c(w2)), L.ptr(y1), L.ptr(d1), L.ptr(ws), B, T, F, C1, C1,
+        L.check(lib.b200asr_conv3x3_bwd_data(L.ptr(d2), L.ptr(_f32c(w2)), L.ptr(y1), L.ptr(d1), None, L.ptr(ws), B, T, F, C1, C1,
                                              prec, st), "conv2_dgrad")
-        del d2
+        del d2, d2p
         dw0, db0 = torch.empty_like(w0), new(C1)
         L.check(lib.b200asr_conv3x3_c1_bwd_weight(L.ptr(x), L.ptr(d1), L.ptr(dw0), L.ptr(db0), B, F, T, C1, st), "conv1_wgrad")
         return None, dw0, db0, dw2, db2, dw5, db5, dw7, db7

@@ -195,18 +195,22 @@ int b200asr_conv3x3_c1_bwd_weight(const float* x, const float* dy, float* dw, fl
 /* x [B,T,F,Ci] -> y [B,T,F,Co]; ws: b200asr_conv3x3_ws_bytes(Ci,Co) */
 int b200asr_conv3x3_fwd(const float* x, const float* w, const float* bias, float* y, void* ws, int B, int T,
                         int F, int Ci, int Co, int relu, int precision, b200asr_stream_t stream);
-/* dx[B,T,F,Ci] = conv_transpose(dy) .* (relu_out > 0 if relu_out != NULL) */
-int b200asr_conv3x3_bwd_data(const float* dy, const float* w, const float* relu_out, float* dx, void* ws,
+/* dx[B,T,F,Ci] = conv_transpose(dy) .* (relu_out > 0 if relu_out != NULL).
+ * dx16 (optional, precisions 6 / 2 only): the same gradient additionally as bf16 hi | lo "pairs" [2][B,T,F,Ci] (hi = bf16(v),
+ * lo = bf16(v - hi)) -- what b200asr_conv3x3_bwd_weight of the layer below takes as dy16. */
+int b200asr_conv3x3_bwd_data(const float* dy, const float* w, const float* relu_out, float* dx, void* dx16, void* ws,
                              int B, int T, int F, int Ci, int Co, int precision, b200asr_stream_t stream);
-/* dw[Co,Ci,3,3], dbias[Co] overwritten */
-int b200asr_conv3x3_bwd_weight(const float* dy, const float* x, float* dw, float* dbias, void* ws, int B,
-                               int T, int F, int Ci, int Co, int precision, b200asr_stream_t stream);
+/* dw[Co,Ci,3,3], dbias[Co] overwritten.  dy16 (optional, precisions 6 / 2): dy as bf16 pairs [2][B,T,F,Co] written by its
+ * producer (b200asr_maxpool2x2_bwd / b200asr_conv3x3_bwd_data): the kernel then takes its B tiles straight from there by TMA
+ * instead of converting the fp32 dy tile (the in-kernel conversion is what bounds the bf16 weight gradient). */
+int b200asr_conv3x3_bwd_weight(const float* dy, const void* dy16, const float* x, float* dw, float* dbias, void* ws,
+                               int B, int T, int F, int Ci, int Co, int precision, b200asr_stream_t stream);
 size_t b200asr_conv3x3_ws_bytes(int Ci, int Co);
 /* MaxPool2d(2, stride 2), floor mode: [B,T,F,C] -> [B,T/2,F/2,C] */
 int b200asr_maxpool2x2_fwd(const float* x, float* y, int B, int T, int F, int C, b200asr_stream_t stream);
 /* dx[B,T,F,C] = route dy to the first maximum of each window (scan order freq-major, as ATen), then
  * .* (x > 0) when relu_mask != 0 (x is the post-ReLU pool input). */
-int b200asr_maxpool2x2_bwd(const float* dy, const float* x, float* dx, int B, int T, int F, int C,
+int b200asr_maxpool2x2_bwd(const float* dy, const float* x, float* dx, void* dx16 /* optional bf16 pairs [2][B,T,F,C] */, int B, int T, int F, int C,
                            int relu_mask, b200asr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------

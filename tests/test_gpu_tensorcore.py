@@ -103,7 +103,7 @@ def test_conv3x3_forward_and_dgrad_tensor_core(L, B, T, F_, Ci, Co, prec, tol):
     assert rel_err(y2, y_ref.relu()) < tol
     dx = torch.full((B, T, F_, Ci), float("nan"), device="cuda")
     mask = torch.randn(B, T, F_, Ci, device="cuda")
-    L.check(lib.b200asr_conv3x3_bwd_data(L.ptr(dy), L.ptr(w), L.ptr(mask), L.ptr(dx), L.ptr(ws), B, T, F_, Ci, Co, prec, _stream()), "conv dgrad")
+    L.check(lib.b200asr_conv3x3_bwd_data(L.ptr(dy), L.ptr(w), L.ptr(mask), L.ptr(dx), None, L.ptr(ws), B, T, F_, Ci, Co, prec, _stream()), "conv dgrad")
     assert rel_err(dx, dx_ref.cuda() * (mask > 0)) < tol
 
 
@@ -268,7 +268,7 @@ def test_conv3x3_weight_gradient_tensor_core(L, B, T, F_, Ci, Co, prec, tol):
     ws = torch.empty(lib.b200asr_conv3x3_ws_bytes(Ci, Co) // 4, device="cuda")
     dw = torch.full((Co, Ci, 3, 3), float("nan"), device="cuda")
     db = torch.full((Co,), float("nan"), device="cuda")
-    L.check(lib.b200asr_conv3x3_bwd_weight(L.ptr(dyc), L.ptr(xc), L.ptr(dw), L.ptr(db), L.ptr(ws), B, T, F_, Ci, Co, prec, _stream()), "conv wgrad")
+    L.check(lib.b200asr_conv3x3_bwd_weight(L.ptr(dyc), None, L.ptr(xc), L.ptr(dw), L.ptr(db), L.ptr(ws), B, T, F_, Ci, Co, prec, _stream()), "conv wgrad")
     assert rel_err(dw, dw_ref) < tol
     assert rel_err(db, dy.double().sum((0, 2, 3))) < 1e-5
 

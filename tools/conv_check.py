@@ -34,7 +34,8 @@ for (B, T, Fq, Ci, Co) in [(1, 16, 8, 32, 64), (2, 37, 21, 64, 64), (2, 40, 40, 
         y = torch.empty(B, T, Fq, Co, device="cuda")
         dx = torch.empty(B, T, Fq, Ci, device="cuda")
         rc1 = lib.b200asr_conv3x3_fwd(x.data_ptr(), w.data_ptr(), bias.data_ptr(), y.data_ptr(), ws.data_ptr(), B, T, Fq, Ci, Co, 0, prec, st)
-        rc2 = lib.b200asr_conv3x3_bwd_data(dy.data_ptr(), w.data_ptr(), None, dx.data_ptr(), ws.data_ptr(), B, T, Fq, Ci, Co, prec, st)
+        dx16 = torch.empty(2, B, T, Fq, Ci, device="cuda", dtype=torch.bfloat16) if prec in (2, 6) else None
+        rc2 = lib.b200asr_conv3x3_bwd_data(dy.data_ptr(), w.data_ptr(), None, dx.data_ptr(), dx16.data_ptr() if dx16 is not None else None, ws.data_ptr(), B, T, Fq, Ci, Co, prec, st)
         torch.cuda.synchronize()
         if rc1 or rc2:
             line += f" p{prec}: rc {rc1},{rc2} {L.last_error()[:60]} |"
@@ -42,14 +43,23 @@ for (B, T, Fq, Ci, Co) in [(1, 16, 8, 32, 64), (2, 37, 21, 64, 64), (2, 40, 40, 
         ey = float((y.double() - y64).abs().max() / y64.abs().max())
         ex = float((dx.double() - dx64).abs().max() / dx64.abs().max())
         line += f" p{prec}: fwd {ey:.1e} dgrad {ex:.1e}"
+        if dx16 is not None:
+            line += f" dx16 {float(((dx16[0].double() + dx16[1].double()) - dx64).abs().max() / dx64.abs().max()):.1e}"
         if Ci % 64 == 0:
             dw = torch.empty_like(w)
             db = torch.empty_like(bias)
-            rc3 = lib.b200asr_conv3x3_bwd_weight(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), B, T, Fq, Ci, Co, prec, st)
+            rc3 = lib.b200asr_conv3x3_bwd_weight(dy.data_ptr(), None, x.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), B, T, Fq, Ci, Co, prec, st)
             torch.cuda.synchronize()
             if rc3:
                 line += f" wgrad rc {rc3} {L.last_error()[:50]}"
             else:
                 line += f" wgrad {float((dw.double() - dw64).abs().max() / dw64.abs().max()):.1e} db {float((db.double() - db64).abs().max() / db64.abs().max()):.1e}"
+            if prec in (2, 6):      # the same with dy arriving as bf16 pairs (B tiles by TMA)
+                hi = dy.bfloat16()
+                dy16 = torch.stack([hi, (dy - hi.float()).bfloat16()]).contiguous()
+                dw2 = torch.empty_like(w); db2 = torch.empty_like(bias)
+                rc4 = lib.b200asr_conv3x3_bwd_weight(dy.data_ptr(), dy16.data_ptr(), x.data_ptr(), dw2.data_ptr(), db2.data_ptr(), ws.data_ptr(), B, T, Fq, Ci, Co, prec, st)
+                torch.cuda.synchronize()
+                line += f" pairs: rc {rc4} wgrad {float((dw2.double() - dw64).abs().max() / dw64.abs().max()):.1e} db {float((db2.double() - db64).abs().max() / db64.abs().max()):.1e}"
         line += " |"
     print(line, flush=True)
