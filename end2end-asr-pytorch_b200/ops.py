@@ -43,6 +43,8 @@ class _Config:
         self.conv_wgrad = _PREC_NAMES[os.environ.get("B200ASR_CONV_WGRAD", "tf32x3")]
         self.attn = _PREC_NAMES[os.environ.get("B200ASR_ATTN", "tf32x3")]          # "bf16x3" = the fused single-kernel path (opt-in)
         self.attn_bwd = _PREC_NAMES[os.environ.get("B200ASR_ATTN_BWD", "fp32")]
+        # emb_cnn's second convolution as implicit GEMMs (tc_emb.cu) instead of im2col + GEMM
+        self.emb_implicit = os.environ.get("B200ASR_EMB_IMPLICIT", "0") != "0"
 
     def set(self, linear=None, conv=None, attn=None, conv_wgrad=None, attn_bwd=None):
         if attn_bwd is not None:
@@ -946,7 +948,7 @@ class EmbFrontendFn(torch.autograd.Function):
         new = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
         C = w0.shape[0]
         gemm = config.conv != L.PREC_FP32 and C % 4 == 0
-        implicit = gemm and C == 32 and w3.shape[1] == 32            # tc_emb.cu takes 32 -> 32 channels
+        implicit = gemm and config.emb_implicit and C == 32 and w3.shape[1] == 32            # tc_emb.cu takes 32 -> 32 channels
         H1, W1 = (H - 41) // 2 + 1, (W + 20 - 11) // 2 + 1
         H2, W2 = (H1 - 21) // 2 + 1, (W1 - 11) // 1 + 1
         P1, P2 = ((W1 + 3) // 4 * 4, (W2 + 3) // 4 * 4) if implicit else (W1, W2)      # TMA: 16-byte row pitches
