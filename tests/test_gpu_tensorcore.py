@@ -273,6 +273,38 @@ def test_conv3x3_weight_gradient_tensor_core(L, B, T, F_, Ci, Co, prec, tol):
     assert rel_err(db, dy.double().sum((0, 2, 3))) < 1e-5
 
 
+@pytest.mark.parametrize("prec,tol", [(6, 1e-4), (2, 1e-2)])
+@pytest.mark.parametrize("B,T,F_,Ci,Co", [(2, 16, 32, 64, 64), (1, 9, 21, 64, 128), (3, 24, 41, 128, 128), (2, 10, 23, 128, 64), (1, 40, 161, 64, 64)])
+def test_conv3x3_weight_gradient_bf16_modes_and_pairs(L, B, T, F_, Ci, Co, prec, tol):
+    """kind::f16 weight gradient: (a) dy converted inside the kernel, (b) dy arriving as the bf16 hi | lo pairs its producers
+    write (max-pool backward with the ReLU mask, incl. the odd-F tail) -- B tiles by TMA, bias gradient from the bf16 tiles."""
+    lib = L.load()
+    g = torch.Generator().manual_seed(B * 11 + T)
+    x = torch.randn(B, Ci, F_, T, generator=g)
+    nhwc = lambda t: t.permute(0, 3, 2, 1).contiguous().cuda()
+    # dy = max-pool backward of a random upstream gradient through a random post-ReLU activation (as in the VGG front end)
+    act = torch.randn(B, Co, F_, T, generator=g).relu()
+    up = torch.randn(B, Co, F_ // 2, T // 2, generator=g)
+    a64 = act.double().requires_grad_(True)
+    torch.nn.functional.max_pool2d(a64, 2, 2).backward(up.double())
+    dy = (a64.grad * (act.double() > 0)).float()
+    dyc = torch.full((B, T, F_, Co), float("nan"), device="cuda")
+    dy16 = torch.full((2, B, T, F_, Co), float("nan"), device="cuda", dtype=torch.bfloat16)
+    L.check(lib.b200asr_maxpool2x2_bwd(L.ptr(nhwc(up)), L.ptr(nhwc(act)), L.ptr(dyc), L.ptr(dy16), B, T, F_, Co, 1, _stream()), "pool bwd")
+    assert rel_err(dyc, nhwc(dy)) < 1e-6
+    assert rel_err(dy16[0].float() + dy16[1].float(), nhwc(dy)) < 2e-5          # hi + lo carries 16 significant bits
+    dw_ref = torch.nn.grad.conv2d_weight(x.double(), (Co, Ci, 3, 3), dy.double(), padding=1)
+    xc = nhwc(x)
+    ws = torch.empty(lib.b200asr_conv3x3_ws_bytes(Ci, Co) // 4, device="cuda")
+    for pairs in (None, dy16):
+        dw = torch.full((Co, Ci, 3, 3), float("nan"), device="cuda")
+        db = torch.full((Co,), float("nan"), device="cuda")
+        L.check(lib.b200asr_conv3x3_bwd_weight(L.ptr(dyc), L.ptr(pairs), L.ptr(xc), L.ptr(dw), L.ptr(db), L.ptr(ws), B, T, F_, Ci, Co, prec,
+                                               _stream()), "conv wgrad")
+        assert rel_err(dw, dw_ref) < tol
+        assert rel_err(db, dy.double().sum((0, 2, 3))) < (2e-5 if pairs is not None else 1e-5)
+
+
 @pytest.mark.parametrize("M,N,K", [(300, 512, 512), (130, 4364, 128), (77, 52, 164), (800, 512, 1280)])
 def test_linear_with_presplit_weights(L, M, N, K):
     """3xTF32 GEMM with the weight pre-split once by b200asr_split_tf32 (forward K-major B, data-gradient MN-major B)."""
