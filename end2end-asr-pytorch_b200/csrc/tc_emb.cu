@@ -6,7 +6,7 @@
 //
 //   forward        y[b, :, oh, ow0 + m]  = sum_{kh, kw} sum_ci  x[b, ci, SH*oh + kh, ow0 + m + kw] * w[:, ci, kh, kw]
 //     one k-block = one (kh, kw): the A tile (128 m x 32 ci, MN-major) is ONE strided window of the activation -- 4 TMA
-//     boxes {32 w, 1 h, 32 c} at (ow0 + kw, SH*oh + kh) -- and the B tile the 32 x 32 weight slice of that tap (K-major,
+//     boxes {32 w, 32 c} of the (w, c, h, b) view at (ow0 + kw, 0, SH*oh + kh) -- and the B tile the 32 x 32 weight slice of that tap (K-major,
 //     pre-converted: bf16 hi | lo for the kind::f16 modes, tf32 hi | lo for 3xTF32).
 //   data gradient  dx[b, :, h, w0 + m]   = sum_{kh == h (mod SH), kw} sum_co  dy[b, co, (h - kh) / SH, w0 + m - kw] * w[co, :, kh, kw]
 //     the same kernel: a gather over the taps whose row parity matches h; boxes that reach outside dy are zero-filled by TMA.
@@ -17,6 +17,12 @@
 // MMA N = 32 (the layer has 32 output channels); the engine's conversion warps turn the fp32 A tile into the tensor-memory
 // operand exactly as for the other policies.  TMA needs 16-byte row pitches, so the NCHW tensors these kernels touch are
 // PITCHED: rows of `pitch` floats (a multiple of 4) of which the first W are valid (W = 205 / 195 at cfg3).
+//
+// TMA also needs the INNERMOST start coordinate of a box to be 16-byte aligned (UTMALDG raises an illegal-instruction
+// fault otherwise -- measured), and the windows above start at ow0 + kw for every kw.  So the tensor whose windows slide
+// (x for forward / weight gradient, dy for the data gradient) is first written as FOUR copies shifted right by s = 0..3
+// floats (copy_s[w'] = src[w' - s], zeros outside: one HBM-bound pass, 5x the activation, against the 231x of an im2col
+// matrix); the window that starts at column v is then the box at v + s of copy s = (-v) mod 4, an aligned coordinate.
 #include "../../include/b200asr.h"
 #include "common.cuh"
 #include "kernels.h"
@@ -73,10 +79,11 @@ struct EmbConvPolicy {
     return nkh * p.e.g.KW;
   }
   static __device__ __forceinline__ void load_a(const Params& p, const Tile& t, const CUtensorMap* mapA, uint32_t sa, uint32_t bar) {
-    const int w = DGRAD ? t.w0 - t.kw : t.w0 + t.kw;
+    const int w = DGRAD ? t.w0 - t.kw : t.w0 + t.kw;                   // window start; copy s = (-w) mod 4 holds it at w + s
+    const int s = (-w) & 3;
     const int h = DGRAD ? (t.r - t.kh) / p.e.g.SH : t.r * p.e.g.SH + t.kh;
 #pragma unroll
-    for (int c = 0; c < 4; c++) tma_load_4d(sa + c * 4096, mapA, bar, w + 32 * c, h, 0, t.b);
+    for (int c = 0; c < 4; c++) tma_load_4d(sa + c * 4096, mapA, bar, w + s + 32 * c, 0, h, s * p.e.g.B + t.b);
   }
   static __device__ __forceinline__ void advance(const Params& p, Tile& t) {
     if (++t.kw == p.e.g.KW) { t.kw = 0; t.kh += DGRAD ? p.e.g.SH : 1; }
@@ -153,9 +160,10 @@ struct EmbWgradPolicy {
       for (int j = 0; j < 4; j++) {
         const int kw = t.mt * 4 + j;
         // taps beyond KW: a box at channel coordinate 32 is entirely out of bounds -> zero rows, same byte count
-        tma_load_4d(sa + j * 4096, mapX, bar, ow0 + kw, p.e.g.SH * oh + t.kh, kw < p.e.g.KW ? 0 : EC, b);
+        const int s = (-kw) & 3;                                        // shifted copy that holds column ow0 + kw at an aligned coordinate
+        tma_load_4d(sa + j * 4096, mapX, bar, ow0 + kw + s, kw < p.e.g.KW ? 0 : EC, p.e.g.SH * oh + t.kh, s * p.e.g.B + b);
       }
-      tma_load_4d(sb, mapDy, bar, ow0, oh, 0, b);
+      tma_load_4d(sb, mapDy, bar, ow0, 0, oh, b);
     }
     if (++t.ob == p.e.owb) { t.ob = 0; t.row++; }
   }
@@ -215,10 +223,42 @@ __global__ void emb_bias_grad_kernel(const float* __restrict__ dy, float* __rest
   }
 }
 
-static int nchw_map(CUtensorMap* m, const float* base, int W, int P, int H, int B, bool atom32) {
-  uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)EC, (uint64_t)B};
-  uint64_t strides[3] = {(uint64_t)P, (uint64_t)H * P, (uint64_t)EC * H * P};
-  uint32_t box[4] = {32, 1, EC, 1};
+// rows [R][Ps] (first W valid) -> four copies [4][R][Pd], copy s shifted right by s floats, zeros elsewhere
+__global__ void emb_shift4_kernel(const float* __restrict__ src, float* __restrict__ dst, long long R, int W, int Ps, int Pd) {
+  const int q = Pd / 4;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * q) return;
+  const long long row = i / q;
+  const int w0 = (int)(i % q) * 4;
+  const float* in = src + row * Ps;
+  float v[7];
+#pragma unroll
+  for (int j = 0; j < 7; j++) {
+    const int w = w0 - 3 + j;
+    v[j] = (w >= 0 && w < W) ? __ldg(in + w) : 0.f;
+  }
+#pragma unroll
+  for (int s = 0; s < 4; s++)
+    *reinterpret_cast<float4*>(dst + ((size_t)s * R + row) * Pd + w0) = make_float4(v[3 - s], v[4 - s], v[5 - s], v[6 - s]);
+}
+
+static inline int shift_pitch(int W) { return (W + 3 + 3) / 4 * 4; }
+static inline size_t shift_floats(int B, int H, int W) { return (size_t)4 * B * EC * H * shift_pitch(W); }
+static inline size_t weight_floats(int KH, int KW) { return ((size_t)2 * KH * KW * EC * EC + 255) / 256 * 256; }
+
+static int make_shifted(const float* src, float* dst, int B, int H, int W, int P, cudaStream_t st) {
+  const long long R = (long long)B * EC * H, n = R * (shift_pitch(W) / 4);
+  emb_shift4_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, st>>>(src, dst, R, W, P, shift_pitch(W));
+  note_launch(1);
+  return check_launch("conv2d_tc_shift4");
+}
+
+// [N, 32, H, .] (row pitch P, W valid columns) seen as the 4-D tensor (w, c, h, n): a box {32 w, 32 c, 1, 1} is one 32 x 32
+// window of a row across all channels.  For the shifted copies N = 4 * B (index s * B + b) and every column is valid.
+static int nchw_map(CUtensorMap* m, const float* base, int W, int P, int H, int N, bool atom32) {
+  uint64_t dims[4] = {(uint64_t)W, (uint64_t)EC, (uint64_t)H, (uint64_t)N};
+  uint64_t strides[3] = {(uint64_t)H * P, (uint64_t)P, (uint64_t)EC * H * P};
+  uint32_t box[4] = {32, EC, 1, 1};
   return make_tensor_map_f32(m, base, 4, dims, strides, box, atom32, false);
 }
 
@@ -250,7 +290,10 @@ using namespace b200asr::tc;
 
 extern "C" {
 
-size_t b200asr_conv2d_tc_ws_bytes(int KH, int KW) { return sizeof(float) * 2 * (size_t)KH * KW * EC * EC; }
+size_t b200asr_conv2d_tc_ws_bytes(int B, int H, int W, int KH, int KW) {
+  if (B <= 0 || H <= 0 || W <= 0 || KH <= 0 || KW <= 0) return 0;
+  return sizeof(float) * (weight_floats(KH, KW) + shift_floats(B, H, W));        // x copies >= dy copies
+}
 
 int b200asr_conv2d_tc_fwd(const float* x, const float* w, const float* bias, float* y, void* ws, int B, int Ci, int H, int W, int Co,
                           int KH, int KW, int SH, int x_pitch, int y_pitch, int precision, b200asr_stream_t stream) {
@@ -264,7 +307,9 @@ int b200asr_conv2d_tc_fwd(const float* x, const float* w, const float* bias, flo
   emb_repack_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, ws, KH, KW, 0, precision);
   note_launch(1);
   CUtensorMap ma, mb;
-  if (int rc = nchw_map(&ma, x, W, x_pitch, H, B, true)) return rc;
+  float* xs = (float*)ws + weight_floats(KH, KW);
+  if (int rc = make_shifted(x, xs, B, H, W, x_pitch, st)) return rc;
+  if (int rc = nchw_map(&ma, xs, shift_pitch(W), shift_pitch(W), H, 4 * B, true)) return rc;
   {
     uint64_t dims[2] = {(uint64_t)EC, (uint64_t)(precision == 2 ? 1 : 2) * KH * KW * EC}, strides[1] = {(uint64_t)EC};
     uint32_t box[2] = {EC, EC};
@@ -287,7 +332,9 @@ int b200asr_conv2d_tc_bwd_data(const float* dy, const float* w, float* dx, void*
   emb_repack_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, ws, KH, KW, 1, precision);
   note_launch(1);
   CUtensorMap ma, mb;
-  if (int rc = nchw_map(&ma, dy, g.OW, y_pitch, g.OH, B, true)) return rc;
+  float* dys = (float*)ws + weight_floats(KH, KW);
+  if (int rc = make_shifted(dy, dys, B, g.OH, g.OW, y_pitch, st)) return rc;
+  if (int rc = nchw_map(&ma, dys, shift_pitch(g.OW), shift_pitch(g.OW), g.OH, 4 * B, true)) return rc;
   {
     uint64_t dims[2] = {(uint64_t)EC, (uint64_t)(precision == 2 ? 1 : 2) * KH * KW * EC}, strides[1] = {(uint64_t)EC};
     uint32_t box[2] = {EC, EC};
@@ -298,16 +345,18 @@ int b200asr_conv2d_tc_bwd_data(const float* dy, const float* w, float* dx, void*
   return launch_emb_conv<true>(ma, mb, e, precision, st);
 }
 
-int b200asr_conv2d_tc_bwd_weight(const float* dy, const float* x, float* dw, float* dbias, int B, int Ci, int H, int W, int Co, int KH,
-                                 int KW, int SH, int x_pitch, int y_pitch, b200asr_stream_t stream) {
-  B200_REQUIRE(dy && x && dw, B200ASR_BAD_ARG, "conv2d_tc_bwd_weight: null pointer");
+int b200asr_conv2d_tc_bwd_weight(const float* dy, const float* x, float* dw, float* dbias, void* ws, int B, int Ci, int H, int W, int Co,
+                                 int KH, int KW, int SH, int x_pitch, int y_pitch, b200asr_stream_t stream) {
+  B200_REQUIRE(dy && x && dw && ws, B200ASR_BAD_ARG, "conv2d_tc_bwd_weight: null pointer");
   EmbG g;
   if (int rc = emb_geom(g, "conv2d_tc_bwd_weight", B, Ci, H, W, Co, KH, KW, SH, x_pitch, y_pitch)) return rc;
-  B200_REQUIRE(aligned16(dy) && aligned16(x), B200ASR_BAD_ALIGN, "conv2d_tc_bwd_weight: alignment");
+  B200_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(ws), B200ASR_BAD_ALIGN, "conv2d_tc_bwd_weight: alignment");
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)EC * EC * KH * KW, st);
   CUtensorMap mx, mdy;
-  if (int rc = nchw_map(&mx, x, W, x_pitch, H, B, false)) return rc;          // K-major tiles: plain 128B swizzle
+  float* xs = (float*)ws + weight_floats(KH, KW);
+  if (int rc = make_shifted(x, xs, B, H, W, x_pitch, st)) return rc;
+  if (int rc = nchw_map(&mx, xs, shift_pitch(W), shift_pitch(W), H, 4 * B, false)) return rc;          // K-major tiles: plain 128B swizzle
   if (int rc = nchw_map(&mdy, dy, g.OW, y_pitch, g.OH, B, false)) return rc;
   EmbWgP e{dw, g, ceil_div(KW, 4), 1, B * g.OH, ceil_div(g.OW, 32)};
   const int base = KH * e.m_tiles, rows = B * g.OH;

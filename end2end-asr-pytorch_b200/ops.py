@@ -966,7 +966,7 @@ class EmbFrontendFn(torch.autograd.Function):
         c2 = new(B, C, H2, P2)
         if implicit:
             prec2 = config.conv if config.conv in (L.PREC_TF32X3, L.PREC_BF16X3, L.PREC_BF16) else L.PREC_TF32X3
-            ws = torch.empty(lib.b200asr_conv2d_tc_ws_bytes(21, 11) // 4, device=dev, dtype=torch.float32)
+            ws = torch.empty(lib.b200asr_conv2d_tc_ws_bytes(B, H1, W1, 21, 11) // 4, device=dev, dtype=torch.float32)
             L.check(lib.b200asr_conv2d_tc_fwd(L.ptr(a1), L.ptr(_f32c(w3)), L.ptr(b3), L.ptr(c2), L.ptr(ws), B, C, H1, W1, C, 21, 11, 2,
                                               P1, P2, prec2, st), "emb_conv2_tc")
         elif gemm:
@@ -1010,10 +1010,10 @@ class EmbFrontendFn(torch.autograd.Function):
         da1 = new(B, C, H1, P1)
         if implicit:
             dw3, db3 = torch.empty_like(w3), new(C)
-            L.check(lib.b200asr_conv2d_tc_bwd_weight(L.ptr(dc2), L.ptr(a1), L.ptr(dw3), L.ptr(db3), B, C, H1, W1, C, 21, 11, 2, P1, P2, st),
+            ws = torch.empty(lib.b200asr_conv2d_tc_ws_bytes(B, H1, W1, 21, 11) // 4, device=dev, dtype=torch.float32)
+            L.check(lib.b200asr_conv2d_tc_bwd_weight(L.ptr(dc2), L.ptr(a1), L.ptr(dw3), L.ptr(db3), L.ptr(ws), B, C, H1, W1, C, 21, 11, 2, P1, P2, st),
                     "emb_conv2_tc_wgrad")
             prec2 = prec if prec in (L.PREC_TF32X3, L.PREC_BF16X3, L.PREC_BF16) else L.PREC_TF32X3
-            ws = torch.empty(lib.b200asr_conv2d_tc_ws_bytes(21, 11) // 4, device=dev, dtype=torch.float32)
             L.check(lib.b200asr_conv2d_tc_bwd_data(L.ptr(dc2), L.ptr(_f32c(w3)), L.ptr(da1), L.ptr(ws), B, C, H1, W1, C, 21, 11, 2, P1, P2,
                                                    prec2, st), "emb_conv2_tc_dgrad")
         elif gemm:

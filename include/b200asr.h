@@ -242,16 +242,19 @@ int b200asr_bn_clamp_bwd(const float* dy, const float* x, const float* y, const 
  * implicit GEMMs on tcgen05 -- no im2col matrix.  x / dx [B,32,H,W] with row pitch x_pitch, y / dy [B,32,OH,OW] with row
  * pitch y_pitch (floats, multiples of 4: TMA); w [32,32,KH,KW].  precision 6 (bf16x3), 3 (3xTF32) or 2 (bf16) for forward
  * and data gradient; the weight gradient runs 3xTF32 and accumulates with atomics (dw is zeroed here).
- * ws: b200asr_conv2d_tc_ws_bytes(KH, KW) bytes (the repacked weight slices). */
-size_t b200asr_conv2d_tc_ws_bytes(int KH, int KW);
+ * ws: b200asr_conv2d_tc_ws_bytes(B, H, W, KH, KW) bytes -- the repacked weight slices, and four copies of the tensor whose
+ * windows slide (x, or dy for the data gradient) shifted by 0..3 floats, because a TMA box must start on a 16-byte
+ * boundary; each call rebuilds what it needs (one HBM-bound pass), so the same buffer may serve all three. */
+size_t b200asr_conv2d_tc_ws_bytes(int B, int H, int W, int KH, int KW);
 int b200asr_conv2d_tc_fwd(const float* x, const float* w, const float* bias, float* y, void* ws, int B, int Ci, int H,
                           int W, int Co, int KH, int KW, int SH, int x_pitch, int y_pitch, int precision,
                           b200asr_stream_t stream);
 int b200asr_conv2d_tc_bwd_data(const float* dy, const float* w, float* dx, void* ws, int B, int Ci, int H, int W, int Co,
                                int KH, int KW, int SH, int x_pitch, int y_pitch, int precision,
                                b200asr_stream_t stream);
-int b200asr_conv2d_tc_bwd_weight(const float* dy, const float* x, float* dw, float* dbias, int B, int Ci, int H, int W,
-                                 int Co, int KH, int KW, int SH, int x_pitch, int y_pitch, b200asr_stream_t stream);
+int b200asr_conv2d_tc_bwd_weight(const float* dy, const float* x, float* dw, float* dbias, void* ws, int B, int Ci, int H,
+                                 int W, int Co, int KH, int KW, int SH, int x_pitch, int y_pitch,
+                                 b200asr_stream_t stream);
 /* x [B,C,F,T] -> y [B,T,C*F] and its inverse (gradient) */
 int b200asr_flatten_bcft_fwd(const float* x, float* y, int B, int C, int F, int T, b200asr_stream_t stream);
 int b200asr_flatten_bcft_bwd(const float* dy, float* dx, int B, int C, int F, int T, b200asr_stream_t stream);

@@ -348,7 +348,7 @@ def test_conv2d_implicit_gemm_32ch(L, B, H, W, KH, KW, SH, prec, tol):
     dypad = torch.full((B, 32, OH, yp), float("nan"), device="cuda"); dypad[..., :OW] = dy
     ypad = torch.full((B, 32, OH, yp), float("nan"), device="cuda")
     dxpad = torch.full((B, 32, H, xp), float("nan"), device="cuda")
-    ws = torch.empty(lib.b200asr_conv2d_tc_ws_bytes(KH, KW) // 4, device="cuda")
+    ws = torch.empty(lib.b200asr_conv2d_tc_ws_bytes(B, H, W, KH, KW) // 4, device="cuda")
     L.check(lib.b200asr_conv2d_tc_fwd(L.ptr(xpad), L.ptr(w), L.ptr(b), L.ptr(ypad), L.ptr(ws), B, 32, H, W, 32, KH, KW, SH, xp, yp, prec, st), "fwd")
     assert rel_err(ypad[..., :OW], y64) < tol
     L.check(lib.b200asr_conv2d_tc_bwd_data(L.ptr(dypad), L.ptr(w), L.ptr(dxpad), L.ptr(ws), B, 32, H, W, 32, KH, KW, SH, xp, yp, prec, st), "dgrad")
@@ -356,6 +356,6 @@ def test_conv2d_implicit_gemm_32ch(L, B, H, W, KH, KW, SH, prec, tol):
     if prec == 3:
         dw = torch.empty_like(w)
         db = torch.empty(32, device="cuda")
-        L.check(lib.b200asr_conv2d_tc_bwd_weight(L.ptr(dypad), L.ptr(xpad), L.ptr(dw), L.ptr(db), B, 32, H, W, 32, KH, KW, SH, xp, yp, st), "wgrad")
+        L.check(lib.b200asr_conv2d_tc_bwd_weight(L.ptr(dypad), L.ptr(xpad), L.ptr(dw), L.ptr(db), L.ptr(ws), B, 32, H, W, 32, KH, KW, SH, xp, yp, st), "wgrad")
         assert rel_err(dw, w64.grad) < tol
         assert rel_err(db, dy.double().sum((0, 2, 3))) < 1e-5
