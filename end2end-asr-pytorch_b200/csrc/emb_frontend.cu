@@ -138,28 +138,69 @@ struct BnIdx {
   }
 };
 
+// Grid = (BN_SPLITS x C): the B*H rows of a channel are cut into BN_SPLITS contiguous ranges, one block each (32 channels
+// alone would leave 116 of the 148 SMs idle).  Pass 1 writes one partial per block -- (count, mean, M2) of its range, each
+// from a two-pass sum inside the block; pass 2 merges the partials of its channel (Chan et al.'s pairwise update, fixed
+// order => deterministic), and applies.  ws: [C][BN_SPLITS][4] floats.
+constexpr int BN_SPLITS = 32;
+
+struct BnRange { int r0, r1; };
+__device__ __forceinline__ BnRange bn_range(int rows) {
+  const int per = (rows + BN_SPLITS - 1) / BN_SPLITS;
+  const int r0 = min(rows, (int)blockIdx.x * per);
+  return BnRange{r0, min(rows, r0 + per)};
+}
+
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, float* __restrict__ ws, BnIdx g, int xp) {
+  __shared__ float red[8];
+  const int c = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const BnRange rr = bn_range(g.B * g.H);
+  const float cnt = (float)(rr.r1 - rr.r0) * (float)g.W;
+  float s = 0.f;
+  for (int r = rr.r0 + warp; r < rr.r1; r += 8)
+    for (int w = lane; w < g.W; w += 32) s += x[g.at(r, w, c, xp)];
+  const float mean = cnt > 0.f ? block_sum256(s, red) / cnt : 0.f;
+  float q = 0.f;
+  for (int r = rr.r0 + warp; r < rr.r1; r += 8)                   // the block's range was just read: L1 / L2 hits
+    for (int w = lane; w < g.W; w += 32) { const float d = x[g.at(r, w, c, xp)] - mean; q += d * d; }
+  q = block_sum256(q, red);
+  if (threadIdx.x == 0) {
+    float* o = ws + ((size_t)c * BN_SPLITS + blockIdx.x) * 4;
+    o[0] = cnt; o[1] = mean; o[2] = q;
+  }
+}
+
+// merge the BN_SPLITS partials of channel c (every thread computes the same values)
+__device__ __forceinline__ void bn_merge(const float* __restrict__ ws, int c, float& mean, float& var) {
+  float n = 0.f, m = 0.f, M2 = 0.f;
+  for (int s = 0; s < BN_SPLITS; s++) {
+    const float* o = ws + ((size_t)c * BN_SPLITS + s) * 4;
+    const float nb = o[0];
+    if (nb <= 0.f) continue;
+    const float d = o[1] - m, nn = n + nb;
+    m += d * (nb / nn);
+    M2 += o[2] + d * d * (n * nb / nn);
+    n = nn;
+  }
+  mean = m;
+  var = n > 0.f ? M2 / n : 0.f;
+}
+
 __global__ void __launch_bounds__(256) bn_clamp_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float* __restrict__ y,
                                                            float* __restrict__ mean_out, float* __restrict__ invstd_out,
                                                            float* __restrict__ running_mean, float* __restrict__ running_var,
-                                                           long long* __restrict__ num_batches, BnIdx g, int xp, int yp, float eps,
-                                                           float momentum, int training, float lo, float hi) {
-  __shared__ float red[8];
-  const int c = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+                                                           long long* __restrict__ num_batches, const float* __restrict__ ws, BnIdx g,
+                                                           int xp, int yp, float eps, float momentum, int training, float lo, float hi) {
+  const int c = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows = g.B * g.H;
   const long long n = (long long)rows * g.W;
   float mean, invstd;
   if (training) {
-    float s = 0.f;
-    for (int r = warp; r < rows; r += 8)
-      for (int w = lane; w < g.W; w += 32) s += x[g.at(r, w, c, xp)];
-    mean = block_sum256(s, red) / (float)n;
-    float q = 0.f;
-    for (int r = warp; r < rows; r += 8)
-      for (int w = lane; w < g.W; w += 32) { const float d = x[g.at(r, w, c, xp)] - mean; q += d * d; }
-    const float var = block_sum256(q, red) / (float)n;
+    float var;
+    bn_merge(ws, c, mean, var);
     invstd = rsqrtf(var + eps);
-    if (threadIdx.x == 0 && running_mean && running_var) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && running_mean && running_var) {
       running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
       const float unbiased = n > 1 ? var * ((float)n / (float)(n - 1)) : var;
       running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
@@ -169,27 +210,27 @@ __global__ void __launch_bounds__(256) bn_clamp_fwd_kernel(const float* __restri
     mean = running_mean[c];
     invstd = rsqrtf(running_var[c] + eps);
   }
-  if (threadIdx.x == 0) { mean_out[c] = mean; invstd_out[c] = invstd; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { mean_out[c] = mean; invstd_out[c] = invstd; }
   const float ga = gamma[c], be = beta[c];
-  for (int r = warp; r < rows; r += 8)
+  const BnRange rr = bn_range(rows);
+  for (int r = rr.r0 + warp; r < rr.r1; r += 8)
     for (int w = lane; w < g.W; w += 32) {
       const float v = (x[g.at(r, w, c, xp)] - mean) * invstd * ga + be;
       y[g.at(r, w, c, yp)] = fminf(fmaxf(v, lo), hi);
     }
 }
 
-__global__ void __launch_bounds__(256) bn_clamp_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                                           const float* __restrict__ y, const float* __restrict__ gamma,
-                                                           const float* __restrict__ mean_in, const float* __restrict__ invstd_in,
-                                                           float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                           BnIdx g, int dyp, int xp, int yp, int dxp, int training, float lo, float hi) {
+// backward pass 1: per-block partial sums of g = dy * [lo < y < hi] and g * xhat
+__global__ void __launch_bounds__(256) bn_bwd_sums_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                          const float* __restrict__ y, const float* __restrict__ mean_in,
+                                                          const float* __restrict__ invstd_in, float* __restrict__ ws, BnIdx g, int dyp,
+                                                          int xp, int yp, float lo, float hi) {
   __shared__ float red[8];
-  const int c = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rows = g.B * g.H;
-  const long long n = (long long)rows * g.W;
-  const float mean = mean_in[c], invstd = invstd_in[c], ga = gamma[c];
+  const int c = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float mean = mean_in[c], invstd = invstd_in[c];
+  const BnRange rr = bn_range(g.B * g.H);
   float s1 = 0.f, s2 = 0.f;
-  for (int r = warp; r < rows; r += 8)
+  for (int r = rr.r0 + warp; r < rr.r1; r += 8)
     for (int w = lane; w < g.W; w += 32) {
       const float yv = y[g.at(r, w, c, yp)];
       const float gg = (yv > lo && yv < hi) ? dy[g.at(r, w, c, dyp)] : 0.f;
@@ -198,9 +239,31 @@ __global__ void __launch_bounds__(256) bn_clamp_bwd_kernel(const float* __restri
     }
   s1 = block_sum256(s1, red);
   s2 = block_sum256(s2, red);
-  if (threadIdx.x == 0) { dbeta[c] = s1; dgamma[c] = s2; }
+  if (threadIdx.x == 0) {
+    float* o = ws + ((size_t)c * BN_SPLITS + blockIdx.x) * 4;
+    o[0] = s1; o[1] = s2;
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_clamp_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                           const float* __restrict__ y, const float* __restrict__ gamma,
+                                                           const float* __restrict__ mean_in, const float* __restrict__ invstd_in,
+                                                           float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                           const float* __restrict__ ws, BnIdx g, int dyp, int xp, int yp, int dxp,
+                                                           int training, float lo, float hi) {
+  const int c = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows = g.B * g.H;
+  const long long n = (long long)rows * g.W;
+  const float mean = mean_in[c], invstd = invstd_in[c], ga = gamma[c];
+  float s1 = 0.f, s2 = 0.f;
+  for (int s = 0; s < BN_SPLITS; s++) {                          // fixed order: deterministic
+    const float* o = ws + ((size_t)c * BN_SPLITS + s) * 4;
+    s1 += o[0]; s2 += o[1];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { dbeta[c] = s1; dgamma[c] = s2; }
   const float inv_n = training ? 1.f / (float)n : 0.f;      // eval mode: the statistics are constants of the graph
-  for (int r = warp; r < rows; r += 8)
+  const BnRange rr = bn_range(rows);
+  for (int r = rr.r0 + warp; r < rr.r1; r += 8)
     for (int w = lane; w < g.W; w += 32) {
       const float yv = y[g.at(r, w, c, yp)];
       const float gg = (yv > lo && yv < hi) ? dy[g.at(r, w, c, dyp)] : 0.f;
@@ -373,26 +436,40 @@ int b200asr_transpose_cp(const float* src, float* dst, int B, int C, int P, int 
   return check_launch("transpose_cp");
 }
 
+size_t b200asr_bn_ws_bytes(int C) { return C > 0 ? sizeof(float) * 4 * BN_SPLITS * (size_t)C : 0; }
+
 int b200asr_bn_clamp_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* invstd,
-                         float* running_mean, float* running_var, long long* num_batches_tracked, int B, int C, int H, int W,
-                         int x_pitch, int y_pitch, float eps, float momentum, int training, float lo, float hi,
+                         float* running_mean, float* running_var, long long* num_batches_tracked, float* ws, int B, int C, int H,
+                         int W, int x_pitch, int y_pitch, float eps, float momentum, int training, float lo, float hi,
                          b200asr_stream_t stream) {
-  B200_REQUIRE(x && gamma && beta && y && mean && invstd && B > 0 && C > 0 && H > 0 && W > 0 && x_pitch >= W && y_pitch >= W,
+  B200_REQUIRE(x && gamma && beta && y && mean && invstd && ws && B > 0 && C > 0 && H > 0 && W > 0 && x_pitch >= W && y_pitch >= W,
                B200ASR_BAD_ARG, "bn_clamp_fwd: bad arguments");
+  B200_REQUIRE(C <= 65535, B200ASR_BAD_SHAPE, "bn_clamp_fwd: at most 65535 channels");
   B200_REQUIRE(training || (running_mean && running_var), B200ASR_BAD_ARG, "bn_clamp_fwd: eval mode needs the running statistics");
-  bn_clamp_fwd_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, y, mean, invstd, running_mean, running_var,
-                                                           num_batches_tracked, BnIdx{B, C, H, W}, x_pitch, y_pitch, eps, momentum,
-                                                           training, lo, hi);
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 grid(BN_SPLITS, C);
+  if (training) {
+    bn_stats_kernel<<<grid, 256, 0, st>>>(x, ws, BnIdx{B, C, H, W}, x_pitch);
+    note_launch(1);
+  }
+  bn_clamp_fwd_kernel<<<grid, 256, 0, st>>>(x, gamma, beta, y, mean, invstd, running_mean, running_var, num_batches_tracked, ws,
+                                            BnIdx{B, C, H, W}, x_pitch, y_pitch, eps, momentum, training, lo, hi);
   return check_launch("bn_clamp_fwd");
 }
 
 int b200asr_bn_clamp_bwd(const float* dy, const float* x, const float* y, const float* gamma, const float* mean,
-                         const float* invstd, float* dx, float* dgamma, float* dbeta, int B, int C, int H, int W, int dy_pitch,
-                         int x_pitch, int y_pitch, int dx_pitch, int training, float lo, float hi, b200asr_stream_t stream) {
-  B200_REQUIRE(dy && x && y && gamma && mean && invstd && dx && dgamma && dbeta, B200ASR_BAD_ARG, "bn_clamp_bwd: null pointer");
+                         const float* invstd, float* dx, float* dgamma, float* dbeta, float* ws, int B, int C, int H, int W,
+                         int dy_pitch, int x_pitch, int y_pitch, int dx_pitch, int training, float lo, float hi,
+                         b200asr_stream_t stream) {
+  B200_REQUIRE(dy && x && y && gamma && mean && invstd && dx && dgamma && dbeta && ws, B200ASR_BAD_ARG, "bn_clamp_bwd: null pointer");
   B200_REQUIRE(dy_pitch >= W && x_pitch >= W && y_pitch >= W && dx_pitch >= W, B200ASR_BAD_ARG, "bn_clamp_bwd: row pitches must cover W");
-  bn_clamp_bwd_kernel<<<C, 256, 0, (cudaStream_t)stream>>>(dy, x, y, gamma, mean, invstd, dx, dgamma, dbeta, BnIdx{B, C, H, W}, dy_pitch,
-                                                           x_pitch, y_pitch, dx_pitch, training, lo, hi);
+  B200_REQUIRE(C <= 65535, B200ASR_BAD_SHAPE, "bn_clamp_bwd: at most 65535 channels");
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 grid(BN_SPLITS, C);
+  bn_bwd_sums_kernel<<<grid, 256, 0, st>>>(dy, x, y, mean, invstd, ws, BnIdx{B, C, H, W}, dy_pitch, x_pitch, y_pitch, lo, hi);
+  note_launch(1);
+  bn_clamp_bwd_kernel<<<grid, 256, 0, st>>>(dy, x, y, gamma, mean, invstd, dx, dgamma, dbeta, ws, BnIdx{B, C, H, W}, dy_pitch, x_pitch,
+                                            y_pitch, dx_pitch, training, lo, hi);
   return check_launch("bn_clamp_bwd");
 }
 

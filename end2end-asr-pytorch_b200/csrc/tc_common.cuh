@@ -193,7 +193,20 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
 // like the tf32 split: bf16(x) = top 16 bits of (bits(x) + 0x8000).
 // pack2(a, b): 32-bit word with bf16(a) in the low half (element k) and bf16(b) in the high half (element k + 1) -- the
 // order in which a TMEM column holds two consecutive-k elements of a 16-bit A operand.
+#ifndef B200ASR_SPLIT_F2FP
+#define B200ASR_SPLIT_F2FP 0
+#endif
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo_elem, float hi_elem) {     // one F2FP: {hi_elem, lo_elem} -> packed bf16x2 (RN)
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_elem), "f"(lo_elem));
+  return d;
+}
 __device__ __forceinline__ void split_bf16_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+#if B200ASR_SPLIT_F2FP
+  hi = cvt_bf16x2(x0, x1);
+  lo = cvt_bf16x2(x0 - __uint_as_float(hi << 16), x1 - __uint_as_float(hi & 0xFFFF0000u));
+  return;
+#endif
   const uint32_t r0 = __float_as_uint(x0) + 0x8000u, r1 = __float_as_uint(x1) + 0x8000u;
   hi = __byte_perm(r0, r1, 0x7632);
   const float l0 = x0 - __uint_as_float(r0 & 0xFFFF0000u), l1 = x1 - __uint_as_float(r1 & 0xFFFF0000u);

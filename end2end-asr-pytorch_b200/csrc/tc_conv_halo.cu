@@ -48,6 +48,10 @@ struct HaloP {
 // warps convert the fp32 patch to bf16 and pack two channels per TMEM column.
 template <int BN, int MODE> struct HaloCfg {
   static constexpr bool kBf16 = MODE != 3;
+#ifndef HALO_CONVERT_ONCE
+#define HALO_CONVERT_ONCE 1
+#endif
+  static constexpr bool kOnce = kBf16 && HALO_CONVERT_ONCE;      // convert each patch once per slice, in place (see the split warps)
   static constexpr int kHalves = MODE == 2 ? 1 : 2;
   static constexpr int kBBytes = BN * (kBf16 ? 64 : 128);
   static constexpr int kACols = MODE == 3 ? 64 : (MODE == 6 ? 32 : 16);        // TMEM columns of A (hi | lo) per stage
@@ -289,14 +293,48 @@ tc_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
       const int pr = prow0 + (tap % 3) * HPF + tap / 3;     // tap = 3 * (df + 1) + (dt + 1)
       const uint8_t* prow = patch + pr * 128;
 #pragma unroll
-      for (int j = 0; j < 8; j++) x[j] = *reinterpret_cast<const float4*>(prow + ((j ^ (pr & 7)) << 4));   // 128B swizzle of the TMA box
+      for (int j = 0; j < (Cfg::kOnce ? 4 * Cfg::kHalves : 8); j++)                                          // 128B swizzle of the TMA box
+        x[j] = *reinterpret_cast<const float4*>(prow + ((j ^ (pr & 7)) << 4));
+    };
+    // kind::f16 modes: every patch pixel is converted ONCE per slice, in place -- its 128-byte row (32 fp32 channels) becomes
+    // 16 words of packed bf16 hi (chunks 0-3) and 16 words of packed bf16 lo (chunks 4-7), same chunk swizzle -- instead of
+    // once per tap by whichever thread maps to it: 180 conversions per slice instead of 9 x 128, and a tap is then eight
+    // LDS.128 and two tcgen05.st.  (ncu on the per-tap version: the split warps were issue-bound on the conversion ALU work,
+    // tensor pipe 39 % at Cout = 64.)
+    const int ctid = threadIdx.x - 192;              // 0 .. HALO_SPLIT-1 over all split warps
+    auto convert_patch = [&](uint8_t* patch) {
+      for (int pr = ctid; pr < HPT * HPF; pr += HALO_SPLIT) {
+        uint8_t* prow = patch + pr * 128;
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = *reinterpret_cast<const float4*>(prow + ((j ^ (pr & 7)) << 4));
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          if constexpr (MODE == 6) {
+            split_bf16_pair(v[j].x, v[j].y, hi[2 * j], lo[2 * j]);
+            split_bf16_pair(v[j].z, v[j].w, hi[2 * j + 1], lo[2 * j + 1]);
+          } else {
+            hi[2 * j] = pack_bf16_pair(v[j].x, v[j].y);
+            hi[2 * j + 1] = pack_bf16_pair(v[j].z, v[j].w);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          *reinterpret_cast<uint4*>(prow + ((j ^ (pr & 7)) << 4)) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+          if constexpr (MODE == 6)
+            *reinterpret_cast<uint4*>(prow + (((4 + j) ^ (pr & 7)) << 4)) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(HALO_SPLIT) : "memory");      // all split warps: the converted patch is complete
     };
     uint32_t kbg = 0, ps = 0, pph = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       for (int sl = 0; sl < p.cch; sl++) {
-        const uint8_t* patch = gen_base + ps * HPATCH_STAGE;
+        uint8_t* patch = gen_base + ps * HPATCH_STAGE;
         const int first = (group + G - (int)(kbg % G)) % G;     // this group's first tap of the slice: (kbg + first) % G == group
         mbar_wait(pfull_bar(ps), pph);                       // every group waits for every patch
+        if constexpr (Cfg::kOnce) convert_patch(patch);
         float4 x[8];
         load_tap(patch, first, x);
         for (int tap = first; tap < 9; tap += G) {
@@ -305,7 +343,23 @@ tc_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
           mbar_wait(empty_bar(s), ((k / S) & 1) ^ 1);       // the MMAs that read this TMEM slot last have completed
           tc_fence_after();
           const uint32_t acol = tmem_base + ((uint32_t)(quarter * 32) << 16) + Cfg::kAccCols + s * Cfg::kACols;
-          if constexpr (Cfg::kBf16) {
+          if constexpr (Cfg::kOnce) {
+            uint32_t w[16];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              w[4 * j] = __float_as_uint(x[j].x); w[4 * j + 1] = __float_as_uint(x[j].y);
+              w[4 * j + 2] = __float_as_uint(x[j].z); w[4 * j + 3] = __float_as_uint(x[j].w);
+            }
+            tmem_st16u(acol, w);
+            if constexpr (MODE == 6) {
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                w[4 * j] = __float_as_uint(x[4 + j].x); w[4 * j + 1] = __float_as_uint(x[4 + j].y);
+                w[4 * j + 2] = __float_as_uint(x[4 + j].z); w[4 * j + 3] = __float_as_uint(x[4 + j].w);
+              }
+              tmem_st16u(acol + 16, w);
+            }
+          } else if constexpr (Cfg::kBf16) {
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int j = 0; j < 8; j++) {
@@ -341,6 +395,7 @@ tc_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
           mbar_arrive(xfm_bar(s));
         }
         kbg += 9;
+        if constexpr (Cfg::kOnce) fence_proxy_async_smem();   // our generic-proxy writes to the slot precede TMA's next write to it
         mbar_arrive(pempty_bar(ps));                 // this thread has read the patch for the last time
         if (++ps == HPATCH_SLOTS) { ps = 0; pph ^= 1; }
       }

@@ -204,22 +204,24 @@ __global__ void emb_repack_kernel(const float* __restrict__ w, void* __restrict_
   }
 }
 
+// db[c] = sum over (b, h, w) of dy: grid (splits, 32 channels), a warp walks a row, partial sums joined by one atomic per block
+// (db zeroed by the caller; the weight gradient next to it accumulates with atomics as well)
 __global__ void emb_bias_grad_kernel(const float* __restrict__ dy, float* __restrict__ db, int B, int H, int W, int P) {
   __shared__ float red[8];
-  const int c = blockIdx.x;
+  const int c = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows = B * H;
   float s = 0.f;
-  for (long long j = threadIdx.x; j < (long long)B * H * W; j += 256) {
-    const int w = (int)(j % W);
-    const long long r = j / W;
-    s += dy[(((size_t)(r / H) * EC + c) * H + (r % H)) * P + w];
+  for (int r = blockIdx.x * 8 + warp; r < rows; r += gridDim.x * 8) {
+    const float* row = dy + (((size_t)(r / H) * EC + c) * H + (r % H)) * P;
+    for (int w = lane; w < W; w += 32) s += row[w];
   }
   s = warp_sum(s);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  if (lane == 0) red[warp] = s;
   __syncthreads();
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int w = 0; w < 8; w++) t += red[w];
-    db[c] = t;
+    atomicAdd(db + c, t);
   }
 }
 
@@ -367,7 +369,8 @@ int b200asr_conv2d_tc_bwd_weight(const float* dy, const float* x, float* dw, flo
   int rc = launch_engine<EmbWgradPolicy, 3>(mx, mdy, p, base * e.splits, st, "conv2d_tc_wgrad");
   if (rc) return rc;
   if (dbias) {
-    emb_bias_grad_kernel<<<EC, 256, 0, st>>>(dy, dbias, B, g.OH, g.OW, y_pitch);
+    cudaMemsetAsync(dbias, 0, sizeof(float) * EC, st);
+    emb_bias_grad_kernel<<<dim3(32, EC), 256, 0, st>>>(dy, dbias, B, g.OH, g.OW, y_pitch);
     return check_launch("conv2d_tc_bias_grad");
   }
   return B200ASR_OK;

@@ -183,7 +183,7 @@ class WeightOperandCache:
 
     def __init__(self, flat):
         self.flat = flat                      # optim.FlatParams
-        self.entries, self.pending = {}, []   # key -> (src_off, N, K, terms, dst_off, dstT_off)
+        self.entries, self.pending = {}, {}   # key -> (src_off, N, K, terms, dst_off, dstT_off); key -> the weight tensor
         self.buf = self.desc = self.prefix = None
         self.tiles = 0
         self.gen = 0                          # number of refreshes so far
@@ -194,14 +194,16 @@ class WeightOperandCache:
         return w2.is_contiguous() and f.data_ptr() <= w2.data_ptr() and w2.data_ptr() + w2.numel() * 4 <= f.data_ptr() + f.numel() * 4
 
     def refresh(self):
+        fresh = None
         if self.pending:
             off = 0 if self.buf is None else self.buf.numel()
-            for key in self.pending:
+            fresh = self.pending
+            for key in fresh:
                 ptr, N, K, terms = key
                 n8 = (N + 7) // 8 * 8
                 self.entries[key] = ((ptr - self.flat.flat.data_ptr()) // 4, N, K, terms, off, off + terms * N * K)
                 off += (terms * N * K + terms * K * n8 + 63) // 64 * 64
-            self.pending = []
+            self.pending = {}
             dev = self.flat.flat.device
             self.buf = torch.empty(off, device=dev, dtype=torch.bfloat16)
             rows, prefix, tiles = [], [], 0
@@ -216,6 +218,9 @@ class WeightOperandCache:
             L.check(_lib().b200asr_split_bf16_batched(L.ptr(self.flat.flat), L.ptr(self.buf), L.ptr(self.desc), L.ptr(self.prefix),
                                                       len(self.entries), self.tiles, _stream()), "split_bf16_batched")
         self.gen += 1
+        if fresh:       # converted just now from the tensors' current contents: the first get() must not convert again
+            for key, w2 in fresh.items():
+                self.seen[key] = [w2._version, self.gen]
 
     def after_optimizer_step(self):
         if self.entries or self.pending:
@@ -227,8 +232,7 @@ class WeightOperandCache:
         key = (w2.data_ptr(), N, K, terms)
         e = self.entries.get(key)
         if e is None:
-            if key not in self.pending:
-                self.pending.append(key)
+            self.pending.setdefault(key, w2)
             return None
         seen = self.seen.get(key)
         if seen is None or seen[0] != w2._version:
@@ -959,9 +963,10 @@ class EmbFrontendFn(torch.autograd.Function):
             c1 = new(B, C, H1, W1)
             L.check(lib.b200asr_conv2d_fwd(L.ptr(x), L.ptr(_f32c(w0)), L.ptr(b0), L.ptr(c1), B, 1, H, W, C, 41, 11, 2, 2, 0, 10, st), "emb_conv1")
         a1, m1, s1 = new(B, C, H1, P1), new(C), new(C)
+        bws = new(lib.b200asr_bn_ws_bytes(C) // 4)
         rm, rv, nbt, mom = bn_args(bn1)
         L.check(lib.b200asr_bn_clamp_fwd(L.ptr(c1), L.ptr(g1), L.ptr(be1), L.ptr(a1), L.ptr(m1), L.ptr(s1), L.ptr(rm), L.ptr(rv),
-                                         L.ptr(nbt), B, C, H1, W1, W1, P1, eps, mom, int(training), 0.0, 20.0, st), "emb_bn1")
+                                         L.ptr(nbt), L.ptr(bws), B, C, H1, W1, W1, P1, eps, mom, int(training), 0.0, 20.0, st), "emb_bn1")
         col2 = None
         c2 = new(B, C, H2, P2)
         if implicit:
@@ -976,7 +981,7 @@ class EmbFrontendFn(torch.autograd.Function):
         a2, m2, s2 = new(B, C, H2, W2), new(C), new(C)
         rm, rv, nbt, mom = bn_args(bn2)
         L.check(lib.b200asr_bn_clamp_fwd(L.ptr(c2), L.ptr(g4), L.ptr(be4), L.ptr(a2), L.ptr(m2), L.ptr(s2), L.ptr(rm), L.ptr(rv),
-                                         L.ptr(nbt), B, C, H2, W2, P2, W2, eps, mom, int(training), 0.0, 20.0, st), "emb_bn2")
+                                         L.ptr(nbt), L.ptr(bws), B, C, H2, W2, P2, W2, eps, mom, int(training), 0.0, 20.0, st), "emb_bn2")
         out = new(B, W2, C * H2)
         L.check(lib.b200asr_flatten_bcft_fwd(L.ptr(a2), L.ptr(out), B, C, H2, W2, st), "emb_flatten")
         ctx.save_for_backward(x, c1, a1, m1, s1, c2, a2, m2, s2, w0, g1, w3, g4)
@@ -1002,11 +1007,12 @@ class EmbFrontendFn(torch.autograd.Function):
         new = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
         dout = _f32c(dout)
         tr = int(ctx.training)
+        bws = new(lib.b200asr_bn_ws_bytes(C) // 4)
         da2 = new(B, C, H2, W2)
         L.check(lib.b200asr_flatten_bcft_bwd(L.ptr(dout), L.ptr(da2), B, C, H2, W2, st), "emb_flatten_bwd")
         dc2, dg4, dbe4 = new(B, C, H2, P2), new(C), new(C)
         L.check(lib.b200asr_bn_clamp_bwd(L.ptr(da2), L.ptr(c2), L.ptr(a2), L.ptr(g4), L.ptr(m2), L.ptr(s2), L.ptr(dc2), L.ptr(dg4), L.ptr(dbe4),
-                                         B, C, H2, W2, W2, P2, W2, P2, tr, 0.0, 20.0, st), "emb_bn2_bwd")
+                                         L.ptr(bws), B, C, H2, W2, W2, P2, W2, P2, tr, 0.0, 20.0, st), "emb_bn2_bwd")
         da1 = new(B, C, H1, P1)
         if implicit:
             dw3, db3 = torch.empty_like(w3), new(C)
@@ -1024,7 +1030,7 @@ class EmbFrontendFn(torch.autograd.Function):
             L.check(lib.b200asr_conv2d_bwd_data(L.ptr(dc2), L.ptr(_f32c(w3)), L.ptr(da1), B, C, H1, W1, C, 21, 11, 2, 1, 0, 0, st), "emb_conv2_dgrad")
         dc1, dg1, dbe1 = new(B, C, H1, W1), new(C), new(C)
         L.check(lib.b200asr_bn_clamp_bwd(L.ptr(da1), L.ptr(c1), L.ptr(a1), L.ptr(g1), L.ptr(m1), L.ptr(s1), L.ptr(dc1), L.ptr(dg1), L.ptr(dbe1),
-                                         B, C, H1, W1, P1, W1, P1, W1, tr, 0.0, 20.0, st), "emb_bn1_bwd")
+                                         L.ptr(bws), B, C, H1, W1, P1, W1, P1, W1, tr, 0.0, 20.0, st), "emb_bn1_bwd")
         if gemm:
             _, dw0, db0 = _conv_gemm_bwd(dc1, x, w0, ctx.cols[0], EmbFrontendFn.G1, prec, prec_w, False)
             ctx.cols = None

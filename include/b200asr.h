@@ -229,13 +229,16 @@ int b200asr_conv2d_bwd_weight(const float* dy, const float* x, float* dw, float*
  * outputs (the statistics used: saved for backward).
  * training != 0: batch statistics (biased variance, as ATen) and, if the buffers are given, the nn.BatchNorm2d state
  * update running_mean/var <- (1-momentum) old + momentum new (unbiased variance), num_batches_tracked (int64) += 1.
- * training == 0 (model.eval(), trainer.py:123): normalise with running_mean / running_var. */
+ * training == 0 (model.eval(), trainer.py:123): normalise with running_mean / running_var.
+ * Each call is two launches over a (splits x C) grid -- per-block partial statistics, then merge + apply --; ws holds the
+ * partials: b200asr_bn_ws_bytes(C) bytes. */
+size_t b200asr_bn_ws_bytes(int C);
 int b200asr_bn_clamp_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean,
                          float* invstd, float* running_mean, float* running_var, long long* num_batches_tracked,
-                         int B, int C, int H, int W, int x_pitch, int y_pitch, float eps, float momentum, int training,
-                         float lo, float hi, b200asr_stream_t stream);
+                         float* ws, int B, int C, int H, int W, int x_pitch, int y_pitch, float eps, float momentum,
+                         int training, float lo, float hi, b200asr_stream_t stream);
 int b200asr_bn_clamp_bwd(const float* dy, const float* x, const float* y, const float* gamma,
-                         const float* mean, const float* invstd, float* dx, float* dgamma, float* dbeta,
+                         const float* mean, const float* invstd, float* dx, float* dgamma, float* dbeta, float* ws,
                          int B, int C, int H, int W, int dy_pitch, int x_pitch, int y_pitch, int dx_pitch, int training,
                          float lo, float hi, b200asr_stream_t stream);
 /* The second emb_cnn convolution (models/asr/transformer.py:37, Conv2d(32, 32, (KH, KW), stride (SH, 1)), no padding) as
