@@ -46,6 +46,8 @@ __device__ __forceinline__ void keep4(const SoftP& p, long long row, int col, bo
 // one warp per (b, h, q) row; the row (<= 128 * NV floats) lives in registers between the passes
 template <int NV>
 __global__ void __launch_bounds__(256) softmax_fwd_kernel(SoftP p, float* __restrict__ probs, float* __restrict__ probs_drop) {
+  griddep_launch();      // programmatic dependent launch (common.cuh)
+  griddep_wait();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= p.rows) return;
@@ -106,6 +108,8 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(SoftP p, float* __rest
 // dS = scale * P (.) (dP - sum_j dP_j P_j),  dP = keep ? dPd / (1 - p) : 0   (in place over dPd)
 template <int NV>
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(SoftP p, const float* __restrict__ probs, float* __restrict__ dpd) {
+  griddep_launch();      // programmatic dependent launch (common.cuh)
+  griddep_wait();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= p.rows) return;
@@ -148,8 +152,8 @@ static int launch_softmax(const SoftP& p, float* a, float* b, cudaStream_t st) {
   const unsigned grid = (unsigned)((p.rows + 7) / 8);
 #define CASE(NVv)                                                                                   \
   if (nv <= NVv) {                                                                                  \
-    if constexpr (FWD) softmax_fwd_kernel<NVv><<<grid, 256, 0, st>>>(p, a, b);                      \
-    else softmax_bwd_kernel<NVv><<<grid, 256, 0, st>>>(p, a, b);                                    \
+    if constexpr (FWD) launch_pdl(softmax_fwd_kernel<NVv>, dim3(grid), dim3(256), 0, st, p, a, (float*)b);          \
+    else launch_pdl(softmax_bwd_kernel<NVv>, dim3(grid), dim3(256), 0, st, p, (const float*)a, b);   \
     return check_launch(FWD ? "softmax_fwd" : "softmax_bwd");                                       \
   }
   CASE(1) CASE(2) CASE(4) CASE(8) CASE(16)

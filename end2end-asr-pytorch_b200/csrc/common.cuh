@@ -32,6 +32,30 @@ int ensure_sm100();                   // B200ASR_OK iff current device is comput
     }                                            \
   } while (0)
 
+// Programmatic dependent launch.  A kernel launched through launch_pdl() may begin while its predecessor in the stream is
+// still draining (the predecessor calls griddep_launch() early; the hardware starts the dependent grid once every CTA of the
+// predecessor has done so or exited): its prologue -- barrier init, TMEM allocation, descriptor prefetch -- and the launch
+// latency then overlap the predecessor's tail.  Contract: EVERY kernel launched this way executes griddep_wait() before its
+// first global-memory access; griddep_wait() returns when the predecessor grid has completed and its writes are visible, so
+// ordering stays transitive along the stream.  Kernels launched the ordinary way are unaffected (both instructions are no-ops
+// for them).  B200ASR_PDL=0 turns the attribute off.
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline void launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);       // errors surface in check_launch()
+}
+#endif
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }

@@ -1,3 +1,4 @@
+#include <stdlib.h>
 // Error plumbing, device checks, version.
 #include <stdarg.h>
 
@@ -36,6 +37,11 @@ int ensure_dynamic_smem(const void* kernel, int bytes, bool (&done)[kMaxDevices]
   if (r != cudaSuccess) { set_error("%s: cannot reserve %d bytes of shared memory: %s", what, bytes, cudaGetErrorString(r)); return B200ASR_CUDA_ERROR; }
   done[dev] = true;
   return B200ASR_OK;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("B200ASR_PDL"); return !(e && e[0] == '0'); }();
+  return on;
 }
 
 int device_sm_count() {

@@ -20,6 +20,8 @@ add_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ res, co
                   const float* __restrict__ rowscale, float* __restrict__ y, float* __restrict__ z,
                   float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int d, float eps,
                   uint32_t thresh, float inv_keep, uint64_t key) {
+  griddep_launch();      // programmatic dependent launch (common.cuh)
+  griddep_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * LN_WARPS + warp;
   if (row >= rows) return;
@@ -90,6 +92,8 @@ add_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ z, con
                   float* __restrict__ partial, int rows, int d, uint32_t thresh, float inv_keep, uint64_t key) {
   __shared__ __align__(16) float sdg[LN_WARPS][NV * 128];
   __shared__ __align__(16) float sdb[LN_WARPS][NV * 128];
+  griddep_launch();      // programmatic dependent launch (common.cuh)
+  griddep_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4 dg[NV], db[NV];
 #pragma unroll
@@ -167,6 +171,8 @@ constexpr int LN_FIN_SLICES = 16;
 __global__ void __launch_bounds__(256) ln_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int d,
                                                               float* __restrict__ dgamma, float* __restrict__ dbeta) {
   __shared__ float ra[8][33], rb[8][33];
+  griddep_launch();      // programmatic dependent launch (common.cuh)
+  griddep_wait();
   const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   const int per = (nblk + gridDim.y - 1) / gridDim.y;
@@ -209,7 +215,7 @@ int b200asr_add_ln_fwd(const float* x, const float* residual, const float* gamma
                B200ASR_BAD_ALIGN, "add_ln_fwd: pointers must be 16-byte aligned");
   if (rows <= 0) return B200ASR_OK;
   uint32_t th = p_drop > 0.f ? dropout_thresh16(p_drop) : 0u;
-#define LN_FWD(NVv) add_ln_fwd_kernel<NVv><<<ceil_div(rows, LN_WARPS), LN_WARPS * 32, 0, (cudaStream_t)stream>>>( \
+#define LN_FWD(NVv) launch_pdl(add_ln_fwd_kernel<NVv>, dim3(ceil_div(rows, LN_WARPS)), dim3(LN_WARPS * 32), 0, (cudaStream_t)stream, \
       x, residual, gamma, beta, post_add, post_period, row_scale, y, z, mean, rstd, rows, d, eps, th, \
       dropout_inv_keep(p_drop), dropout_key(seed, offset))
   const int nv = ceil_div(d, 128);
@@ -235,7 +241,7 @@ int b200asr_add_ln_bwd(const float* dy, const float* z, const float* gamma, cons
   }
   uint32_t th = p_drop > 0.f ? dropout_thresh16(p_drop) : 0u;
   int nblk = ln_bwd_blocks(rows);
-#define LN_BWD(NVv) add_ln_bwd_kernel<NVv><<<nblk, LN_WARPS * 32, 0, st>>>(dy, z, gamma, mean, rstd, row_scale, dz, dx, \
+#define LN_BWD(NVv) launch_pdl(add_ln_bwd_kernel<NVv>, dim3(nblk), dim3(LN_WARPS * 32), 0, st, dy, z, gamma, mean, rstd, row_scale, dz, dx, \
       (float*)partial_ws, rows, d, th, dropout_inv_keep(p_drop), dropout_key(seed, offset))
   const int nv = ceil_div(d, 128);
   if (nv <= 1) LN_BWD(1); else if (nv <= 2) LN_BWD(2); else if (nv <= 4) LN_BWD(4); else if (nv <= 6) LN_BWD(6); else LN_BWD(8);
@@ -246,7 +252,7 @@ int b200asr_add_ln_bwd(const float* dy, const float* z, const float* gamma, cons
     cudaMemsetAsync(dgamma, 0, sizeof(float) * d, st);
     cudaMemsetAsync(dbeta, 0, sizeof(float) * d, st);
   }
-  ln_bwd_finalize_kernel<<<dim3(ceil_div(d, 32), LN_FIN_SLICES), 256, 0, st>>>((const float*)partial_ws, nblk, d, dgamma, dbeta);
+  launch_pdl(ln_bwd_finalize_kernel, dim3(ceil_div(d, 32), LN_FIN_SLICES), dim3(256), 0, st, (const float*)partial_ws, nblk, d, dgamma, dbeta);
   return check_launch("ln_bwd_finalize");
 }
 

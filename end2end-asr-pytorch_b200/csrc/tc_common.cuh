@@ -194,7 +194,7 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
 // pack2(a, b): 32-bit word with bf16(a) in the low half (element k) and bf16(b) in the high half (element k + 1) -- the
 // order in which a TMEM column holds two consecutive-k elements of a 16-bit A operand.
 #ifndef B200ASR_SPLIT_F2FP
-#define B200ASR_SPLIT_F2FP 0
+#define B200ASR_SPLIT_F2FP 1
 #endif
 __device__ __forceinline__ uint32_t cvt_bf16x2(float lo_elem, float hi_elem) {     // one F2FP: {hi_elem, lo_elem} -> packed bf16x2 (RN)
   uint32_t d;

@@ -112,6 +112,8 @@ tc_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
+  griddep_launch();      // programmatic dependent launch, see common.cuh
+  griddep_wait();
 
   auto decode = [&](int tile, int& f0, int& t0, int& b) {
     f0 = (tile % p.nft) * HF;
@@ -420,7 +422,7 @@ static int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const HaloP
   if (tiles <= 0) return B200ASR_OK;
   if (tiles >= (1LL << 31)) { set_error("tc_conv3x3_halo: too many tiles"); return B200ASR_BAD_SHAPE; }
   const int grid = (int)min(tiles, (long long)device_sm_count());
-  kern<<<grid, HALO_THREADS, Cfg::kSmemBytes, st>>>(ma, mb, p);
+  launch_pdl(kern, dim3(grid), dim3(HALO_THREADS), Cfg::kSmemBytes, st, ma, mb, p);
   return check_launch("tc_conv3x3_halo");
 }
 

@@ -124,6 +124,8 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - smem_base));
+  griddep_launch();      // the next kernel in the stream may start its own prologue as our CTAs retire ...
+  griddep_wait();        // ... and ours ran under the predecessor's tail: from here on its results are visible (common.cuh)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (whole warp loops, one lane issues)
@@ -485,7 +487,7 @@ int launch_engine(const CUtensorMap& ma, const CUtensorMap& mb, const typename P
   if (int rc = ensure_dynamic_smem((const void*)kern, Cfg::kSmemBytes, attr_set, what)) return rc;
   if (ntiles <= 0) return B200ASR_OK;
   const int grid = min(ntiles, device_sm_count());
-  kern<<<grid, eng_has_split_warps(NSPLIT) ? ENG_THREADS_X3 : ENG_THREADS_X1, Cfg::kSmemBytes, st>>>(ma, mb, p);
+  launch_pdl(kern, dim3(grid), dim3(eng_has_split_warps(NSPLIT) ? ENG_THREADS_X3 : ENG_THREADS_X1), Cfg::kSmemBytes, st, ma, mb, p);
   return check_launch(what);
 }
 
