@@ -172,7 +172,7 @@ struct WgradPolicy {
     if (t.nkb == 0) return;
     float* orow = p.e.dwr + ((size_t)(slot == 0 ? t.tap_a : t.tap_b) * p.e.Ci + ci) * p.e.Co + c0;
 #pragma unroll
-    for (int j = 0; j < 32; j++) atomicAdd(orow + j, v[j]);
+    for (int j = 0; j < 32; j += 4) red_add_v4(orow + j, v[j], v[j + 1], v[j + 2], v[j + 3]);     // dwr: 16-byte aligned rows of Co floats
   }
 };
 

@@ -163,6 +163,12 @@ struct GemmPolicy {
     float* crow = e.C + (size_t)row * e.ldc;
     const float* mrow = e.relu_mask ? e.relu_mask + (size_t)row * e.ldc : nullptr;
     if (e.splits > 1) {
+      if (((e.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0) && col0 + 32 <= e.N && !(e.bias && z == 0)) {
+        // a TMEM lane is a row, so the 32 lanes of a reduction instruction touch 32 rows whatever we do: make each one carry 16 bytes
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) red_add_v4(crow + col0 + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+        return;
+      }
 #pragma unroll
       for (int j = 0; j < 32; j++) {
         const int col = col0 + j;
