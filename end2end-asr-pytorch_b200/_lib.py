@@ -70,6 +70,9 @@ SIGNATURES = {
     "b200asr_bn_clamp_fwd": (_i, [_vp] * 10 + [_i] * 6 + [_f, _f, _i, _f, _f, _vp]),
     "b200asr_bn_clamp_bwd": (_i, [_vp] * 10 + [_i] * 9 + [_f, _f, _vp]),
     "b200asr_conv2d_tc_ws_bytes": (_sz, [_i] * 5),
+    "b200asr_conv2d_c1_tc_ws_bytes": (_sz, [_i] * 5),
+    "b200asr_conv2d_c1_tc_fwd": (_i, [_vp] * 5 + [_i] * 9 + [_vp]),
+    "b200asr_conv2d_c1_tc_bwd_weight": (_i, [_vp] * 5 + [_i] * 8 + [_vp]),
     "b200asr_conv2d_tc_fwd": (_i, [_vp] * 5 + [_i] * 11 + [_vp]),
     "b200asr_conv2d_tc_bwd_data": (_i, [_vp] * 4 + [_i] * 11 + [_vp]),
     "b200asr_conv2d_tc_bwd_weight": (_i, [_vp] * 5 + [_i] * 10 + [_vp]),

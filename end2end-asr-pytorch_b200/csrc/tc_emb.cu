@@ -179,6 +179,187 @@ struct EmbWgradPolicy {
   }
 };
 
+// ----------------------------------------------------------------------------------------------------------------------
+// First emb_cnn convolution (models/asr/transformer.py:33: Conv2d(1, 32, (41, 11), stride (2, 2), padding (0, 10))) on the
+// same engine.  With ONE input channel the contraction index is the tap itself; the 41 taps along H take the role of the
+// channels: the activation is read through an OVERLAPPING tensor-map view (w, kh, oh, n) whose kh stride is one input row
+// and whose oh stride is two, so a box {32 w, 32 kh} is a 32 x 32 window of "channel" rows for output row oh (rows beyond
+// kh = 40 are out of bounds of the view: zero fill).  A k-block = (kw, block of 32 kh): 11 x 2 per tile.  The stride 2 along
+// W is taken out by de-interleaving: input column 2 (ow + q) + r with r = (kw - PW) & 1, q = (kw - PW - r) / 2 lives in the
+// parity-r copy at column ow + q; each parity copy exists in the four 16-byte alignments (see above): eight half-width copies.
+struct Emb1G {
+  int B, H, W, OH, OW, KH, KW, PW, pd;      // pd: pitch of the de-interleaved copies
+};
+__device__ __forceinline__ void emb1_window(int kw, int PW, int w0, int& col, int& copy) {
+  const int e = kw - PW, r = e & 1, q = (e - r) >> 1;          // e - r is even: exact for negative values too
+  const int v = w0 + q, s = (-v) & 3;
+  col = v + s;
+  copy = r * 4 + s;
+}
+
+struct Emb1ConvP {
+  float* out;            // y [B, 32, OH, OW], row pitch `pitch`
+  const float* bias;
+  Emb1G g;
+  int pitch, tiles_w, nkblk;      // 128-wide tiles per output row; 32-deep kh blocks (2 for KH = 41)
+};
+
+struct Emb1ConvPolicy {
+  static constexpr int BN = EC, kABytes = 4 * 4096, kBBytes = EC * 128;
+  static constexpr bool kSplitA = true, kSplitB = false, kAMN = true, kBMN = false, kSumA = false, kSumB = false;
+  struct Params { Emb1ConvP e; };
+  static __device__ __forceinline__ int num_tiles(const Params& p) { return p.e.g.B * p.e.g.OH * p.e.tiles_w; }
+  struct Tile { int w0, oh, b, t; };                     // t: k-block cursor = kw * nkblk + kblk
+  static __device__ __forceinline__ Tile tile(const Params& p, int tile) {
+    Tile t;
+    t.w0 = (tile % p.e.tiles_w) * 128;
+    const int q = tile / p.e.tiles_w;
+    t.oh = q % p.e.g.OH; t.b = q / p.e.g.OH; t.t = 0;
+    return t;
+  }
+  static __device__ __forceinline__ int num_kb(const Params& p, int) { return p.e.g.KW * p.e.nkblk; }
+  static __device__ __forceinline__ void load_a(const Params& p, const Tile& t, const CUtensorMap* mapA, uint32_t sa, uint32_t bar) {
+    int col, copy;
+    emb1_window(t.t / p.e.nkblk, p.e.g.PW, t.w0, col, copy);
+    const int kh0 = (t.t % p.e.nkblk) * 32;
+#pragma unroll
+    for (int c = 0; c < 4; c++) tma_load_4d(sa + c * 4096, mapA, bar, col + 32 * c, kh0, t.oh, copy * p.e.g.B + t.b);
+  }
+  static __device__ __forceinline__ void load(const Params& p, Tile& t, const CUtensorMap* mapA, const CUtensorMap* mapB,
+                                              uint32_t sa, uint32_t sb, uint32_t sb_lo, uint32_t bar, bool leader) {
+    if (leader) {
+      load_a(p, t, mapA, sa, bar);
+      tma_load_2d(sb, mapB, bar, 0, t.t * EC);
+      tma_load_2d(sb_lo, mapB, bar, 0, (p.e.g.KW * p.e.nkblk + t.t) * EC);
+    }
+    t.t++;
+  }
+  static __device__ __forceinline__ void load16(const Params& p, Tile& t, const CUtensorMap* mapA, const CUtensorMap* mapB,
+                                                uint32_t sa, uint32_t sb, uint32_t sb_lo, uint32_t bar, bool leader, int halves) {
+    if (leader) {
+      load_a(p, t, mapA, sa, bar);
+      tma_load_2d(sb, mapB, bar, 0, t.t * EC);
+      if (halves == 2) tma_load_2d(sb_lo, mapB, bar, 0, (p.e.g.KW * p.e.nkblk + t.t) * EC);
+    }
+    t.t++;
+  }
+  static __device__ __forceinline__ uint64_t a_desc(uint32_t s, int ks) { return make_smem_desc(s + ks * 1024, 4096, 512, kLayoutSW128Base32B); }
+  static __device__ __forceinline__ uint64_t b_desc(uint32_t s, int ks) { return make_smem_desc(s + ks * 32, 16, 1024); }
+  static __device__ __forceinline__ uint64_t b_desc16(uint32_t s, int ks) { return make_smem_desc(s + ks * 32, 16, 512, kLayoutSW64); }
+  static __device__ __forceinline__ void store(const Params& p, const Tile& t, int r, int c0, const float (&v)[32]) {
+    const int w = t.w0 + r;
+    if (w >= p.e.g.OW) return;
+    float* o = p.e.out + (((size_t)t.b * EC + c0) * p.e.g.OH + t.oh) * p.e.pitch + w;
+    const size_t cs = (size_t)p.e.g.OH * p.e.pitch;
+#pragma unroll
+    for (int j = 0; j < 32; j++) o[j * cs] = v[j] + (p.e.bias ? __ldg(p.e.bias + c0 + j) : 0.f);
+  }
+};
+
+// weight gradient of the first convolution: rows = (kw (4 per tile), kh in its 32-block), columns = co, contraction = output
+// pixels along ow (32 per k-block); x windows from the de-interleaved copies, dy [B, 32, OH, OW] (row pitch a multiple of 4)
+struct Emb1WgP {
+  float* dw;             // [32 co, 1, KH, KW], zeroed by the caller
+  Emb1G g;
+  int m_tiles, nkblk, splits, rows_per_split, owb;
+};
+
+struct Emb1WgradPolicy {
+  static constexpr int BN = EC, kABytes = 4 * 4096, kBBytes = EC * 128;
+  static constexpr bool kSplitA = true, kSplitB = true, kAMN = false, kBMN = false, kSumA = false, kSumB = false;
+  struct Params { Emb1WgP e; };
+  static __device__ __forceinline__ int num_tiles(const Params& p) { return p.e.nkblk * p.e.m_tiles * p.e.splits; }
+  struct Tile { int kblk, mt, row, row_end, ob; };
+  static __device__ __forceinline__ Tile tile(const Params& p, int tile) {
+    Tile t;
+    t.kblk = tile % p.e.nkblk;
+    const int q = tile / p.e.nkblk;
+    t.mt = q % p.e.m_tiles;
+    const int z = q / p.e.m_tiles;
+    t.row = z * p.e.rows_per_split;
+    t.row_end = min(p.e.g.B * p.e.g.OH, t.row + p.e.rows_per_split);
+    t.ob = 0;
+    return t;
+  }
+  static __device__ __forceinline__ int num_kb(const Params& p, int tile) {
+    const int z = tile / (p.e.nkblk * p.e.m_tiles);
+    const int r0 = z * p.e.rows_per_split, r1 = min(p.e.g.B * p.e.g.OH, r0 + p.e.rows_per_split);
+    return max(0, r1 - r0) * p.e.owb;
+  }
+  static __device__ __forceinline__ void load(const Params& p, Tile& t, const CUtensorMap* mapX, const CUtensorMap* mapDy,
+                                              uint32_t sa, uint32_t sb, uint32_t, uint32_t bar, bool leader) {
+    if (leader) {
+      const int b = t.row / p.e.g.OH, oh = t.row % p.e.g.OH, ow0 = t.ob * 32;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int kw = t.mt * 4 + j;
+        int col, copy;
+        emb1_window(min(kw, p.e.g.KW - 1), p.e.g.PW, ow0, col, copy);
+        // taps beyond KW: a box at kh coordinate 64 is entirely outside the view -> zero rows, same byte count
+        tma_load_4d(sa + j * 4096, mapX, bar, col, kw < p.e.g.KW ? t.kblk * 32 : 64, oh, copy * p.e.g.B + b);
+      }
+      tma_load_4d(sb, mapDy, bar, ow0, 0, oh, b);
+    }
+    if (++t.ob == p.e.owb) { t.ob = 0; t.row++; }
+  }
+  static __device__ __forceinline__ uint64_t a_desc(uint32_t s, int ks) { return make_smem_desc(s + ks * 32, 16, 1024); }
+  static __device__ __forceinline__ uint64_t b_desc(uint32_t s, int ks) { return make_smem_desc(s + ks * 32, 16, 1024); }
+  static __device__ __forceinline__ void store(const Params& p, const Tile& t, int r, int c0, const float (&v)[32]) {
+    const int kw = t.mt * 4 + r / 32, kh = t.kblk * 32 + r % 32;
+    if (kw >= p.e.g.KW || kh >= p.e.g.KH) return;
+    float* o = p.e.dw + (size_t)kh * p.e.g.KW + kw;        // + co * (KH * KW)
+    const size_t cs = (size_t)p.e.g.KH * p.e.g.KW;
+#pragma unroll
+    for (int j = 0; j < 32; j++) atomicAdd(o + (size_t)(c0 + j) * cs, v[j]);
+  }
+};
+
+// x [B, H, W] -> eight copies [parity r][shift s][B][H][pd]: copy[w'] = x[2 (w' - s) + r], zeros outside
+__global__ void emb1_prep_kernel(const float* __restrict__ x, float* __restrict__ dst, long long R, int W, int pd) {
+  const int q = pd / 4;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * q) return;
+  const long long row = i / q;
+  const int w0 = (int)(i % q) * 4;
+  const float* in = x + row * W;
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    float v[7];
+#pragma unroll
+    for (int j = 0; j < 7; j++) {
+      const int c = 2 * (w0 - 3 + j) + r;
+      v[j] = (c >= 0 && c < W) ? __ldg(in + c) : 0.f;
+    }
+#pragma unroll
+    for (int s = 0; s < 4; s++)
+      *reinterpret_cast<float4*>(dst + ((size_t)(r * 4 + s) * R + row) * pd + w0) = make_float4(v[3 - s], v[4 - s], v[5 - s], v[6 - s]);
+  }
+}
+
+// w [32 co, 1, KH, KW] -> [(kw, kblk)][co][32 kh] (zero beyond KH); mode 3: fp32 hi | lo, modes 6 / 2: bf16 hi (| lo)
+__global__ void emb1_repack_kernel(const float* __restrict__ w, void* __restrict__ out, int KH, int KW, int nkblk, int mode) {
+  const int total = KW * nkblk * EC * 32;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int k = i % 32, co = (i / 32) % EC, t = i / (32 * EC);
+  const int kh = (t % nkblk) * 32 + k, kw = t / nkblk;
+  const float v = kh < KH ? w[((size_t)co * KH + kh) * KW + kw] : 0.f;
+  if (mode == 3) {
+    float* o = (float*)out;
+    const float hi = tf32_rn(v);
+    o[i] = hi;
+    o[total + i] = v - hi;
+  } else {
+    uint16_t* o = (uint16_t*)out;
+    const uint32_t r = __float_as_uint(v) + 0x8000u;
+    o[i] = (uint16_t)(r >> 16);
+    if (mode == 6) {
+      const float lo = v - __uint_as_float(r & 0xFFFF0000u);
+      o[total + i] = (uint16_t)((__float_as_uint(lo) + 0x8000u) >> 16);
+    }
+  }
+}
+
 // w [32 co, 32 ci, KH, KW] -> tap-major 32 x 32 slices: forward [(kh, kw)][co][ci], data gradient [(kh, kw)][ci][co];
 // mode 3: fp32 (rn_tf32(w) | w - hi); modes 6 / 2: bf16 (hi | lo) / hi
 __global__ void emb_repack_kernel(const float* __restrict__ w, void* __restrict__ out, int KH, int KW, int dgrad, int mode) {
@@ -262,6 +443,29 @@ static int nchw_map(CUtensorMap* m, const float* base, int W, int P, int H, int 
   uint64_t strides[3] = {(uint64_t)H * P, (uint64_t)P, (uint64_t)EC * H * P};
   uint32_t box[4] = {32, EC, 1, 1};
   return make_tensor_map_f32(m, base, 4, dims, strides, box, atom32, false);
+}
+
+static inline int emb1_pitch(int W) { return ((W + 1) / 2 + 3 + 3) / 4 * 4; }
+static inline size_t emb1_copy_floats(int B, int H, int W) { return (size_t)8 * B * H * emb1_pitch(W); }
+static inline size_t emb1_weight_floats(int KH, int KW) { return ((size_t)2 * KW * ((KH + 31) / 32) * EC * 32 + 255) / 256 * 256; }
+
+static int emb1_geom(Emb1G& g, const char* who, int B, int H, int W, int Co, int KH, int KW, int PW) {
+  B200_REQUIRE(Co == EC, B200ASR_BAD_SHAPE, "%s: 32 output channels (Co=%d)", who, Co);
+  B200_REQUIRE(B > 0 && KH > 0 && KH <= 64 && KW > 0 && PW >= 0 && H >= KH && W + 2 * PW >= KW, B200ASR_BAD_SHAPE, "%s: bad geometry", who);
+  g = Emb1G{B, H, W, (H - KH) / 2 + 1, (W + 2 * PW - KW) / 2 + 1, KH, KW, PW, emb1_pitch(W)};
+  return B200ASR_OK;
+}
+
+// the de-interleaved, shifted copies and the overlapping (w, kh, oh, n) view of them
+static int emb1_prepare(CUtensorMap* m, const float* x, float* copies, const Emb1G& g, bool atom32, cudaStream_t st) {
+  const long long R = (long long)g.B * g.H, n = R * (g.pd / 4);
+  emb1_prep_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, st>>>(x, copies, R, g.W, g.pd);
+  note_launch(1);
+  if (int rc = check_launch("conv2d_c1_prep")) return rc;
+  uint64_t dims[4] = {(uint64_t)g.pd, (uint64_t)g.KH, (uint64_t)g.OH, (uint64_t)8 * g.B};
+  uint64_t strides[3] = {(uint64_t)g.pd, (uint64_t)2 * g.pd, (uint64_t)g.H * g.pd};
+  uint32_t box[4] = {32, 32, 1, 1};
+  return make_tensor_map_f32(m, copies, 4, dims, strides, box, atom32, false);
 }
 
 template <bool DGRAD>
@@ -372,6 +576,66 @@ int b200asr_conv2d_tc_bwd_weight(const float* dy, const float* x, float* dw, flo
     cudaMemsetAsync(dbias, 0, sizeof(float) * EC, st);
     emb_bias_grad_kernel<<<dim3(32, EC), 256, 0, st>>>(dy, dbias, B, g.OH, g.OW, y_pitch);
     return check_launch("conv2d_tc_bias_grad");
+  }
+  return B200ASR_OK;
+}
+
+size_t b200asr_conv2d_c1_tc_ws_bytes(int B, int H, int W, int KH, int KW) {
+  if (B <= 0 || H <= 0 || W <= 0 || KH <= 0 || KW <= 0) return 0;
+  return sizeof(float) * (emb1_weight_floats(KH, KW) + emb1_copy_floats(B, H, W));
+}
+
+int b200asr_conv2d_c1_tc_fwd(const float* x, const float* w, const float* bias, float* y, void* ws, int B, int H, int W, int Co, int KH,
+                             int KW, int PW, int y_pitch, int precision, b200asr_stream_t stream) {
+  B200_REQUIRE(x && w && y && ws, B200ASR_BAD_ARG, "conv2d_c1_tc_fwd: null pointer");
+  B200_REQUIRE(precision == 3 || precision == 6 || precision == 2, B200ASR_BAD_ARG, "conv2d_c1_tc_fwd: precision must be 3, 6 or 2");
+  Emb1G g;
+  if (int rc = emb1_geom(g, "conv2d_c1_tc_fwd", B, H, W, Co, KH, KW, PW)) return rc;
+  B200_REQUIRE(y_pitch >= g.OW && aligned16(ws), B200ASR_BAD_ALIGN, "conv2d_c1_tc_fwd: pitch / alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nkblk = ceil_div(KH, 32), rows = KW * nkblk * EC;
+  emb1_repack_kernel<<<ceil_div(rows * 32, 256), 256, 0, st>>>(w, ws, KH, KW, nkblk, precision);
+  note_launch(1);
+  CUtensorMap ma, mb;
+  if (int rc = emb1_prepare(&ma, x, (float*)ws + emb1_weight_floats(KH, KW), g, true, st)) return rc;
+  {
+    uint64_t dims[2] = {32, (uint64_t)(precision == 2 ? 1 : 2) * rows}, strides[1] = {32};
+    uint32_t box[2] = {32, EC};
+    int rc = precision == 3 ? make_tensor_map_f32(&mb, ws, 2, dims, strides, box, false, false) : make_tensor_map_bf16(&mb, ws, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  Emb1ConvPolicy::Params p{Emb1ConvP{y, bias, g, y_pitch, ceil_div(g.OW, 128), nkblk}};
+  const long long tiles = (long long)B * g.OH * p.e.tiles_w;
+  if (tiles >= (1LL << 31)) { set_error("conv2d_c1_tc: too many tiles"); return B200ASR_BAD_SHAPE; }
+  if (precision == 3) return launch_engine<Emb1ConvPolicy, 3>(ma, mb, p, (int)tiles, st, "conv2d_c1_tc");
+  if (precision == 6) return launch_engine<Emb1ConvPolicy, 6>(ma, mb, p, (int)tiles, st, "conv2d_c1_tc");
+  return launch_engine<Emb1ConvPolicy, 2>(ma, mb, p, (int)tiles, st, "conv2d_c1_tc");
+}
+
+int b200asr_conv2d_c1_tc_bwd_weight(const float* dy, const float* x, float* dw, float* dbias, void* ws, int B, int H, int W, int Co,
+                                    int KH, int KW, int PW, int y_pitch, b200asr_stream_t stream) {
+  B200_REQUIRE(dy && x && dw && ws, B200ASR_BAD_ARG, "conv2d_c1_tc_bwd_weight: null pointer");
+  Emb1G g;
+  if (int rc = emb1_geom(g, "conv2d_c1_tc_bwd_weight", B, H, W, Co, KH, KW, PW)) return rc;
+  B200_REQUIRE(y_pitch >= g.OW && y_pitch % 4 == 0 && aligned16(dy) && aligned16(ws), B200ASR_BAD_ALIGN,
+               "conv2d_c1_tc_bwd_weight: dy needs a 16-byte aligned base and a row pitch that is a multiple of 4 floats (TMA)");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)EC * KH * KW, st);
+  CUtensorMap mx, mdy;
+  if (int rc = emb1_prepare(&mx, x, (float*)ws + emb1_weight_floats(KH, KW), g, false, st)) return rc;
+  if (int rc = nchw_map(&mdy, dy, g.OW, y_pitch, g.OH, B, false)) return rc;
+  Emb1WgP e{dw, g, ceil_div(KW, 4), ceil_div(KH, 32), 1, B * g.OH, ceil_div(g.OW, 32)};
+  const int base = e.nkblk * e.m_tiles, rows = B * g.OH;
+  int splits = max(1, (3 * device_sm_count()) / base);
+  e.rows_per_split = max(8, ceil_div(rows, splits));
+  e.splits = ceil_div(rows, e.rows_per_split);
+  Emb1WgradPolicy::Params p{e};
+  int rc = launch_engine<Emb1WgradPolicy, 3>(mx, mdy, p, base * e.splits, st, "conv2d_c1_tc_wgrad");
+  if (rc) return rc;
+  if (dbias) {
+    cudaMemsetAsync(dbias, 0, sizeof(float) * EC, st);
+    emb_bias_grad_kernel<<<dim3(32, EC), 256, 0, st>>>(dy, dbias, B, g.OH, g.OW, y_pitch);
+    return check_launch("conv2d_c1_tc_bias_grad");
   }
   return B200ASR_OK;
 }

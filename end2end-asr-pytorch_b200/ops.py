@@ -952,12 +952,19 @@ class EmbFrontendFn(torch.autograd.Function):
         new = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
         C = w0.shape[0]
         gemm = config.conv != L.PREC_FP32 and C % 4 == 0
-        implicit = gemm and config.emb_implicit and C == 32 and w3.shape[1] == 32            # tc_emb.cu takes 32 -> 32 channels
+        implicit = (gemm and config.emb_implicit and C == 32 and w3.shape[1] == 32          # tc_emb.cu: 1 -> 32 and 32 -> 32 channels
+                    and tuple(w0.shape) == (32, 1, 41, 11) and tuple(w3.shape[2:]) == (21, 11))
         H1, W1 = (H - 41) // 2 + 1, (W + 20 - 11) // 2 + 1
         H2, W2 = (H1 - 21) // 2 + 1, (W1 - 11) // 1 + 1
         P1, P2 = ((W1 + 3) // 4 * 4, (W2 + 3) // 4 * 4) if implicit else (W1, W2)      # TMA: 16-byte row pitches
         col1 = None
-        if gemm:
+        prec2 = config.conv if config.conv in (L.PREC_TF32X3, L.PREC_BF16X3, L.PREC_BF16) else L.PREC_TF32X3
+        if implicit:
+            c1 = new(B, C, H1, W1)
+            ws1 = torch.empty(lib.b200asr_conv2d_c1_tc_ws_bytes(B, H, W, 41, 11) // 4, device=dev, dtype=torch.float32)
+            L.check(lib.b200asr_conv2d_c1_tc_fwd(L.ptr(x), L.ptr(_f32c(w0)), L.ptr(b0), L.ptr(c1), L.ptr(ws1), B, H, W, C, 41, 11, 10, W1, prec2, st),
+                    "emb_conv1_tc")
+        elif gemm:
             c1, col1 = _conv_gemm_fwd(x, w0, b0, EmbFrontendFn.G1, config.conv)
         else:
             c1 = new(B, C, H1, W1)
@@ -970,7 +977,6 @@ class EmbFrontendFn(torch.autograd.Function):
         col2 = None
         c2 = new(B, C, H2, P2)
         if implicit:
-            prec2 = config.conv if config.conv in (L.PREC_TF32X3, L.PREC_BF16X3, L.PREC_BF16) else L.PREC_TF32X3
             ws = torch.empty(lib.b200asr_conv2d_tc_ws_bytes(B, H1, W1, 21, 11) // 4, device=dev, dtype=torch.float32)
             L.check(lib.b200asr_conv2d_tc_fwd(L.ptr(a1), L.ptr(_f32c(w3)), L.ptr(b3), L.ptr(c2), L.ptr(ws), B, C, H1, W1, C, 21, 11, 2,
                                               P1, P2, prec2, st), "emb_conv2_tc")
@@ -1028,10 +1034,15 @@ class EmbFrontendFn(torch.autograd.Function):
             dw3, db3 = torch.empty_like(w3), new(C)
             L.check(lib.b200asr_conv2d_bwd_weight(L.ptr(dc2), L.ptr(a1), L.ptr(dw3), L.ptr(db3), B, C, H1, W1, C, 21, 11, 2, 1, 0, 0, st), "emb_conv2_wgrad")
             L.check(lib.b200asr_conv2d_bwd_data(L.ptr(dc2), L.ptr(_f32c(w3)), L.ptr(da1), B, C, H1, W1, C, 21, 11, 2, 1, 0, 0, st), "emb_conv2_dgrad")
-        dc1, dg1, dbe1 = new(B, C, H1, W1), new(C), new(C)
+        dc1, dg1, dbe1 = new(B, C, H1, P1), new(C), new(C)          # P1 = W1 unless the implicit-GEMM weight gradient reads it by TMA
         L.check(lib.b200asr_bn_clamp_bwd(L.ptr(da1), L.ptr(c1), L.ptr(a1), L.ptr(g1), L.ptr(m1), L.ptr(s1), L.ptr(dc1), L.ptr(dg1), L.ptr(dbe1),
-                                         L.ptr(bws), B, C, H1, W1, P1, W1, P1, W1, tr, 0.0, 20.0, st), "emb_bn1_bwd")
-        if gemm:
+                                         L.ptr(bws), B, C, H1, W1, P1, W1, P1, P1, tr, 0.0, 20.0, st), "emb_bn1_bwd")
+        if implicit:
+            dw0, db0 = torch.empty_like(w0), new(C)
+            ws1 = torch.empty(lib.b200asr_conv2d_c1_tc_ws_bytes(B, H, W, 41, 11) // 4, device=dev, dtype=torch.float32)
+            L.check(lib.b200asr_conv2d_c1_tc_bwd_weight(L.ptr(dc1), L.ptr(x), L.ptr(dw0), L.ptr(db0), L.ptr(ws1), B, H, W, C, 41, 11, 10, P1, st),
+                    "emb_conv1_tc_wgrad")
+        elif gemm:
             _, dw0, db0 = _conv_gemm_bwd(dc1, x, w0, ctx.cols[0], EmbFrontendFn.G1, prec, prec_w, False)
             ctx.cols = None
         else:

@@ -258,6 +258,16 @@ int b200asr_conv2d_tc_bwd_data(const float* dy, const float* w, float* dx, void*
 int b200asr_conv2d_tc_bwd_weight(const float* dy, const float* x, float* dw, float* dbias, void* ws, int B, int Ci, int H,
                                  int W, int Co, int KH, int KW, int SH, int x_pitch, int y_pitch,
                                  b200asr_stream_t stream);
+/* The FIRST emb_cnn convolution (models/asr/transformer.py:33, Conv2d(1, 32, (KH, KW), stride (2, 2), padding (0, PW))) on the
+ * same engine: the KH taps along H play the role of input channels (an overlapping tensor-map view of the activation), the
+ * stride along W is removed by de-interleaving x into parity copies (x 4 alignments, see above).  x [B,1,H,W] dense;
+ * y / dy [B,32,OH,OW] with row pitch y_pitch (any value >= OW for the forward, a multiple of 4 for the weight gradient: TMA).
+ * No data gradient (the input is data).  ws: b200asr_conv2d_c1_tc_ws_bytes(B, H, W, KH, KW) bytes. */
+size_t b200asr_conv2d_c1_tc_ws_bytes(int B, int H, int W, int KH, int KW);
+int b200asr_conv2d_c1_tc_fwd(const float* x, const float* w, const float* bias, float* y, void* ws, int B, int H, int W,
+                             int Co, int KH, int KW, int PW, int y_pitch, int precision, b200asr_stream_t stream);
+int b200asr_conv2d_c1_tc_bwd_weight(const float* dy, const float* x, float* dw, float* dbias, void* ws, int B, int H,
+                                    int W, int Co, int KH, int KW, int PW, int y_pitch, b200asr_stream_t stream);
 /* x [B,C,F,T] -> y [B,T,C*F] and its inverse (gradient) */
 int b200asr_flatten_bcft_fwd(const float* x, float* y, int B, int C, int F, int T, b200asr_stream_t stream);
 int b200asr_flatten_bcft_bwd(const float* dy, float* dx, int B, int C, int F, int T, b200asr_stream_t stream);

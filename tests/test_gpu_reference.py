@@ -12,6 +12,7 @@ The reference checkout travels to the GPU box as oracle/_ref (staged by oracle/m
 """
 import copy
 import os
+import importlib
 import tempfile
 
 import pytest
@@ -66,13 +67,59 @@ def _batch(B, freq, T, vocab, Lt, seed=0, ragged=True):
     return src, lens.to(torch.int32), tgt, tl.to(torch.int32)
 
 
-def _step(ns, model, src, lens, tgt, dev):
+def _region(kind, t):
+    """The branch every unit took: ReLU 0 / 1 (from the post-activation value), Hardtanh(0, 20) 0 / 1 / 2."""
+    t = t.detach().float().cpu()
+    return (t > 0).to(torch.int8) + ((t >= 20).to(torch.int8) if kind == "hardtanh" else 0)
+
+
+class _RefDecisions:
+    """Forward hooks on the UNMODIFIED reference: the branch taken by every Hardtanh / ReLU unit of the CNN front end and by
+    every ReLU of the position-wise FFNs (F.relu there: hooked through conv_1's output), in execution order -- the order in
+    which ops.decision_capture lists the same units of our path (its max-pool entries have no counterpart here)."""
+
+    def __init__(self, model):
+        self.out, self.handles = [], []
+        for m in model.modules():
+            if isinstance(m, torch.nn.Hardtanh):
+                self.handles.append(m.register_forward_hook(lambda _m, _i, o: self.out.append(_region("hardtanh", o))))
+            elif isinstance(m, torch.nn.ReLU):
+                self.handles.append(m.register_forward_hook(lambda _m, _i, o: self.out.append(_region("relu", o))))
+            elif type(m).__name__ == "PositionwiseFeedForwardWithConv":      # conv_1 output is [B, d_inner, T]
+                self.handles.append(m.conv_1.register_forward_hook(lambda _m, _i, o: self.out.append(_region("relu", o.transpose(1, 2)))))
+
+    def close(self):
+        for h in self.handles:
+            h.remove()
+        return self.out
+
+
+def _count_flips(ref, ours):
+    """(# units whose branch differs, # units); None if the two lists do not describe the same units."""
+    ours = [_region(k, t) for k, t in ours if k != "pool"]
+    if len(ours) != len(ref) or any(a.shape != b.shape for a, b in zip(ours, ref)):
+        return None
+    return sum(int((a != b).sum()) for a, b in zip(ours, ref)), sum(a.numel() for a in ref)
+
+
+def _step(ns, model, src, lens, tgt, dev, decisions=None):
+    """One forward / loss / backward through the reference's own code.  decisions: "hooks" records the branch decisions of the
+    (uninstalled) reference, "capture" those of our kernels; they are returned as the seventh element."""
+    import b200asr
+    ops = importlib.import_module(b200asr.__name__ + ".ops")
     model.zero_grad(set_to_none=True)
-    pred, gold, hyp, _ = model(src.to(dev), lens, tgt.to(dev), verbose=False)
+    rec = _RefDecisions(model) if decisions == "hooks" else None
+    if decisions == "capture":
+        ops.decision_capture = []
+    try:
+        pred, gold, hyp, _ = model(src.to(dev), lens, tgt.to(dev), verbose=False)
+    finally:
+        dec = rec.close() if rec else ops.decision_capture
+        ops.decision_capture = None
     loss, n_correct = ns.metrics.calculate_metrics(pred, gold, smoothing=0.1, loss_type="ce")
     loss.backward()
     grads = {n: p.grad.detach().float().cpu() for n, p in model.named_parameters()}
-    return pred.detach().float().cpu(), gold.cpu(), hyp.cpu(), float(loss.item()), int(n_correct), grads
+    return pred.detach().float().cpu(), gold.cpu(), hyp.cpu(), float(loss.item()), int(n_correct), grads, dec
 
 
 @pytest.mark.parametrize("case", ["small_vgg", "small_emb", "cfg2_arch"])
@@ -85,15 +132,15 @@ def test_install_on_unmodified_reference_matches_reference_forward_backward(case
     keys = list(model.state_dict().keys())
     model.train()
     _fp32_flags()
-    cpu = _step(ns, model, src, lens, tgt, "cpu")                       # (i) the reference's own CPU forward/backward
+    cpu = _step(ns, model, src, lens, tgt, "cpu", "hooks")              # (i) the reference's own CPU forward/backward
     model = model.cuda()
-    eager = _step(ns, model, src, lens, tgt, "cuda")                    # (ii) the reference eager on the B200
+    eager = _step(ns, model, src, lens, tgt, "cuda", "hooks")           # (ii) the reference eager on the B200
     orig_forward = ns.transformer.Transformer.forward
     b200asr.install()
     try:
         assert ns.transformer.Transformer.forward is not orig_forward
         launches0 = b200asr._lib.load().b200asr_launch_count()
-        ours = _step(ns, model, src, lens, tgt, "cuda")                 # (iii) our kernels behind the reference's classes
+        ours = _step(ns, model, src, lens, tgt, "cuda", "capture")      # (iii) our kernels behind the reference's classes
         assert b200asr._lib.load().b200asr_launch_count() > launches0   # ... and they did launch
     finally:
         b200asr.uninstall()
@@ -117,7 +164,14 @@ def test_install_on_unmodified_reference_matches_reference_forward_backward(case
         # this reference, where decisions can be frozen); here: the median tensor in the max norm, every tensor in the
         # relative L2 norm.
         med = sorted(errs.values())[len(errs) // 2]
-        assert med < (5 if case == "cfg2_arch" else 1) * TOL, (name, med)
+        unit_flips = _count_flips(other[6], ours[6])
+        print(f"[{case}] installed vs {name}: ReLU / Hardtanh units that took another branch: {unit_flips}")
+        assert unit_flips is not None, "decision lists of the reference hooks and of ops.decision_capture do not line up"
+        if unit_flips[0] == 0:
+            assert med < (5 if case == "cfg2_arch" else 1) * TOL, (name, med)
+        else:       # a unit within rounding of its threshold moves a token's gradient by O(1 / sqrt(d_inner)): bounded, not exact
+            assert unit_flips[0] <= 2 + unit_flips[1] // 100000, (name, unit_flips)
+            assert med < 10 * TOL, (name, med, unit_flips)
         for k, r in other[5].items():
             denom = max(float(r.norm()), 1e-3 * max(float(v.abs().max()) for v in other[5].values()) * r.numel() ** 0.5)
             assert float((ours[5][k] - r).norm()) / denom < 10 * TOL, (name, k)
