@@ -167,14 +167,15 @@ def test_install_on_unmodified_reference_matches_reference_forward_backward(case
         unit_flips = _count_flips(other[6], ours[6])
         print(f"[{case}] installed vs {name}: ReLU / Hardtanh units that took another branch: {unit_flips}")
         assert unit_flips is not None, "decision lists of the reference hooks and of ops.decision_capture do not line up"
-        if unit_flips[0] == 0:
-            assert med < (5 if case == "cfg2_arch" else 1) * TOL, (name, med)
-        else:       # a unit within rounding of its threshold moves a token's gradient by O(1 / sqrt(d_inner)): bounded, not exact
-            assert unit_flips[0] <= 2 + unit_flips[1] // 100000, (name, unit_flips)
-            assert med < 10 * TOL, (name, med, unit_flips)
+        # every unit on the same branch: tight bounds.  Otherwise (k of ~1e5 .. 1e7 units within rounding of their threshold):
+        # a flipped FFN unit adds / removes one token's term in ITS row of that layer's weight gradient (relative L2 of the
+        # tensor up to ~1/sqrt(d_inner)) and moves the gradients below it by O(1 / (tokens sqrt(d_inner))): bounded, not exact.
+        same = unit_flips[0] == 0
+        assert unit_flips[0] <= 2 + unit_flips[1] // 100000, (name, unit_flips)
+        assert med < ((5 if case == "cfg2_arch" else 1) * TOL if same else 10 * TOL), (name, med, unit_flips)
         for k, r in other[5].items():
             denom = max(float(r.norm()), 1e-3 * max(float(v.abs().max()) for v in other[5].values()) * r.numel() ** 0.5)
-            assert float((ours[5][k] - r).norm()) / denom < 10 * TOL, (name, k)
+            assert float((ours[5][k] - r).norm()) / denom < (10 * TOL if same else 0.2), (name, k, unit_flips)
         assert flips <= max(1, int(real.sum()) // 100)                  # near-ties at random init
         assert abs(ours[4] - other[4]) <= max(1, int(real.sum()) // 100)
 
