@@ -638,6 +638,23 @@ int b200asr_conv3x3_fwd(const float* x, const float* w, const float* bias, float
   return conv3x3_tc(x, (const float*)ws, bias, nullptr, y, B, T, F, Ci, Co, relu, precision, st);
 }
 
+int b200asr_conv3x3_fwd_pool(const float* x, const float* w, const float* bias, float* y, float* pooled, void* ws, int B, int T, int F,
+                             int Ci, int Co, int relu, int precision, b200asr_stream_t stream) {
+  B200_REQUIRE(x && w && y && pooled && ws, B200ASR_BAD_ARG, "conv3x3_fwd_pool: null pointer");
+  if (conv_is_bf16(precision)) {       // the pooling rides in the convolution's epilogue (tc_conv_halo.cu)
+    int rc = conv_shape_ok("conv3x3_fwd_pool", Ci, Co);
+    if (rc) return rc;
+    B200_REQUIRE(Ci % 32 == 0 && (Co == 64 || Co == 128), B200ASR_BAD_SHAPE, "conv3x3_fwd_pool (bf16): needs Ci %% 32 == 0 and Co in {64,128}");
+    B200_REQUIRE(aligned16(pooled), B200ASR_BAD_ALIGN, "conv3x3_fwd_pool: alignment");
+    cudaStream_t st = (cudaStream_t)stream;
+    note_launch(1);
+    conv_repack_k_bf16_kernel<<<ceil_div(9 * Ci * Co, 256), 256, 0, st>>>(w, (uint16_t*)ws, Ci, Co, 0, precision == B200ASR_PREC_BF16X3 ? 2 : 1);
+    return conv3x3_tc_halo(x, ws, bias, nullptr, y, B, T, F, Ci, Co, relu, precision, st, nullptr, pooled);
+  }
+  if (int rc = b200asr_conv3x3_fwd(x, w, bias, y, ws, B, T, F, Ci, Co, relu, precision, stream)) return rc;
+  return b200asr_maxpool2x2_fwd(y, pooled, B, T, F, Co, stream);
+}
+
 int b200asr_conv3x3_bwd_data(const float* dy, const float* w, const float* relu_out, float* dx, void* dx16, void* ws, int B, int T,
                              int F, int Ci, int Co, int precision, b200asr_stream_t stream) {
   B200_REQUIRE(dy && w && dx && ws, B200ASR_BAD_ARG, "conv3x3_bwd_data: null pointer");

@@ -37,6 +37,7 @@ constexpr int HALO_GROUPS = HALO_GROUPS_N, HALO_SPLIT = 128 * HALO_GROUPS, HALO_
 
 struct HaloP {
   uint16_t* out16;       // optional bf16 hi | lo pairs of the output, [2][pixels][Cout] (lo at + npix * Cout), or nullptr
+  float* pool;           // optional MaxPool2d(2, 2) of the output, [B, T/2, F/2, Cout] (floor mode), or nullptr
   float* out;
   const float* bias;
   const float* mask;
@@ -253,15 +254,15 @@ tc_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
           tc_fence_before();
           mbar_arrive(tempty_bar(buf));
         }
-        if (!valid) continue;
+        if (!valid && !p.pool) continue;                // (with pooling every lane takes part in the shuffles below)
 #pragma unroll
         for (int half = 0; half < 2; half++) {     // all loads of a 16-channel half before its first store
           float4 bb[4], mm[4];
 #pragma unroll
           for (int q = 0; q < 4; q++) {
             const int col = c * 32 + half * 16 + q * 4;
-            bb[q] = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            mm[q] = mrow ? __ldg(reinterpret_cast<const float4*>(mrow + col)) : make_float4(1.f, 1.f, 1.f, 1.f);
+            bb[q] = (p.bias && valid) ? __ldg(reinterpret_cast<const float4*>(p.bias + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            mm[q] = (mrow && valid) ? __ldg(reinterpret_cast<const float4*>(mrow + col)) : make_float4(1.f, 1.f, 1.f, 1.f);
           }
 #pragma unroll
           for (int q = 0; q < 4; q++) {
@@ -270,13 +271,25 @@ tc_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
             if (p.relu) { o[0] = fmaxf(o[0], 0.f); o[1] = fmaxf(o[1], 0.f); o[2] = fmaxf(o[2], 0.f); o[3] = fmaxf(o[3], 0.f); }
             o[0] = mm[q].x > 0.f ? o[0] : 0.f; o[1] = mm[q].y > 0.f ? o[1] : 0.f;
             o[2] = mm[q].z > 0.f ? o[2] : 0.f; o[3] = mm[q].w > 0.f ? o[3] : 0.f;
-            *reinterpret_cast<float4*>(orow + col) = make_float4(o[0], o[1], o[2], o[3]);
-            if (orow16) {       // the same values as bf16 pairs: the weight-gradient kernel's B operand (WgradPairPolicy)
+            if (valid) *reinterpret_cast<float4*>(orow + col) = make_float4(o[0], o[1], o[2], o[3]);
+            if (orow16 && valid) {       // the same values as bf16 pairs: the weight-gradient kernel's B operand (WgradPairPolicy)
               uint2 ph, pl;
               split_bf16_pair(o[0], o[1], ph.x, pl.x);
               split_bf16_pair(o[2], o[3], ph.y, pl.y);
               *reinterpret_cast<uint2*>(orow16 + col) = ph;
               *reinterpret_cast<uint2*>(orow16 + lo_off + col) = pl;
+            }
+            if (p.pool) {
+              // fused MaxPool2d(2, 2): a warp holds 4 time rows x 8 freq bins of the tile (lane = 8 * row + bin, tile origin
+              // even in both), so the 2 x 2 window of lane l is {l, l ^ 1, l ^ 8, l ^ 9}; the even / even lane stores it
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                o[e] = fmaxf(o[e], __shfl_xor_sync(0xffffffffu, o[e], 1));
+                o[e] = fmaxf(o[e], __shfl_xor_sync(0xffffffffu, o[e], 8));
+              }
+              if ((lane & 9) == 0 && tt + 1 < p.T && ff + 1 < p.F)
+                *reinterpret_cast<float4*>(p.pool + ((((size_t)b * (p.T >> 1) + (tt >> 1)) * (p.F >> 1) + (ff >> 1)) * p.Cout + col)) =
+                    make_float4(o[0], o[1], o[2], o[3]);
             }
           }
         }
@@ -431,7 +444,7 @@ static int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const HaloP
 // wk: mode 3: [2][9][Cout][Cin] fp32 pre-split K-major weights (hi | lo), as for conv3x3_tc with precision 3;
 //     mode 6 / 2: [2 or 1][9][Cout][Cin] bf16 (conv_repack_k_bf16_kernel)
 int conv3x3_tc_halo(const float* in, const void* wk, const float* bias, const float* mask, float* out, int B, int T, int F,
-                    int Cin, int Cout, int relu, int mode, cudaStream_t st, void* out16) {
+                    int Cin, int Cout, int relu, int mode, cudaStream_t st, void* out16, float* pool) {
   using namespace tc;
   B200_REQUIRE(mode == 3 || mode == 6 || mode == 2, B200ASR_BAD_ARG, "conv3x3_tc_halo: mode must be 3 (3xTF32), 6 (bf16x3) or 2 (bf16)");
   B200_REQUIRE(Cin % 32 == 0 && (Cout == 64 || Cout == 128), B200ASR_BAD_SHAPE,
@@ -453,7 +466,7 @@ int conv3x3_tc_halo(const float* in, const void* wk, const float* bias, const fl
     int rc = mode == 3 ? make_tensor_map_f32(&mb, wk, 2, dims, strides, box, false, false) : make_tensor_map_bf16(&mb, wk, 2, dims, strides, box);
     if (rc) return rc;
   }
-  HaloP p{(uint16_t*)out16, out, bias, mask, relu, B, T, F, Cin, Cout, ceil_div(F, HF), ceil_div(T, HT), Cin / 32};
+  HaloP p{(uint16_t*)out16, pool, out, bias, mask, relu, B, T, F, Cin, Cout, ceil_div(F, HF), ceil_div(T, HT), Cin / 32};
   if (mode == 3) return Cout == 64 ? launch_halo<64, 3>(ma, mb, p, st) : launch_halo<128, 3>(ma, mb, p, st);
   if (mode == 6) return Cout == 64 ? launch_halo<64, 6>(ma, mb, p, st) : launch_halo<128, 6>(ma, mb, p, st);
   return Cout == 64 ? launch_halo<64, 2>(ma, mb, p, st) : launch_halo<128, 2>(ma, mb, p, st);

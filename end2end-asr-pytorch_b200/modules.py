@@ -46,11 +46,13 @@ def _mha_core(self, query, key, value, key_pad=None, dense_mask=None, causal=Fal
     p_attn = _drop_p(self, self.attention.dropout)
     scale = 1.0 / float(self.attention.temperature)
     ql, kl, vl = self.query_linear, self.key_linear, self.value_linear
+    link = None
     if key is value:
+        link = ops.ResidualLink() if torch.is_grad_enabled() else None
         # projections + attention as one autograd node: Q/K/V (or K/V) run as ONE GEMM when their weights lie back to back
         # in memory (optim.FlatParams), and the attention kernels address the packed output through strides
         o = ops.AttnProjFn.apply(query, key, ql.weight, ql.bias, kl.weight, kl.bias, vl.weight, vl.bias, H, dk, dv,
-                                 key_pad, dense_mask, causal, scale, p_attn)                # [B,Tq,H*dv], token-major
+                                 key_pad, dense_mask, causal, scale, p_attn, link)          # [B,Tq,H*dv], token-major
     else:
         q = ops.LinearFn.apply(query, ql.weight, ql.bias).view(B, Tq, H, dk).permute(0, 2, 1, 3)
         k = ops.LinearFn.apply(key, kl.weight, kl.bias).view(B, Tk, H, dk).permute(0, 2, 1, 3)
@@ -59,14 +61,15 @@ def _mha_core(self, query, key, value, key_pad=None, dense_mask=None, causal=Fal
         o = o.permute(0, 2, 1, 3).reshape(B, Tq, H * dv)                                  # free: memory is token-major
     o = ops.LinearFn.apply(o, self.output_linear.weight, self.output_linear.bias)
     ln = self.layer_norm
-    return ops.AddLNFn.apply(o, query, ln.weight, ln.bias, None, row_scale, ln.eps, _drop_p(self, self.dropout))
+    return ops.AddLNFn.apply(o, query, ln.weight, ln.bias, None, row_scale, ln.eps, _drop_p(self, self.dropout), link)
 
 
 def _ffn_core(self, x, row_scale=None):
     """PositionwiseFeedForwardWithConv body (models/common_layers.py:135-142)."""
-    y = ops.FFNFn.apply(x, self.conv_1.weight, self.conv_1.bias, self.conv_2.weight, self.conv_2.bias)
+    link = ops.ResidualLink() if torch.is_grad_enabled() else None
+    y = ops.FFNFn.apply(x, self.conv_1.weight, self.conv_1.bias, self.conv_2.weight, self.conv_2.bias, link)
     ln = self.layer_norm
-    return ops.AddLNFn.apply(y, x, ln.weight, ln.bias, None, row_scale, ln.eps, _drop_p(self, self.dropout))
+    return ops.AddLNFn.apply(y, x, ln.weight, ln.bias, None, row_scale, ln.eps, _drop_p(self, self.dropout), link)
 
 
 # ------------------------------------------------------------------------------------------------ forwards (bindable)

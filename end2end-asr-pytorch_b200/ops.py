@@ -275,13 +275,34 @@ def linear_fwd(x2, w, b, relu, prec, w_split=None):
     return y
 
 
-def linear_bwd_data(dy2, w, relu_out, prec, w_split=None):
+def linear_bwd_data(dy2, w, relu_out, prec, w_split=None, accumulate_into=None):
+    """dx = dy W (masked by relu_out > 0 if given); accumulate_into: a contiguous fp32 [M, K] tensor the product is ADDED to in
+    the GEMM epilogue (and which is returned) -- how residual-branch gradients are summed without an extra pass."""
     M, N = dy2.shape
     K = w.shape[1]
-    dx = torch.empty((M, K), device=dy2.device, dtype=torch.float32)
-    L.check(_lib().b200asr_linear_bwd_data(L.ptr(dy2), L.ptr(w), L.ptr(relu_out), L.ptr(dx), M, N, K, 0, prec,
+    acc = accumulate_into is not None
+    if acc and not (accumulate_into.is_contiguous() and accumulate_into.dtype == torch.float32 and accumulate_into.numel() == M * K):
+        raise RuntimeError("linear_bwd_data: accumulate_into must be a contiguous fp32 tensor of M * K elements")
+    dx = accumulate_into.view(M, K) if acc else torch.empty((M, K), device=dy2.device, dtype=torch.float32)
+    L.check(_lib().b200asr_linear_bwd_data(L.ptr(dy2), L.ptr(w), L.ptr(relu_out), L.ptr(dx), M, N, K, int(acc), prec,
                                            L.ptr(w_split.bwd if w_split is not None else None), _stream()), "linear_bwd_data")
     return dx
+
+
+class ResidualLink:
+    """One per sub-layer y = LN(dropout(f(x)) + x): carries the residual-branch gradient from AddLNFn.backward to the backward
+    of the node that consumes x (FFNFn / AttnProjFn), whose data-gradient GEMM adds its product into it (accumulate epilogue).
+    Without it autograd sums the two gradients of x with a separate elementwise kernel per sub-layer.  `armed` is set in the
+    consumer's forward (x needs a gradient and the consumer will compute one); AddLNFn then hands dz over instead of
+    returning it."""
+    __slots__ = ("armed", "dz")
+
+    def __init__(self):
+        self.armed, self.dz = False, None
+
+    def take(self):
+        dz, self.dz = self.dz, None
+        return dz
 
 
 def _grad_sink(param):
@@ -398,8 +419,11 @@ class FFNFn(torch.autograd.Function):
     """y = relu(x W1^T + b1) W2^T + b2   (models/common_layers.py:137-139; dropout/residual/LN follow in AddLNFn)."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, b2):
+    def forward(ctx, x, w1, b1, w2, b2, link=None):
         _need_cuda(x, w1, w2)
+        ctx.link = link
+        if link is not None:
+            link.armed = bool(ctx.needs_input_grad[0])
         w1m = _f32c(w1.reshape(w1.shape[0], -1))
         w2m = _f32c(w2.reshape(w2.shape[0], -1))
         x2 = _f32c(x).reshape(-1, w1m.shape[1])
@@ -429,9 +453,10 @@ class FFNFn(torch.autograd.Function):
         dh = linear_bwd_data(dy2, w2m, h, ctx.prec, ws2) if (need[0] or need[1] or need[2]) else None     # masked by relu'(h)
         if need[1] or need[2]:
             dw1, db1 = linear_bwd_weight(dh, x2, True, ctx.prec, _grad_sink(w1), _grad_sink(b1))
-        dx = linear_bwd_data(dh, w1m, None, ctx.prec, ws1) if need[0] else None
+        res = ctx.link.take() if ctx.link is not None else None          # residual-branch gradient of x, if AddLNFn handed it over
+        dx = linear_bwd_data(dh, w1m, None, ctx.prec, ws1, accumulate_into=res) if need[0] else None
         return ((dx.view(xs) if dx is not None else None), (dw1.view(w1s) if dw1 is not None else None), db1,
-                (dw2.view(w2s) if dw2 is not None else None), db2)
+                (dw2.view(w2s) if dw2 is not None else None), db2, None)
 
 
 # ----------------------------------------------------------------------------------------------- residual + LN
@@ -439,8 +464,9 @@ class AddLNFn(torch.autograd.Function):
     """y = (LN(dropout(x) + residual) * gamma + beta + post_add[row % period]) * row_scale[row]."""
 
     @staticmethod
-    def forward(ctx, x, residual, gamma, beta, post_add, row_scale, eps, p_drop):
+    def forward(ctx, x, residual, gamma, beta, post_add, row_scale, eps, p_drop, link=None):
         _need_cuda(x, gamma, beta)
+        ctx.link = link if (link is not None and link.armed and residual is not None and ctx.needs_input_grad[1]) else None
         d = x.shape[-1]
         x2 = _f32c(x).reshape(-1, d)
         rows = x2.shape[0]
@@ -470,7 +496,8 @@ class AddLNFn(torch.autograd.Function):
         dy2 = _f32c(dy).reshape(-1, d)
         lib = _lib()
         dz = torch.empty_like(dy2)
-        dx = torch.empty_like(dy2) if p_drop > 0.0 else dz
+        # with a link, dz is later added to in place by the consumer of the residual: keep it distinct from dx
+        dx = torch.empty_like(dy2) if (p_drop > 0.0 or ctx.link is not None) else dz
         # gamma / beta gradients go straight into the parameters' .grad (flat gradient buffer) when that exists: no
         # zero-fill, no AccumulateGrad add -- four tiny launches less per LayerNorm
         g_sink, b_sink = _grad_sink(ctx.params[0]), _grad_sink(ctx.params[1])
@@ -481,8 +508,11 @@ class AddLNFn(torch.autograd.Function):
         L.check(lib.b200asr_add_ln_bwd(L.ptr(dy2), L.ptr(z), L.ptr(gamma), L.ptr(mean), L.ptr(rstd), L.ptr(rs), L.ptr(dz),
                                        L.ptr(dx), L.ptr(dgamma), L.ptr(dbeta), L.ptr(ws), rows, d, p_drop, seed, off,
                                        int(direct), _stream()), "add_ln_bwd")
+        if ctx.link is not None:
+            ctx.link.dz = dz                       # summed into the data gradient of the node that consumes the residual
+            has_res = False
         return (dx.view(xshape), (dz.view(xshape) if has_res else None), None if direct else dgamma, None if direct else dbeta,
-                None, None, None, None)
+                None, None, None, None, None)
 
 
 # ----------------------------------------------------------------------------------------------- attention
@@ -641,8 +671,11 @@ class AttnProjFn(torch.autograd.Function):
     buffer, all through strides.  Any other memory arrangement runs the same arithmetic as three GEMMs."""
 
     @staticmethod
-    def forward(ctx, xq, xkv, wq, bq, wk, bk, wv, bv, H, dk, dv, key_pad, dense_mask, causal, scale, p_drop):
+    def forward(ctx, xq, xkv, wq, bq, wk, bk, wv, bv, H, dk, dv, key_pad, dense_mask, causal, scale, p_drop, link=None):
         _need_cuda(xq, xkv, wq, wk, wv)
+        ctx.link = link
+        if link is not None:
+            link.armed = bool(ctx.needs_input_grad[0])
         same = xq is xkv
         B, Tq, D = xq.shape
         Tk = xkv.shape[1]
@@ -707,18 +740,20 @@ class AttnProjFn(torch.autograd.Function):
         ctx.state = None
         params = ctx.params
         grads_w, grads_b = [None] * 3, [None] * 3
-        dxq = dxkv = None
+        dxkv = None
         need_xq, need_xkv = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        # running sums: every further contribution is added in its GEMM's epilogue; dxq starts from the residual-branch
+        # gradient of the query input when AddLNFn handed it over (ResidualLink)
+        dxq = ctx.link.take() if ctx.link is not None else None
+        if dxq is not None and not need_xq:
+            dxq = None
         for (idx, x2, W, wsplit, prec), dy in zip(ctx.saved, dys):
             feeds_q = 0 in idx
             if (feeds_q and need_xq) or (not feeds_q and (need_xkv or (same and need_xq))):
-                dx = linear_bwd_data(dy, W, None, prec, wsplit)
-                if feeds_q:
-                    dxq = dx if dxq is None else dxq + dx
-                elif same:
-                    dxq = dx if dxq is None else dxq + dx
+                if feeds_q or same:
+                    dxq = linear_bwd_data(dy, W, None, prec, wsplit, accumulate_into=dxq)
                 else:
-                    dxkv = dx if dxkv is None else dxkv + dx
+                    dxkv = linear_bwd_data(dy, W, None, prec, wsplit, accumulate_into=dxkv)
             ws_ = [params[2 * i] for i in idx]
             bs_ = [params[2 * i + 1] for i in idx]
             sinks_w = [_grad_sink(w) for w in ws_]
@@ -739,7 +774,7 @@ class AttnProjFn(torch.autograd.Function):
         dxq = dxq.view(xq_shape) if dxq is not None else None
         dxkv = dxkv.view(xkv_shape) if dxkv is not None else None
         return (dxq, dxkv, grads_w[0], grads_b[0], grads_w[1], grads_b[1], grads_w[2], grads_b[2],
-                None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None)
 
 
 def _dense_like(t):
@@ -772,20 +807,19 @@ class VggFrontendFn(torch.autograd.Function):
         y1 = new(B, T, F, C1)
         L.check(lib.b200asr_conv3x3_c1_fwd(L.ptr(x), L.ptr(_f32c(w0)), L.ptr(b0), L.ptr(y1), B, F, T, C1, 1, st), "conv1")
         y2 = new(B, T, F, C1)
-        L.check(lib.b200asr_conv3x3_fwd(L.ptr(y1), L.ptr(_f32c(w2)), L.ptr(b2), L.ptr(y2), L.ptr(ws), B, T, F, C1, C1, 1,
-                                        prec, st), "conv2")
         T2, F2 = T // 2, F // 2
         p1 = new(B, T2, F2, C1)
-        L.check(lib.b200asr_maxpool2x2_fwd(L.ptr(y2), L.ptr(p1), B, T, F, C1, st), "pool1")
+        # conv + ReLU + MaxPool2d(2, 2): in the kind::f16 modes the pooling is the convolution's epilogue
+        L.check(lib.b200asr_conv3x3_fwd_pool(L.ptr(y1), L.ptr(_f32c(w2)), L.ptr(b2), L.ptr(y2), L.ptr(p1), L.ptr(ws), B, T, F, C1, C1, 1,
+                                             prec, st), "conv2+pool1")
         y3 = new(B, T2, F2, C2)
         L.check(lib.b200asr_conv3x3_fwd(L.ptr(p1), L.ptr(_f32c(w5)), L.ptr(b5), L.ptr(y3), L.ptr(ws), B, T2, F2, C1, C2, 1,
                                         prec, st), "conv3")
         y4 = new(B, T2, F2, C2)
-        L.check(lib.b200asr_conv3x3_fwd(L.ptr(y3), L.ptr(_f32c(w7)), L.ptr(b7), L.ptr(y4), L.ptr(ws), B, T2, F2, C2, C2, 1,
-                                        prec, st), "conv4")
         T4, F4 = T2 // 2, F2 // 2
         p2 = new(B, T4, F4, C2)
-        L.check(lib.b200asr_maxpool2x2_fwd(L.ptr(y4), L.ptr(p2), B, T2, F2, C2, st), "pool2")
+        L.check(lib.b200asr_conv3x3_fwd_pool(L.ptr(y3), L.ptr(_f32c(w7)), L.ptr(b7), L.ptr(y4), L.ptr(p2), L.ptr(ws), B, T2, F2, C2, C2, 1,
+                                             prec, st), "conv4+pool2")
         ctx.save_for_backward(x, y1, y2, p1, y3, y4, w0, w2, w5, w7)
         if decision_capture is not None:      # channels-last [B,T,F,C] -> the reference's (B,C,F,T)
             nchw = lambda t: t.permute(0, 3, 2, 1)

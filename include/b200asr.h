@@ -195,6 +195,11 @@ int b200asr_conv3x3_c1_bwd_weight(const float* x, const float* dy, float* dw, fl
 /* x [B,T,F,Ci] -> y [B,T,F,Co]; ws: b200asr_conv3x3_ws_bytes(Ci,Co) */
 int b200asr_conv3x3_fwd(const float* x, const float* w, const float* bias, float* y, void* ws, int B, int T,
                         int F, int Ci, int Co, int relu, int precision, b200asr_stream_t stream);
+/* The same convolution followed by MaxPool2d(2, stride 2) (models/asr/transformer.py:44-52: conv, ReLU, pool): y as above AND
+ * pooled [B,T/2,F/2,Co] (floor mode).  In the kind::f16 modes the 2x2 maximum is taken in the convolution's epilogue (four
+ * lanes of a warp hold a window), so the activation is not read back; other precisions run the two kernels. */
+int b200asr_conv3x3_fwd_pool(const float* x, const float* w, const float* bias, float* y, float* pooled, void* ws, int B,
+                             int T, int F, int Ci, int Co, int relu, int precision, b200asr_stream_t stream);
 /* dx[B,T,F,Ci] = conv_transpose(dy) .* (relu_out > 0 if relu_out != NULL).
  * dx16 (optional, precisions 6 / 2 only): the same gradient additionally as bf16 hi | lo "pairs" [2][B,T,F,Ci] (hi = bf16(v),
  * lo = bf16(v - hi)) -- what b200asr_conv3x3_bwd_weight of the layer below takes as dy16. */

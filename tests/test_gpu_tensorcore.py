@@ -394,3 +394,24 @@ def test_conv2d_first_layer_implicit_gemm(L, B, H, W, prec, tol):
         L.check(lib.b200asr_conv2d_c1_tc_bwd_weight(L.ptr(dypad), L.ptr(x), L.ptr(dw), L.ptr(db), L.ptr(ws), B, H, W, 32, KH, KW, PW, yp, st), "wgrad")
         assert rel_err(dw, w64.grad) < 3e-5
         assert rel_err(db, dy.double().sum((0, 2, 3))) < 1e-5
+
+
+@pytest.mark.parametrize("prec", [6, 2, 3, 0])
+@pytest.mark.parametrize("B,T,F_,Ci,Co", [(2, 32, 16, 64, 64), (1, 37, 21, 64, 128), (2, 18, 161, 128, 128)])
+def test_conv3x3_with_fused_max_pool(L, B, T, F_, Ci, Co, prec):
+    """b200asr_conv3x3_fwd_pool == b200asr_conv3x3_fwd followed by b200asr_maxpool2x2_fwd, bit for bit (the kind::f16 modes take
+    the 2x2 maximum in the convolution's epilogue; odd T / F exercise the floor-mode edges and partial tiles)."""
+    lib = L.load()
+    g = torch.Generator().manual_seed(B + T)
+    x = torch.randn(B, T, F_, Ci, generator=g).cuda()
+    w = (torch.randn(Co, Ci, 3, 3, generator=g) * (9 * Ci) ** -0.5).cuda()
+    b = torch.randn(Co, generator=g).cuda()
+    ws = torch.empty(lib.b200asr_conv3x3_ws_bytes(Ci, Co) // 4, device="cuda")
+    st = _stream()
+    y0 = torch.full((B, T, F_, Co), float("nan"), device="cuda")
+    p0 = torch.full((B, T // 2, F_ // 2, Co), float("nan"), device="cuda")
+    L.check(lib.b200asr_conv3x3_fwd(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y0), L.ptr(ws), B, T, F_, Ci, Co, 1, prec, st), "conv")
+    L.check(lib.b200asr_maxpool2x2_fwd(L.ptr(y0), L.ptr(p0), B, T, F_, Co, st), "pool")
+    y1, p1 = torch.full_like(y0, float("nan")), torch.full_like(p0, float("nan"))
+    L.check(lib.b200asr_conv3x3_fwd_pool(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y1), L.ptr(p1), L.ptr(ws), B, T, F_, Ci, Co, 1, prec, st), "conv+pool")
+    assert torch.equal(y0, y1) and torch.equal(p0, p1)
