@@ -144,7 +144,7 @@ def test_bench_flop_accounting_reads_integer_dimensions_of_the_abi():
     import importlib
     import bench
     L = importlib.import_module(b200asr.__name__ + "._lib")
-    for name in ("linear_fwd", "linear_bwd_data", "linear_bwd_weight", "conv3x3_fwd", "conv3x3_bwd_data", "conv3x3_bwd_weight",
+    for name in ("linear_fwd", "linear_bwd_data", "linear_bwd_weight", "conv3x3_fwd", "conv3x3_fwd_pool", "conv3x3_bwd_data", "conv3x3_bwd_weight",
                  "conv3x3_c1_fwd", "conv3x3_c1_bwd_weight", "sdpa_fwd", "sdpa_bwd", "sdpa_mat_fwd", "sdpa_mat_bwd", "sdpa_fused_fwd",
                  "sdpa_fused_bwd"):
         argtypes = L.SIGNATURES["b200asr_" + name][1]
