@@ -1,8 +1,7 @@
-timeout 900 python -m pytest tests/test_gpu_tensorcore.py tests/test_gpu_parity.py -m gpu -q -k "pool or vgg or conv3x3" 2>&1 | grep -v Warning | tail -4
-timeout 400 python bench.py --no-cpu --no-ref-gpu --steps 10 2>&1 | tail -1 > gpurun_out/r2_bench_pool.json
-python - <<'PY'
-import json
-d=json.loads(open("gpurun_out/r2_bench_pool.json").read())
-print("ms/step", round(d["ms_per_step"],3), "e2e", round(d["e2e"]["ms_per_step"],3), "loss", d["final_loss"], "launches", d["gpu_launches"])
-for k in d["kernels"][:14]: print("   %-28s %5.0f launches %7.3f ms" % (k["kernel"], k["launches_per_step"], k["ms_per_step"]))
-PY
+set -x
+NCU="ncu --clock-control none"
+timeout 600 $NCU --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv --log-file gpurun_out/launches_r2.csv python tools/one_step.py 3 > gpurun_out/one_step_ncu.log 2>&1
+timeout 400 $NCU --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv --log-file gpurun_out/launches_cfg3_r2.csv python tools/one_step.py 3 cfg3 > gpurun_out/one_step_cfg3_ncu.log 2>&1
+timeout 400 $NCU --set full --import-source on -k regex:halo -s 12 -c 6 -f -o gpurun_out/prof_halo_r2 python tools/one_step.py 3 > gpurun_out/ncu_halo.log 2>&1
+timeout 400 $NCU --set full --import-source on --kernel-name-base demangled -k regex:"Emb" -s 5 -c 5 -f -o gpurun_out/prof_emb_r2 python tools/one_step.py 2 cfg3 16 > gpurun_out/ncu_emb.log 2>&1
+ls -la gpurun_out/*r2.ncu-rep
