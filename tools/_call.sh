@@ -1,7 +1,4 @@
-set -x
-NCU="ncu --clock-control none"
-timeout 600 $NCU --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv --log-file gpurun_out/launches_r2.csv python tools/one_step.py 3 > gpurun_out/one_step_ncu.log 2>&1
-timeout 400 $NCU --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv --log-file gpurun_out/launches_cfg3_r2.csv python tools/one_step.py 3 cfg3 > gpurun_out/one_step_cfg3_ncu.log 2>&1
-timeout 400 $NCU --set full --import-source on -k regex:halo -s 12 -c 6 -f -o gpurun_out/prof_halo_r2 python tools/one_step.py 3 > gpurun_out/ncu_halo.log 2>&1
-timeout 400 $NCU --set full --import-source on --kernel-name-base demangled -k regex:"Emb" -s 5 -c 5 -f -o gpurun_out/prof_emb_r2 python tools/one_step.py 2 cfg3 16 > gpurun_out/ncu_emb.log 2>&1
-ls -la gpurun_out/*r2.ncu-rep
+for c in cfg1 cfg2 cfg3 cfg4 cfg5; do timeout 300 python tools/run_configs.py $c 2>&1 | tail -1; done > gpurun_out/r2_configs_default.jsonl
+timeout 300 python tools/run_configs.py cfg5 --mode bf16 2>&1 | tail -1 > gpurun_out/r2_configs_cfg5_bf16.jsonl
+timeout 300 python tools/run_configs.py cfg2 --mode tf32x3 2>&1 | tail -1 > gpurun_out/r2_configs_cfg2_tf32x3.jsonl
+cat gpurun_out/r2_configs_default.jsonl gpurun_out/r2_configs_cfg5_bf16.jsonl gpurun_out/r2_configs_cfg2_tf32x3.jsonl | cut -c1-260

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """One training step (zero_grad + fwd + CE + bwd + Adam) at every BASELINE.json configuration's per-GPU shape: checks that each
 shape is supported end to end (finite loss, no shape/alignment rejection) and prints one JSON line per configuration
-(CUDA-event timed, 3 warm-up + 10 timed steps).  Usage:
+(CUDA-event timed, 10 warm-up + 20 timed steps).  Usage:
     python tools/run_configs.py [cfg1 cfg2 ...] [--batch N] [--mode default|bf16|tf32x3|fp32]
 Modes: default = package default (bf16x3 linear/conv fwd+dgrad, tf32x3 conv wgrad + attention); bf16 = BASELINE cfg5's
 "bf16" (one kind::f16 MMA per product everywhere, TF32 flash attention); tf32x3 = 3xTF32 everywhere; fp32 = CUDA cores."""
@@ -33,23 +33,23 @@ for name in names:
     lens = torch.full((B,), T, dtype=torch.int32)
     tgt = torch.randint(3, cfg.vocab, (B, cfg.tgt_max_len - 1), device=dev)
     try:
-        for _ in range(3):
+        for _ in range(10):                      # long enough for the SM clocks to ramp up from idle in a fresh process
             dp.step(src, lens, tgt)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(10):
+        for _ in range(20):
             dp.step(src, lens, tgt)
         e1.record()
         torch.cuda.synchronize()
         loss = float(dp.global_loss())
-        ms = e0.elapsed_time(e1) / 10
+        ms = e0.elapsed_time(e1) / 20
         print(json.dumps({"config": name, "mode": mode, "per_gpu_batch": B, "t_src": T, "t_enc": cfg.t_enc(T), "t_tgt": cfg.tgt_max_len,
                           "layers": cfg.num_layers, "d_model": cfg.dim_model, "feat": cfg.feat_extractor or "none",
                           "params_M": round(sum(p.numel() for p in model.parameters()) / 1e6, 1), "ms_per_step": round(ms, 2),
                           "utt_per_s": round(B / ms * 1e3, 1), "loss": round(loss, 4),
                           "peak_mem_GiB": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1), "dropout": cfg.dropout,
-                          "step": "zero_grad+fwd+CE+bwd+adam, 10 timed steps after 3 warm-up, CUDA events"}), flush=True)
+                          "step": "zero_grad+fwd+CE+bwd+adam, 20 timed steps after 10 warm-up, CUDA events"}), flush=True)
         assert loss == loss and abs(loss) < 1e4
     except Exception as e:  # noqa: BLE001
         print(json.dumps({"config": name, "mode": mode, "error": f"{type(e).__name__}: {str(e)[:300]}"}), flush=True)
