@@ -380,14 +380,14 @@ def run_b200(args, rank, local_rank, world):
     # ---- end-to-end: pinned host inputs copied in, loss read back, every step
     loss_h = torch.zeros(1).pin_memory()
     for _ in range(min(2, args.warmup)):
-        dp.step(src_h.to(dev, non_blocking=True), lens_d, tgt_h.to(dev, non_blocking=True))
+        dp.step(src_h.to(dev, non_blocking=True), lens, tgt_h.to(dev, non_blocking=True))
     barrier()
     t0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         s = src_h.to(dev, non_blocking=True)
         t = tgt_h.to(dev, non_blocking=True)
-        dp.step(s, lens_d, t)
+        dp.step(s, lens, t)                               # lengths as the reference's loader hands them over: a CPU tensor
         loss_h.copy_(dp.global_loss().reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()         # the caller reads the loss every step
     e1.record()

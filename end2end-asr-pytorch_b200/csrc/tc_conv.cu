@@ -119,6 +119,12 @@ struct WgradPolicy {
   static constexpr int BN = BN_, kABytes = 4 * 4096, kBBytes = (BN_ / 32) * 4096;
   static constexpr bool kSplitA = true, kSplitB = true, kAMN = true, kBMN = true;
   static constexpr bool kSumA = false, kSumB = true;       // bias gradient = column sums of the dy tiles
+#ifndef WGRAD_CAT
+#define WGRAD_CAT 0
+#endif
+  // Co = 64: [hi*hi | hi*lo] as one N = 128 MMA (tc_engine.cuh).  Measured at cfg2's conv1_2: 1.91 ms with, 1.76 ms without --
+  // the wider accumulator leaves 4 instead of 6 stages of A in tensor memory, which costs more than the N = 64 MMAs do.
+  static constexpr bool kCat = WGRAD_CAT != 0;
   static constexpr int kGroups = CI == 64 ? 5 : 9;
   struct Params { WgP e; int splits; };
   static __device__ __forceinline__ int num_tiles(const Params& p) { return kGroups * p.splits; }

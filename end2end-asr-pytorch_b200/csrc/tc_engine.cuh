@@ -25,6 +25,8 @@
 // re-derived (b, t, f, tap) with integer divisions for every k-block -- ~1000 clk each -- and that, not the tensor pipe,
 // set the pace; see profiles/engine_ConvPolicy_r1.md).
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -56,14 +58,23 @@ constexpr int ENG_SPLIT_THREADS = 256;
 // holds only [A_raw | B_hi | B_lo] per stage (48 KB instead of 64 KB for a 128x128 tile -> one more stage in flight) and the
 // tensor core no longer competes with the split for smem bandwidth on the A side (an SS 128x128x8 MMA reads 8 KB of smem
 // per 64 cycles = the full 128 B/clk of the SM).
+// A policy may opt in (static constexpr bool kCat = true) to the "concatenated" form of the 3xTF32 products at BN = 64: the
+// tensor core is markedly less efficient at N = 64 than at N = 128 (see tc_conv_halo.cu), so hi*hi and hi*lo become ONE N = 128
+// MMA against the adjacent [B_hi ; B_lo] tiles of the stage into a 128-column accumulator, lo*hi an N = 64 MMA into its first
+// half, and the epilogue adds the halves.  Costs accumulator columns: 4 stages of A in tensor memory instead of 6.
+template <class P, class = void> struct policy_cat : std::false_type {};
+template <class P> struct policy_cat<P, std::void_t<decltype(P::kCat)>> : std::bool_constant<P::kCat> {};
+
 template <class Policy, int NSPLIT> struct EngineCfg {
   static constexpr bool kBf16 = eng_is_bf16(NSPLIT);
+  static constexpr bool kCat = policy_cat<Policy>::value && Policy::BN == 64 && NSPLIT == 3;
+  static constexpr int kAccW = kCat ? 128 : Policy::BN;                                      // accumulator columns per buffer
   static constexpr int kBHalves = (NSPLIT == 3 || NSPLIT == 6) ? 2 : 1;                     // B tiles per stage (hi | lo)
   static constexpr int kBTile = kBf16 ? Policy::BN * 64 : Policy::kBBytes;                   // bf16: 32 k x 2 B = 64-byte rows
   static constexpr int kACols = NSPLIT == 3 ? 64 : (NSPLIT == 6 ? 32 : (NSPLIT == 2 ? 16 : 0));   // TMEM columns of A per stage
   static constexpr int kBRaw = (kBf16 && Policy::kSplitB) ? Policy::kBBytes : 0;             // bf16 + in-kernel B conversion: raw fp32 tile
   static constexpr int kStageBytes = Policy::kABytes + kBRaw + kBHalves * kBTile;
-  static constexpr int kMaxByTmem = NSPLIT == 1 ? 8 : (512 - 2 * Policy::BN) / kACols;
+  static constexpr int kMaxByTmem = NSPLIT == 1 ? 8 : (512 - 2 * kAccW) / kACols;
   static constexpr int kBySmem = (200 * 1024) / kStageBytes;
 #ifndef ENG_MAX_STAGES
 #define ENG_MAX_STAGES 8
@@ -76,7 +87,7 @@ template <class Policy, int NSPLIT> struct EngineCfg {
   static constexpr int kOffBlo = kOffBhi + kBTile;
   static constexpr int kBarOff = kStages * kStageBytes;
   static constexpr int kSmemBytes = kBarOff + 512 + 1024;
-  static constexpr int kAccCols = 2 * Policy::BN;
+  static constexpr int kAccCols = 2 * kAccW;
   static constexpr int kTmemCols = NSPLIT != 1 ? 512 : (kAccCols <= 32 ? 32 : (kAccCols <= 64 ? 64 : (kAccCols <= 128 ? 128 : 256)));
   static constexpr int kTxBytes = kBf16 ? Policy::kABytes + (Policy::kSplitB ? Policy::kBBytes : kBHalves * kBTile)
                                         : Policy::kABytes + Policy::kBBytes +
@@ -155,6 +166,7 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const bool leader = elect_one();
     constexpr uint32_t idesc = make_idesc_tf32(128, BN, Policy::kAMN, Policy::kBMN);
     constexpr uint32_t idesc_ts = make_idesc_tf32(128, BN, false, Policy::kBMN);
+    constexpr uint32_t idesc_cat = make_idesc_tf32(128, 128, false, Policy::kBMN);
     constexpr bool kNeedXfm = NSPLIT != 1;
     constexpr uint32_t idesc_bf = make_idesc_bf16(128, BN, false, Policy::kBMN);
     constexpr uint32_t kStageStep = Cfg::kStageBytes >> 4, kLoStep = Cfg::kBTile >> 4;
@@ -176,7 +188,7 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const uint32_t buf = tcount & 1;
       mbar_wait(tempty_bar(buf), ((tcount >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + buf * BN;
+      const uint32_t d_tmem = tmem_base + buf * Cfg::kAccW;
       for (int kb = 0; kb < nkb; kb++) {
         mbar_wait(kNeedXfm ? xfm_bar(s) : full_bar(s), ph);
         tc_fence_after();
@@ -200,9 +212,14 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             } else {
               const uint64_t b_lo = mk(bd_hi, b_lo32 + kLoStep + ks * b_ks);
               const uint32_t a_hi = a_t + ks * 8, a_lo = a_hi + 32;
-              umma_tf32_ts(d_tmem, a_lo, b_hi, idesc_ts, acc0);
-              umma_tf32_ts(d_tmem, a_hi, b_lo, idesc_ts, 1u);
-              umma_tf32_ts(d_tmem, a_hi, b_hi, idesc_ts, 1u);
+              if constexpr (Cfg::kCat) {
+                umma_tf32_ts(d_tmem, a_hi, b_hi, idesc_cat, acc0);             // [hi*hi | hi*lo]: B_lo follows B_hi in the stage
+                umma_tf32_ts(d_tmem, a_lo, b_hi, idesc_ts, 1u);                // + lo*hi into the first 64 columns
+              } else {
+                umma_tf32_ts(d_tmem, a_lo, b_hi, idesc_ts, acc0);
+                umma_tf32_ts(d_tmem, a_hi, b_lo, idesc_ts, 1u);
+                umma_tf32_ts(d_tmem, a_hi, b_hi, idesc_ts, 1u);
+              }
             }
           }
           umma_commit(empty_bar(s));
@@ -227,8 +244,15 @@ tc_engine_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll 1
       for (int c = 0; c < BN / 32; c++) {
         float v[32];
-        if (nkb > 0) tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + (uint32_t)(c * 32), v);
-        else
+        if (nkb > 0) {
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * Cfg::kAccW + (uint32_t)(c * 32), v);
+          if constexpr (Cfg::kCat) {
+            float w[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * Cfg::kAccW + (uint32_t)(64 + c * 32), w);
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] += w[j];
+          }
+        } else
 #pragma unroll
           for (int j = 0; j < 32; j++) v[j] = 0.f;
         if (c == BN / 32 - 1) {            // all TMEM reads of this buffer are done: hand it back before the global stores

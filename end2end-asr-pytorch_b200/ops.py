@@ -1128,9 +1128,42 @@ def preprocess_targets(padded_target: torch.Tensor, tgt_max_len: int):
     return seq_in, seq_out, key_pad, non_pad
 
 
+class _PinnedStage:
+    """Small host tensors -> device without stalling the launch queue.  The reference's loader hands `input_lengths` over as a
+    pageable CPU tensor (utils/data_loader.py:213, trainer.py:63-68); a cudaMemcpyAsync from pageable memory synchronises the
+    stream before it starts, i.e. the host stops running ahead of the GPU twice per step (measured: 16.8 -> 19.8 ms per step at
+    cfg2).  Here the values go through a small ring of pinned buffers (an event per slot guards reuse) and an async copy."""
+
+    def __init__(self, slots=8):
+        self.bufs, self.events, self.i = [None] * slots, [None] * slots, 0
+
+    def to_device(self, t, device):
+        t = t.detach().to(torch.int32).contiguous().view(-1)
+        n, i = t.numel(), self.i
+        self.i = (i + 1) % len(self.bufs)
+        if self.bufs[i] is None or self.bufs[i].numel() < n:
+            self.bufs[i], self.events[i] = torch.empty(max(n, 256), dtype=torch.int32).pin_memory(), None
+        if self.events[i] is not None:
+            self.events[i].synchronize()          # the copy that used this slot last has run (it is several steps old)
+        buf = self.bufs[i][:n]
+        buf.copy_(t)
+        with torch.cuda.device(device):
+            out = buf.to(device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        self.events[i] = ev
+        return out
+
+
+_pinned_stage = _PinnedStage()
+
+
 def length_masks(lengths: torch.Tensor, B: int, T: int, device):
     """key_pad (uint8 [B,T], 1 = frame >= length) and non_pad (float [B,T]) from raw lengths (quirk Q1 preserved)."""
-    lens = lengths.to(device=device, dtype=torch.int32).contiguous()
+    if lengths.device.type == "cpu":
+        lens = _pinned_stage.to_device(lengths, device)
+    else:
+        lens = lengths.to(device=device, dtype=torch.int32).contiguous()
     key_pad = torch.empty((B, T), device=device, dtype=torch.uint8)
     non_pad = torch.empty((B, T), device=device, dtype=torch.float32)
     L.check(_lib().b200asr_length_masks(L.ptr(lens), L.ptr(key_pad), L.ptr(non_pad), B, T, _stream()), "length_masks")
