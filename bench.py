@@ -377,16 +377,22 @@ def run_b200(args, rank, local_rank, world):
     clocks = sampler.stop() if rank == 0 else None
     report = ops.profiler.report()
 
-    # ---- end-to-end: pinned host inputs copied in, loss read back, every step
+    # ---- end-to-end through the public API: every step's inputs are copied from pinned host memory (on the prefetcher's side
+    #      stream, one batch ahead, as a pin_memory DataLoader would) and the loss is read back by the host, every step
     loss_h = torch.zeros(1).pin_memory()
+    pf = b200asr.HostBatchPrefetcher(dev)
     for _ in range(min(2, args.warmup)):
-        dp.step(src_h.to(dev, non_blocking=True), lens, tgt_h.to(dev, non_blocking=True))
+        pf.submit(src_h, tgt_h)
+        s, t = pf.take()
+        dp.step(s, lens, t)
     barrier()
     t0 = time.perf_counter()
     e0.record()
-    for _ in range(args.steps):
-        s = src_h.to(dev, non_blocking=True)
-        t = tgt_h.to(dev, non_blocking=True)
+    pf.submit(src_h, tgt_h)                               # the first batch's copy is inside the timed region too
+    for i in range(args.steps):
+        s, t = pf.take()
+        if i + 1 < args.steps:
+            pf.submit(src_h, tgt_h)                       # next batch: copied under this step's kernels
         dp.step(s, lens, t)                               # lengths as the reference's loader hands them over: a CPU tensor
         loss_h.copy_(dp.global_loss().reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()         # the caller reads the loss every step
@@ -463,7 +469,10 @@ def run_b200(args, rank, local_rank, world):
                       "step": "zero_grad+fwd+CE+bwd+allreduce+adam", "parallelism": f"dp{world}",
                       "l2": "per-step working set (GBs of activations) >> 126 MB L2; no explicit flush"},
            "e2e": {"value": world * B / (ms_e2e / 1e3), "unit": "utt/s", "h2d_bytes_per_step": world * (src_h.numel() * 4 + tgt_h.numel() * 8),
-                   "d2h_bytes_per_step": world * 4, "ms_per_step": ms_e2e, "wall_ms_per_step": wall_ms},
+                   "d2h_bytes_per_step": world * 4, "ms_per_step": ms_e2e, "wall_ms_per_step": wall_ms,
+                   "how": "b200asr.HostBatchPrefetcher (pinned host batch copied on a side stream one step ahead, every step) -> "
+                          "DataParallelStep.step(src, CPU lengths, tgt) -> loss copied to pinned host memory and the stream "
+                          "synchronised, every step"},
            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "attention_roofline": attention, "kernels": groups[:24], "profiled_ms_per_step": ms_prof,
            "final_loss": final_loss}
     if world == 1 and not args.no_ref_gpu:

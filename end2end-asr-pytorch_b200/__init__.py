@@ -13,9 +13,9 @@ from .modules import (Decoder, DecoderLayer, Encoder, EncoderLayer, MultiHeadAtt
                       PositionwiseFeedForwardWithConv, ScaledDotProductAttention, Transformer, build_model)
 from .ops import config as precision, manual_seed
 from .optim import FlatParams, FusedAdam, NoamOpt
-from .parallel import DataParallelStep, shard_batch
+from .parallel import DataParallelStep, HostBatchPrefetcher, shard_batch
 
 __all__ = ["ASRConfig", "BASELINE_CONFIGS", "install", "uninstall", "calculate_loss", "calculate_metrics",
            "loss_and_stats", "Transformer", "Encoder", "Decoder", "EncoderLayer", "DecoderLayer", "MultiHeadAttention",
            "ScaledDotProductAttention", "PositionwiseFeedForwardWithConv", "PositionalEncoding", "build_model",
-           "precision", "manual_seed", "spectrogram_batch", "FlatParams", "FusedAdam", "NoamOpt", "DataParallelStep", "shard_batch"]
+           "precision", "manual_seed", "spectrogram_batch", "FlatParams", "FusedAdam", "NoamOpt", "DataParallelStep", "HostBatchPrefetcher", "shard_batch"]

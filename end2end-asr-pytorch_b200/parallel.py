@@ -28,6 +28,42 @@ def shard_batch(src, lengths, tgt, rank: int, world: int):
     return src[sl], lengths[sl], tgt[sl]
 
 
+class HostBatchPrefetcher:
+    """Pinned host batches -> device on a side stream, one batch ahead of the step that consumes them (what a DataLoader with
+    pin_memory does for the reference's `src.cuda()` / `tgt.cuda()`, trainer/asr/trainer.py:66-68, minus the stall: the copy of
+    batch i+1 runs under the kernels of batch i).
+
+        pf = HostBatchPrefetcher(device)
+        pf.submit(src_h, tgt_h)                 # before the loop
+        for ...:
+            src, tgt = pf.take()                # the compute stream waits for that copy only
+            pf.submit(next_src_h, next_tgt_h)   # starts copying now
+            dp.step(src, lengths, tgt)
+    """
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.pending = None
+
+    def submit(self, *host_tensors):
+        with torch.cuda.stream(self.stream):
+            dev = tuple(t.to(self.device, non_blocking=True) for t in host_tensors)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.pending = (dev, ev)
+
+    def take(self):
+        if self.pending is None:
+            raise RuntimeError("HostBatchPrefetcher.take() without a submitted batch")
+        (dev, ev), self.pending = self.pending, None
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        for t in dev:
+            t.record_stream(cur)                # allocated on the side stream, consumed on the compute stream
+        return dev
+
+
 class DataParallelStep:
     """zero_grad -> forward -> CE(sum) -> backward -> single all-reduce -> Adam(1/global_tokens)."""
 

@@ -505,3 +505,29 @@ def test_greedy_decode_matches_reference_greedy_search_fixture(b200):
     sub = enc[1:].cuda()
     ids_sub = dec.greedy_decode_cached(sub, steps=300, stop_at_eos=True, check_every=4)
     assert ids_sub.shape == (3, 300) and int((ids_sub >= 0).sum(1).max()) < 300
+
+
+@pytest.mark.gpu
+def test_host_batch_prefetcher_hands_over_each_batch_intact():
+    """HostBatchPrefetcher: pinned host batches copied on a side stream one step ahead; the consumer's stream waits for exactly
+    that copy (the kernels launched right after take() must see the data), batch after batch."""
+    import b200asr
+    dev = torch.device("cuda")
+    pf = b200asr.HostBatchPrefetcher(dev)
+    g = torch.Generator().manual_seed(0)
+    batches = [(torch.randn(4, 1, 161, 300, generator=g).pin_memory(), torch.randint(0, 100, (4, 20), generator=g).pin_memory()) for _ in range(4)]
+    busy = torch.randn(4096, 4096, device=dev)
+    pf.submit(*batches[0])
+    sums = []
+    for i in range(len(batches)):
+        src, tgt = pf.take()
+        if i + 1 < len(batches):
+            pf.submit(*batches[i + 1])
+        busy = busy @ busy * 1e-4                      # keep the compute stream busy while the next copy runs
+        sums.append((src.double().sum(), tgt.sum(), src, tgt))
+    torch.cuda.synchronize()
+    for (s_sum, t_sum, src, tgt), (hs, ht) in zip(sums, batches):
+        assert torch.equal(src.cpu(), hs) and torch.equal(tgt.cpu(), ht)
+        assert float(s_sum) == pytest.approx(float(hs.double().sum()), rel=1e-9) and int(t_sum) == int(ht.sum())
+    with pytest.raises(RuntimeError):
+        pf.take()

@@ -1,5 +1,5 @@
-for c in cfg1 cfg2 cfg3 cfg4 cfg5; do timeout 300 python tools/run_configs.py $c 2>&1 | tail -1; done > gpurun_out/r2_configs_default.jsonl
-timeout 300 python tools/run_configs.py cfg5 --mode bf16 2>&1 | tail -1 > gpurun_out/r2_configs_cfg5_bf16.jsonl
-timeout 300 python tools/run_configs.py cfg2 --mode tf32x3 2>&1 | tail -1 > gpurun_out/r2_configs_cfg2_tf32x3.jsonl
-cat gpurun_out/r2_configs_default.jsonl gpurun_out/r2_configs_cfg5_bf16.jsonl gpurun_out/r2_configs_cfg2_tf32x3.jsonl | cut -c1-260
-timeout 1200 python -m pytest tests -m gpu -q 2>&1 | grep -v Warning | tail -4
+NCU="ncu --clock-control none"
+B200ASR_ATTN=bf16x3 timeout 500 $NCU --set full --import-source on -k regex:sdpa_fused -s 36 -c 6 -f -o gpurun_out/prof_attn_fused_r2 python tools/one_step.py 3 > gpurun_out/ncu_attn_fused.log 2>&1
+tail -3 gpurun_out/ncu_attn_fused.log
+B200ASR_ATTN=bf16x3 timeout 300 python bench.py --no-cpu --no-ref-gpu --steps 10 2>&1 | tail -1 > gpurun_out/r2_bench_fused_attn.json
+python tools/show_bench.py gpurun_out/r2_bench_fused_attn.json 2>/dev/null | sed -n 1,14p
