@@ -363,6 +363,21 @@ def run_b200(args, rank, local_rank, world):
     barrier()
     launches = (lib.b200asr_launch_count() - launches0) / args.steps
     ms_dev = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    # ---- forward + loss + backward alone (BASELINE.json's metric names fwd+bwd; `value` above is the whole step incl. the
+    #      all-reduce and Adam): single GPU only, the weights do not change so the operand cache stays valid
+    fwd_bwd = None
+    if world == 1:
+        fb_steps = min(args.steps, 10)
+        dp.forward_backward(src_d, lens_d, tgt_d)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(fb_steps):
+            dp.forward_backward(src_d, lens_d, tgt_d)
+        e1.record()
+        torch.cuda.synchronize()
+        fb_ms = e0.elapsed_time(e1) / fb_steps
+        fwd_bwd = {"ms_per_step": fb_ms, "value": B / (fb_ms / 1e3), "unit": "utt/s", "steps": fb_steps,
+                   "note": "zero_grad + forward + label-smoothed CE + backward; no all-reduce, no optimizer step"}
     # ---- same steps again with a CUDA-event pair around every C-ABI call (per-kernel-group durations for the roofline);
     #      kept out of `value` because the extra host work per call can starve a ~40 ms step
     prof_steps = min(args.steps, 5)
@@ -475,6 +490,8 @@ def run_b200(args, rank, local_rank, world):
                           "synchronised, every step"},
            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "attention_roofline": attention, "kernels": groups[:24], "profiled_ms_per_step": ms_prof,
            "final_loss": final_loss}
+    if fwd_bwd is not None:
+        out["fwd_bwd_only"] = fwd_bwd
     if world == 1 and not args.no_ref_gpu:
         try:
             out["reference_gpu"] = gpu_reference_throughput(dev, B)
