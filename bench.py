@@ -94,8 +94,8 @@ def algorithmic_flops(name, a):
     if name == "conv3x3_fwd":
         B, T, F, Ci, Co = a[5], a[6], a[7], a[8], a[9]
         return 2.0 * 9 * B * T * F * Ci * Co
-    if name == "conv3x3_fwd_pool":                               # x, w, bias, y, pooled, ws, then the dims
-        B, T, F, Ci, Co = a[6], a[7], a[8], a[9], a[10]
+    if name == "conv3x3_fwd_pool":                               # x, w, bias, y, pooled, pool_idx, ws, then the dims
+        B, T, F, Ci, Co = a[7], a[8], a[9], a[10], a[11]
         return 2.0 * 9 * B * T * F * Ci * Co
     if name in ("conv3x3_bwd_data", "conv3x3_bwd_weight"):       # one more pointer (the bf16 pair output / input) before the dims
         B, T, F, Ci, Co = a[6], a[7], a[8], a[9], a[10]

@@ -58,7 +58,9 @@ SIGNATURES = {
     "b200asr_conv3x3_c1_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200asr_conv3x3_c1_bwd_weight": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "b200asr_conv3x3_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "b200asr_conv3x3_fwd_pool": (_i, [_vp] * 6 + [_i] * 7 + [_vp]),
+    "b200asr_conv3x3_fwd_pool": (_i, [_vp] * 7 + [_i] * 7 + [_vp]),
+    "b200asr_maxpool2x2_fwd_idx": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "b200asr_maxpool2x2_bwd_idx": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "b200asr_conv3x3_bwd_data": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "b200asr_conv3x3_bwd_weight": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "b200asr_conv3x3_ws_bytes": (_sz, [_i, _i]),

@@ -404,7 +404,19 @@ __global__ void __launch_bounds__(256) conv3x3_wgrad_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ pooling
-__global__ void maxpool2x2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int T, int F, int C) {
+// which element of the 2x2 window carries the gradient: ATen scans the window freq-major -- (f, t), (f, t+1), (f+1, t),
+// (f+1, t+1) = codes 0..3 -- and keeps the FIRST maximum; bit 2 is set when that maximum is not positive (a ReLU in front of
+// the pooling then passes no gradient at all).  One byte per pooled element, written by the forward, read by the backward
+// instead of the full-resolution activation.
+__device__ __forceinline__ uint32_t pool_code(float a0, float a1, float a2, float a3) {
+  int best = 0; float m = a0;
+  if (a1 > m) { m = a1; best = 1; }
+  if (a2 > m) { m = a2; best = 2; }
+  if (a3 > m) { m = a3; best = 3; }
+  return (uint32_t)best | (m > 0.f ? 0u : 4u);
+}
+
+__global__ void maxpool2x2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ idx, int B, int T, int F, int C) {
   const int T2 = T / 2, F2 = F / 2, C4 = C / 4;
   long long n = (long long)B * T2 * F2 * C4;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -424,7 +436,11 @@ __global__ void maxpool2x2_fwd_kernel(const float* __restrict__ x, float* __rest
   o.y = fmaxf(fmaxf(a.y, bq.y), fmaxf(cq.y, d.y));
   o.z = fmaxf(fmaxf(a.z, bq.z), fmaxf(cq.z, d.z));
   o.w = fmaxf(fmaxf(a.w, bq.w), fmaxf(cq.w, d.w));
-  *reinterpret_cast<float4*>(y + (((size_t)b * T2 + t2) * F2 + f2) * C + c) = o;
+  const size_t po = (((size_t)b * T2 + t2) * F2 + f2) * C + c;
+  *reinterpret_cast<float4*>(y + po) = o;
+  if (idx)      // scan order: (f, t) = a, (f, t+1) = cq, (f+1, t) = bq, (f+1, t+1) = d
+    *reinterpret_cast<uint32_t*>(idx + po) = pool_code(a.x, cq.x, bq.x, d.x) | (pool_code(a.y, cq.y, bq.y, d.y) << 8) |
+                                             (pool_code(a.z, cq.z, bq.z, d.z) << 16) | (pool_code(a.w, cq.w, bq.w, d.w) << 24);
 }
 
 // one thread = one 2x2 window x 4 channels; writes all four dx positions (and zeroes are written for the odd tails
@@ -479,6 +495,41 @@ __global__ void maxpool2x2_bwd_kernel(const float* __restrict__ dy, const float*
   route(v[0].w, v[1].w, v[2].w, v[3].w, g.w, out[0].w, out[1].w, out[2].w, out[3].w);
 #pragma unroll
   for (int k = 0; k < 4; k++) *reinterpret_cast<float4*>(dx + base + offs[k]) = out[k];
+  if (dx16) {
+    const size_t lo_off = (size_t)B * T * F * C;
+#pragma unroll
+    for (int k = 0; k < 4; k++) store_pairs4(dx16, lo_off, base + offs[k], out[k]);
+  }
+}
+// the same routing from the forward's index bytes: reads dy and one byte per pooled element instead of the activation
+__global__ void maxpool2x2_bwd_idx_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ idx, float* __restrict__ dx,
+                                          uint16_t* __restrict__ dx16, int B, int T, int F, int C, int relu_mask) {
+  const int T2 = T / 2, F2 = F / 2, C4 = C / 4;
+  long long n = (long long)B * T2 * F2 * C4;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = (int)(i % C4) * 4;
+  long long r = i / C4;
+  int f2 = (int)(r % F2); r /= F2;
+  int t2 = (int)(r % T2);
+  int b = (int)(r / T2);
+  const size_t po = (((size_t)b * T2 + t2) * F2 + f2) * C + c;
+  const float4 g = *reinterpret_cast<const float4*>(dy + po);
+  const uint32_t codes = *reinterpret_cast<const uint32_t*>(idx + po);
+  const size_t base = (((size_t)b * T + 2 * t2) * F + 2 * f2) * C + c;
+  const size_t o_f = C, o_t = (size_t)F * C;
+  const size_t offs[4] = {0, o_t, o_f, o_f + o_t};         // scan order, as in maxpool2x2_bwd_kernel
+  const uint32_t dead = relu_mask ? 4u : 8u;                // bit 2 = "maximum not positive" counts only behind a ReLU
+  const uint32_t c0 = codes & 7u, c1 = (codes >> 8) & 7u, c2 = (codes >> 16) & 7u, c3 = (codes >> 24) & 7u;
+  float4 out[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    out[k].x = (!(c0 & dead) && (c0 & 3u) == (uint32_t)k) ? g.x : 0.f;
+    out[k].y = (!(c1 & dead) && (c1 & 3u) == (uint32_t)k) ? g.y : 0.f;
+    out[k].z = (!(c2 & dead) && (c2 & 3u) == (uint32_t)k) ? g.z : 0.f;
+    out[k].w = (!(c3 & dead) && (c3 & 3u) == (uint32_t)k) ? g.w : 0.f;
+    *reinterpret_cast<float4*>(dx + base + offs[k]) = out[k];
+  }
   if (dx16) {
     const size_t lo_off = (size_t)B * T * F * C;
 #pragma unroll
@@ -638,8 +689,8 @@ int b200asr_conv3x3_fwd(const float* x, const float* w, const float* bias, float
   return conv3x3_tc(x, (const float*)ws, bias, nullptr, y, B, T, F, Ci, Co, relu, precision, st);
 }
 
-int b200asr_conv3x3_fwd_pool(const float* x, const float* w, const float* bias, float* y, float* pooled, void* ws, int B, int T, int F,
-                             int Ci, int Co, int relu, int precision, b200asr_stream_t stream) {
+int b200asr_conv3x3_fwd_pool(const float* x, const float* w, const float* bias, float* y, float* pooled, unsigned char* pool_idx, void* ws,
+                             int B, int T, int F, int Ci, int Co, int relu, int precision, b200asr_stream_t stream) {
   B200_REQUIRE(x && w && y && pooled && ws, B200ASR_BAD_ARG, "conv3x3_fwd_pool: null pointer");
   if (conv_is_bf16(precision)) {       // the pooling rides in the convolution's epilogue (tc_conv_halo.cu)
     int rc = conv_shape_ok("conv3x3_fwd_pool", Ci, Co);
@@ -649,10 +700,10 @@ int b200asr_conv3x3_fwd_pool(const float* x, const float* w, const float* bias, 
     cudaStream_t st = (cudaStream_t)stream;
     note_launch(1);
     conv_repack_k_bf16_kernel<<<ceil_div(9 * Ci * Co, 256), 256, 0, st>>>(w, (uint16_t*)ws, Ci, Co, 0, precision == B200ASR_PREC_BF16X3 ? 2 : 1);
-    return conv3x3_tc_halo(x, ws, bias, nullptr, y, B, T, F, Ci, Co, relu, precision, st, nullptr, pooled);
+    return conv3x3_tc_halo(x, ws, bias, nullptr, y, B, T, F, Ci, Co, relu, precision, st, nullptr, pooled, pool_idx);
   }
   if (int rc = b200asr_conv3x3_fwd(x, w, bias, y, ws, B, T, F, Ci, Co, relu, precision, stream)) return rc;
-  return b200asr_maxpool2x2_fwd(y, pooled, B, T, F, Co, stream);
+  return pool_idx ? b200asr_maxpool2x2_fwd_idx(y, pooled, pool_idx, B, T, F, Co, stream) : b200asr_maxpool2x2_fwd(y, pooled, B, T, F, Co, stream);
 }
 
 int b200asr_conv3x3_bwd_data(const float* dy, const float* w, const float* relu_out, float* dx, void* dx16, void* ws, int B, int T,
@@ -704,8 +755,30 @@ int b200asr_maxpool2x2_fwd(const float* x, float* y, int B, int T, int F, int C,
   B200_REQUIRE(x && y && C % 4 == 0, B200ASR_BAD_ARG, "maxpool2x2_fwd: bad arguments");
   long long n = (long long)B * (T / 2) * (F / 2) * (C / 4);
   if (n <= 0) return B200ASR_OK;
-  maxpool2x2_fwd_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, B, T, F, C);
+  maxpool2x2_fwd_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, nullptr, B, T, F, C);
   return check_launch("maxpool2x2_fwd");
+}
+
+int b200asr_maxpool2x2_fwd_idx(const float* x, float* y, unsigned char* idx, int B, int T, int F, int C, b200asr_stream_t stream) {
+  B200_REQUIRE(x && y && idx && C % 4 == 0, B200ASR_BAD_ARG, "maxpool2x2_fwd_idx: bad arguments");
+  long long n = (long long)B * (T / 2) * (F / 2) * (C / 4);
+  if (n <= 0) return B200ASR_OK;
+  maxpool2x2_fwd_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, idx, B, T, F, C);
+  return check_launch("maxpool2x2_fwd_idx");
+}
+
+int b200asr_maxpool2x2_bwd_idx(const float* dy, const unsigned char* idx, float* dx, void* dx16, int B, int T, int F, int C,
+                               int relu_mask, b200asr_stream_t stream) {
+  B200_REQUIRE(dy && idx && dx && C % 4 == 0, B200ASR_BAD_ARG, "maxpool2x2_bwd_idx: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long n = (long long)B * (T / 2) * (F / 2) * (C / 4);
+  if (n > 0) maxpool2x2_bwd_idx_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, st>>>(dy, idx, dx, (uint16_t*)dx16, B, T, F, C, relu_mask);
+  if ((T & 1) || (F & 1)) {
+    long long tot = ((F & 1) ? (long long)B * (T / 2) * 2 * (C / 4) : 0) + ((T & 1) ? (long long)B * F * (C / 4) : 0);
+    maxpool2x2_bwd_tail_kernel<<<(unsigned)ceil_div_ll(tot, 256), 256, 0, st>>>(dx, (uint16_t*)dx16, B, T, F, C);
+    note_launch(1);
+  }
+  return check_launch("maxpool2x2_bwd_idx");
 }
 
 int b200asr_maxpool2x2_bwd(const float* dy, const float* x, float* dx, void* dx16, int B, int T, int F, int C, int relu_mask,

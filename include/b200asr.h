@@ -197,9 +197,12 @@ int b200asr_conv3x3_fwd(const float* x, const float* w, const float* bias, float
                         int F, int Ci, int Co, int relu, int precision, b200asr_stream_t stream);
 /* The same convolution followed by MaxPool2d(2, stride 2) (models/asr/transformer.py:44-52: conv, ReLU, pool): y as above AND
  * pooled [B,T/2,F/2,Co] (floor mode).  In the kind::f16 modes the 2x2 maximum is taken in the convolution's epilogue (four
- * lanes of a warp hold a window), so the activation is not read back; other precisions run the two kernels. */
-int b200asr_conv3x3_fwd_pool(const float* x, const float* w, const float* bias, float* y, float* pooled, void* ws, int B,
-                             int T, int F, int Ci, int Co, int relu, int precision, b200asr_stream_t stream);
+ * lanes of a warp hold a window), so the activation is not read back; other precisions run the two kernels.
+ * pool_idx (optional) [B,T/2,F/2,Co] bytes: which element of each window holds the maximum (ATen's scan order, first maximum;
+ * bit 2 set when the maximum is not positive) -- what b200asr_maxpool2x2_bwd_idx routes the gradient by. */
+int b200asr_conv3x3_fwd_pool(const float* x, const float* w, const float* bias, float* y, float* pooled,
+                             unsigned char* pool_idx, void* ws, int B, int T, int F, int Ci, int Co, int relu, int precision,
+                             b200asr_stream_t stream);
 /* dx[B,T,F,Ci] = conv_transpose(dy) .* (relu_out > 0 if relu_out != NULL).
  * dx16 (optional, precisions 6 / 2 only): the same gradient additionally as bf16 hi | lo "pairs" [2][B,T,F,Ci] (hi = bf16(v),
  * lo = bf16(v - hi)) -- what b200asr_conv3x3_bwd_weight of the layer below takes as dy16. */
@@ -213,10 +216,17 @@ int b200asr_conv3x3_bwd_weight(const float* dy, const void* dy16, const float* x
 size_t b200asr_conv3x3_ws_bytes(int Ci, int Co);
 /* MaxPool2d(2, stride 2), floor mode: [B,T,F,C] -> [B,T/2,F/2,C] */
 int b200asr_maxpool2x2_fwd(const float* x, float* y, int B, int T, int F, int C, b200asr_stream_t stream);
+/* the same pooling, additionally writing the index bytes described at b200asr_conv3x3_fwd_pool */
+int b200asr_maxpool2x2_fwd_idx(const float* x, float* y, unsigned char* idx, int B, int T, int F, int C,
+                               b200asr_stream_t stream);
 /* dx[B,T,F,C] = route dy to the first maximum of each window (scan order freq-major, as ATen), then
  * .* (x > 0) when relu_mask != 0 (x is the post-ReLU pool input). */
 int b200asr_maxpool2x2_bwd(const float* dy, const float* x, float* dx, void* dx16 /* optional bf16 pairs [2][B,T,F,C] */, int B, int T, int F, int C,
                            int relu_mask, b200asr_stream_t stream);
+/* b200asr_maxpool2x2_bwd from the forward's index bytes instead of the activation (reads 1 byte instead of 16 per pooled
+ * element): identical result.  relu_mask != 0: a window whose maximum is not positive passes no gradient. */
+int b200asr_maxpool2x2_bwd_idx(const float* dy, const unsigned char* idx, float* dx, void* dx16, int B, int T, int F, int C,
+                               int relu_mask, b200asr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * emb_cnn front end (models/asr/transformer.py:33-40): generic strided NCHW convolution, BatchNorm2d

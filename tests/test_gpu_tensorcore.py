@@ -413,5 +413,19 @@ def test_conv3x3_with_fused_max_pool(L, B, T, F_, Ci, Co, prec):
     L.check(lib.b200asr_conv3x3_fwd(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y0), L.ptr(ws), B, T, F_, Ci, Co, 1, prec, st), "conv")
     L.check(lib.b200asr_maxpool2x2_fwd(L.ptr(y0), L.ptr(p0), B, T, F_, Co, st), "pool")
     y1, p1 = torch.full_like(y0, float("nan")), torch.full_like(p0, float("nan"))
-    L.check(lib.b200asr_conv3x3_fwd_pool(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y1), L.ptr(p1), L.ptr(ws), B, T, F_, Ci, Co, 1, prec, st), "conv+pool")
+    i1 = torch.full(p0.shape, 255, device="cuda", dtype=torch.uint8)
+    L.check(lib.b200asr_conv3x3_fwd_pool(L.ptr(x), L.ptr(w), L.ptr(b), L.ptr(y1), L.ptr(p1), L.ptr(i1), L.ptr(ws), B, T, F_, Ci, Co, 1, prec, st), "conv+pool")
     assert torch.equal(y0, y1) and torch.equal(p0, p1)
+    # the index bytes: the stand-alone pooling kernel writes the same ones, and the backward that reads them routes every
+    # gradient exactly as the backward that re-reads the activation (post-ReLU zeros make exact ties: first maximum wins)
+    i0 = torch.full_like(i1, 255)
+    p0b = torch.full_like(p0, float("nan"))
+    L.check(lib.b200asr_maxpool2x2_fwd_idx(L.ptr(y0), L.ptr(p0b), L.ptr(i0), B, T, F_, Co, st), "pool idx")
+    assert torch.equal(p0b, p0) and torch.equal(i0, i1) and int(i1.max()) <= 7
+    g = torch.randn(p0.shape, device="cuda")
+    dx0, dx1 = torch.full_like(y0, float("nan")), torch.full_like(y0, float("nan"))
+    pr0 = torch.full((2,) + tuple(y0.shape), float("nan"), device="cuda", dtype=torch.bfloat16)
+    pr1 = torch.full_like(pr0, float("nan"))
+    L.check(lib.b200asr_maxpool2x2_bwd(L.ptr(g), L.ptr(y0), L.ptr(dx0), L.ptr(pr0), B, T, F_, Co, 1, st), "pool bwd")
+    L.check(lib.b200asr_maxpool2x2_bwd_idx(L.ptr(g), L.ptr(i1), L.ptr(dx1), L.ptr(pr1), B, T, F_, Co, 1, st), "pool bwd idx")
+    assert torch.equal(dx0, dx1) and torch.equal(pr0.view(torch.int16), pr1.view(torch.int16))
