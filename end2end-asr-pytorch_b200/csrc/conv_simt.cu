@@ -692,7 +692,10 @@ int b200asr_conv3x3_fwd(const float* x, const float* w, const float* bias, float
 int b200asr_conv3x3_fwd_pool(const float* x, const float* w, const float* bias, float* y, float* pooled, unsigned char* pool_idx, void* ws,
                              int B, int T, int F, int Ci, int Co, int relu, int precision, b200asr_stream_t stream) {
   B200_REQUIRE(x && w && y && pooled && ws, B200ASR_BAD_ARG, "conv3x3_fwd_pool: null pointer");
-  if (conv_is_bf16(precision)) {       // the pooling rides in the convolution's epilogue (tc_conv_halo.cu)
+  // the pooling rides in the convolution's epilogue (tc_conv_halo.cu) -- unless the arg-max bytes are wanted as well: computing
+  // them there was measured to lengthen the epilogue (the critical path of the Cout = 64 kernel) by more than the index-based
+  // pooling backward saves, so that request runs the stand-alone pooling kernel
+  if (conv_is_bf16(precision) && !pool_idx) {
     int rc = conv_shape_ok("conv3x3_fwd_pool", Ci, Co);
     if (rc) return rc;
     B200_REQUIRE(Ci % 32 == 0 && (Co == 64 || Co == 128), B200ASR_BAD_SHAPE, "conv3x3_fwd_pool (bf16): needs Ci %% 32 == 0 and Co in {64,128}");
@@ -700,7 +703,7 @@ int b200asr_conv3x3_fwd_pool(const float* x, const float* w, const float* bias, 
     cudaStream_t st = (cudaStream_t)stream;
     note_launch(1);
     conv_repack_k_bf16_kernel<<<ceil_div(9 * Ci * Co, 256), 256, 0, st>>>(w, (uint16_t*)ws, Ci, Co, 0, precision == B200ASR_PREC_BF16X3 ? 2 : 1);
-    return conv3x3_tc_halo(x, ws, bias, nullptr, y, B, T, F, Ci, Co, relu, precision, st, nullptr, pooled, pool_idx);
+    return conv3x3_tc_halo(x, ws, bias, nullptr, y, B, T, F, Ci, Co, relu, precision, st, nullptr, pooled);
   }
   if (int rc = b200asr_conv3x3_fwd(x, w, bias, y, ws, B, T, F, Ci, Co, relu, precision, stream)) return rc;
   return pool_idx ? b200asr_maxpool2x2_fwd_idx(y, pooled, pool_idx, B, T, F, Co, stream) : b200asr_maxpool2x2_fwd(y, pooled, B, T, F, Co, stream);

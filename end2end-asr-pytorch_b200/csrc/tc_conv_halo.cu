@@ -38,7 +38,6 @@ constexpr int HALO_GROUPS = HALO_GROUPS_N, HALO_SPLIT = 128 * HALO_GROUPS, HALO_
 struct HaloP {
   uint16_t* out16;       // optional bf16 hi | lo pairs of the output, [2][pixels][Cout] (lo at + npix * Cout), or nullptr
   float* pool;           // optional MaxPool2d(2, 2) of the output, [B, T/2, F/2, Cout] (floor mode), or nullptr
-  uint8_t* pool_idx;     // optional, with pool: which window element is the maximum (conv_simt.cu pool_code), one byte each
   float* out;
   const float* bias;
   const float* mask;
@@ -283,31 +282,14 @@ tc_conv3x3_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_co
             if (p.pool) {
               // fused MaxPool2d(2, 2): a warp holds 4 time rows x 8 freq bins of the tile (lane = 8 * row + bin, tile origin
               // even in both), so the 2 x 2 window of lane l is {l, l ^ 1, l ^ 8, l ^ 9}; the even / even lane stores it
-              float mine[4] = {o[0], o[1], o[2], o[3]};
 #pragma unroll
               for (int e = 0; e < 4; e++) {
                 o[e] = fmaxf(o[e], __shfl_xor_sync(0xffffffffu, o[e], 1));
                 o[e] = fmaxf(o[e], __shfl_xor_sync(0xffffffffu, o[e], 8));
               }
-              // which lanes of the window hold the maximum: bit (4 e + code) with code = 2 * (freq parity) + (time parity),
-              // ATen's scan order; the first set bit of each nibble is the element the gradient goes to
-              const int code = ((lane & 1) << 1) | ((lane >> 3) & 1);
-              uint32_t hit = 0;
-#pragma unroll
-              for (int e = 0; e < 4; e++) hit |= (mine[e] == o[e] ? 1u : 0u) << (4 * e + code);
-              hit |= __shfl_xor_sync(0xffffffffu, hit, 1);
-              hit |= __shfl_xor_sync(0xffffffffu, hit, 8);
-              if ((lane & 9) == 0 && tt + 1 < p.T && ff + 1 < p.F) {
-                const size_t po = (((size_t)b * (p.T >> 1) + (tt >> 1)) * (p.F >> 1) + (ff >> 1)) * p.Cout + col;
-                *reinterpret_cast<float4*>(p.pool + po) = make_float4(o[0], o[1], o[2], o[3]);
-                if (p.pool_idx) {
-                  uint32_t codes = 0;
-#pragma unroll
-                  for (int e = 0; e < 4; e++)
-                    codes |= ((uint32_t)(__ffs((hit >> (4 * e)) & 15u) - 1) | (o[e] > 0.f ? 0u : 4u)) << (8 * e);
-                  *reinterpret_cast<uint32_t*>(p.pool_idx + po) = codes;
-                }
-              }
+              if ((lane & 9) == 0 && tt + 1 < p.T && ff + 1 < p.F)
+                *reinterpret_cast<float4*>(p.pool + ((((size_t)b * (p.T >> 1) + (tt >> 1)) * (p.F >> 1) + (ff >> 1)) * p.Cout + col)) =
+                    make_float4(o[0], o[1], o[2], o[3]);
             }
           }
         }
@@ -462,7 +444,7 @@ static int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const HaloP
 // wk: mode 3: [2][9][Cout][Cin] fp32 pre-split K-major weights (hi | lo), as for conv3x3_tc with precision 3;
 //     mode 6 / 2: [2 or 1][9][Cout][Cin] bf16 (conv_repack_k_bf16_kernel)
 int conv3x3_tc_halo(const float* in, const void* wk, const float* bias, const float* mask, float* out, int B, int T, int F,
-                    int Cin, int Cout, int relu, int mode, cudaStream_t st, void* out16, float* pool, unsigned char* pool_idx) {
+                    int Cin, int Cout, int relu, int mode, cudaStream_t st, void* out16, float* pool) {
   using namespace tc;
   B200_REQUIRE(mode == 3 || mode == 6 || mode == 2, B200ASR_BAD_ARG, "conv3x3_tc_halo: mode must be 3 (3xTF32), 6 (bf16x3) or 2 (bf16)");
   B200_REQUIRE(Cin % 32 == 0 && (Cout == 64 || Cout == 128), B200ASR_BAD_SHAPE,
@@ -484,7 +466,7 @@ int conv3x3_tc_halo(const float* in, const void* wk, const float* bias, const fl
     int rc = mode == 3 ? make_tensor_map_f32(&mb, wk, 2, dims, strides, box, false, false) : make_tensor_map_bf16(&mb, wk, 2, dims, strides, box);
     if (rc) return rc;
   }
-  HaloP p{(uint16_t*)out16, pool, pool_idx, out, bias, mask, relu, B, T, F, Cin, Cout, ceil_div(F, HF), ceil_div(T, HT), Cin / 32};
+  HaloP p{(uint16_t*)out16, pool, out, bias, mask, relu, B, T, F, Cin, Cout, ceil_div(F, HF), ceil_div(T, HT), Cin / 32};
   if (mode == 3) return Cout == 64 ? launch_halo<64, 3>(ma, mb, p, st) : launch_halo<128, 3>(ma, mb, p, st);
   if (mode == 6) return Cout == 64 ? launch_halo<64, 6>(ma, mb, p, st) : launch_halo<128, 6>(ma, mb, p, st);
   return Cout == 64 ? launch_halo<64, 2>(ma, mb, p, st) : launch_halo<128, 2>(ma, mb, p, st);

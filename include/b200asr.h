@@ -199,7 +199,9 @@ int b200asr_conv3x3_fwd(const float* x, const float* w, const float* bias, float
  * pooled [B,T/2,F/2,Co] (floor mode).  In the kind::f16 modes the 2x2 maximum is taken in the convolution's epilogue (four
  * lanes of a warp hold a window), so the activation is not read back; other precisions run the two kernels.
  * pool_idx (optional) [B,T/2,F/2,Co] bytes: which element of each window holds the maximum (ATen's scan order, first maximum;
- * bit 2 set when the maximum is not positive) -- what b200asr_maxpool2x2_bwd_idx routes the gradient by. */
+ * bit 2 set when the maximum is not positive) -- what b200asr_maxpool2x2_bwd_idx routes the gradient by; asking for it runs
+ * the stand-alone pooling kernel after the convolution (computing the bytes in the epilogue was measured to cost more than the
+ * index-based backward saves). */
 int b200asr_conv3x3_fwd_pool(const float* x, const float* w, const float* bias, float* y, float* pooled,
                              unsigned char* pool_idx, void* ws, int B, int T, int F, int Ci, int Co, int relu, int precision,
                              b200asr_stream_t stream);
