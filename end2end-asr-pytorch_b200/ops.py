@@ -178,31 +178,31 @@ class WeightOperandCache:
 
     A matrix is registered the first time split_weight() is asked for it (that request is served by the per-weight kernel);
     from the next refresh on its operands are views of one bf16 buffer.  Freshness: the Adam kernel writes through raw
-    pointers, so FusedAdam.step() calls refresh() itself; any other in-place change of a weight (load_state_dict, manual
-    edits) bumps that tensor's autograd version counter, which get() compares with the one it last saw."""
+    pointers, so FusedAdam.step() calls refresh() itself; any other in-place change of a weight (torch optimizers,
+    load_state_dict, manual edits) moves that tensor's autograd version counter away from the one recorded at the last
+    conversion, and get() then converts again (once: a refresh records the versions of all registered weights)."""
 
     def __init__(self, flat):
         self.flat = flat                      # optim.FlatParams
         self.entries, self.pending = {}, {}   # key -> (src_off, N, K, terms, dst_off, dstT_off); key -> the weight tensor
         self.buf = self.desc = self.prefix = None
         self.tiles = 0
-        self.gen = 0                          # number of refreshes so far
-        self.seen = {}                        # key -> [tensor version last seen, refresh generation at that time]
+        self.tensors = {}                     # key -> the weight (a view of the flat buffer) as last seen
+        self.converted_at = {}                # key -> its version counter when its operands were last converted
 
     def owns(self, w2):
         f = self.flat.flat
         return w2.is_contiguous() and f.data_ptr() <= w2.data_ptr() and w2.data_ptr() + w2.numel() * 4 <= f.data_ptr() + f.numel() * 4
 
     def refresh(self):
-        fresh = None
         if self.pending:
             off = 0 if self.buf is None else self.buf.numel()
-            fresh = self.pending
-            for key in fresh:
+            for key, w2 in self.pending.items():
                 ptr, N, K, terms = key
                 n8 = (N + 7) // 8 * 8
                 self.entries[key] = ((ptr - self.flat.flat.data_ptr()) // 4, N, K, terms, off, off + terms * N * K)
                 off += (terms * N * K + terms * K * n8 + 63) // 64 * 64
+                self.tensors[key] = w2
             self.pending = {}
             dev = self.flat.flat.device
             self.buf = torch.empty(off, device=dev, dtype=torch.bfloat16)
@@ -217,10 +217,8 @@ class WeightOperandCache:
         if self.entries:
             L.check(_lib().b200asr_split_bf16_batched(L.ptr(self.flat.flat), L.ptr(self.buf), L.ptr(self.desc), L.ptr(self.prefix),
                                                       len(self.entries), self.tiles, _stream()), "split_bf16_batched")
-        self.gen += 1
-        if fresh:       # converted just now from the tensors' current contents: the first get() must not convert again
-            for key, w2 in fresh.items():
-                self.seen[key] = [w2._version, self.gen]
+            for key, w2 in self.tensors.items():
+                self.converted_at[key] = w2._version
 
     def after_optimizer_step(self):
         if self.entries or self.pending:
@@ -234,11 +232,9 @@ class WeightOperandCache:
         if e is None:
             self.pending.setdefault(key, w2)
             return None
-        seen = self.seen.get(key)
-        if seen is None or seen[0] != w2._version:
-            if seen is None or seen[1] == self.gen:      # changed in place since the last conversion (not by our optimizer)
-                self.refresh()
-            self.seen[key] = [w2._version, self.gen]
+        self.tensors[key] = w2
+        if self.converted_at.get(key) != w2._version:       # changed in place since the last conversion (not by our optimizer)
+            self.refresh()
         _, _, _, _, do, dto = e
         n8 = (N + 7) // 8 * 8
         return WSplit(self.buf[do:do + terms * N * K].view(terms, N, K), self.buf[dto:dto + terms * K * n8].view(terms, K, n8))

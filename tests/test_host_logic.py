@@ -157,3 +157,44 @@ def test_bench_flop_accounting_reads_integer_dimensions_of_the_abi():
                 return [3] * len(idx) if isinstance(i, slice) else 3
 
         assert bench.algorithmic_flops(name, Probe(range(len(argtypes)))) > 0
+
+
+def test_weight_operand_cache_converts_once_per_change(monkeypatch):
+    """ops.WeightOperandCache bookkeeping with the conversion kernel stubbed out (no GPU): a weight is registered on first use,
+    converted by the refresh of the optimizer step, NOT converted again by the first get() after that (the regression: every
+    weight's first get() re-converted all of them -- 46 launches in the step after registration), and converted again when
+    the tensor changes in place behind the optimizer's back."""
+    ops = importlib.import_module(b200asr.__name__ + ".ops")
+    L = importlib.import_module(b200asr.__name__ + "._lib")
+    calls = []
+
+    class FakeLib:
+        def b200asr_split_bf16_batched(self, *a):
+            calls.append(a[4])          # number of matrices in the batch
+            return 0
+
+    monkeypatch.setattr(ops, "_lib", lambda: FakeLib())
+    monkeypatch.setattr(ops, "_stream", lambda: 0)
+
+    class Flat:
+        flat = torch.zeros(4096)
+    cache = ops.WeightOperandCache(Flat())
+    w1, w2 = Flat.flat[:512].view(16, 32), Flat.flat[1024:2048].view(32, 32)
+    assert cache.owns(w1) and not cache.owns(torch.zeros(16, 32))
+    assert cache.get(w1, L.PREC_BF16X3) is None and cache.get(w2, L.PREC_BF16X3) is None      # registered, not converted yet
+    assert calls == []
+    cache.after_optimizer_step()
+    assert calls == [2]                                                                      # one launch for both
+    s1 = cache.get(w1, L.PREC_BF16X3)
+    s2 = cache.get(w2, L.PREC_BF16X3)
+    assert s1 is not None and s2 is not None and calls == [2]                                # fresh: no second conversion
+    assert tuple(s1.fwd.shape) == (2, 16, 32) and tuple(s2.bwd.shape) == (2, 32, 32)
+    cache.after_optimizer_step()
+    cache.get(w1, L.PREC_BF16X3)
+    assert calls == [2, 2]                                                                   # the optimizer's refresh only
+    w1.add_(1.0)                                                                             # in-place edit: version counter moves
+    cache.get(w1, L.PREC_BF16X3)
+    assert calls == [2, 2, 2]
+    cache.get(w1, L.PREC_BF16X3)
+    cache.get(w2, L.PREC_BF16X3)                 # w2 shares the buffer's version counter: its view changed version too, but
+    assert calls == [2, 2, 2]                    # the refresh that followed the edit already covers it
